@@ -1,0 +1,144 @@
+"""Seeded synthetic weights / objects / frames for the GATsSPG hot path.
+
+Everything here is numpy ``RandomState`` based so that the same seed gives the
+same bytes in this container, on the GPU box and inside the golden-fixture
+generator (``tests/golden/make_golden.py``) -- no dependence on torch's RNG or
+on the reference tree.
+
+Recipe follows SURVEY.md section 8(d) / section 7 step 0:
+  * weights: reference-shaped state dict (key names as produced by
+    ``GATsSuperGlue`` -- reference ``GATs_SuperGlue.py:143-177`` and
+    ``GATs.py:25-28``), optionally *damped* (``mlp[-1].weight *= 0.02``,
+    ``final_proj.weight = I + 0.02 W0``) so that planted correspondences
+    survive the 0.2 threshold;
+  * object: unit-norm 3D descriptors ``[256, M]`` and leaves ``[256, M*L]``
+    with column ``i*L + j`` = leaf j of point i (reference ``GATs.py:46``);
+  * frame: unit-norm query descriptors ``[256, N]``, the first N/2 columns
+    planted as noisy copies of a random subset of the 3D descriptors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+D = 256
+HEADS = 4
+GNN_LAYERS = ["GATs", "self", "cross"] * 4  # reference GATs_SuperGlue.py:162
+
+DEFAULT_HPARAMS = {
+    # reference configs/experiment/train_GATsSPG.yaml:44-60
+    "descriptor_dim": 256,
+    "keypoints_encoder": [32, 64, 128],
+    "match_type": "softmax",
+    "scale_factor": 0.07,
+    "match_threshold": 0.2,
+    "include_self": True,
+    "additional": False,
+    "with_linear_transform": False,
+}
+
+
+def _conv(rs: np.random.RandomState, cout: int, cin: int):
+    """Conv1d(k=1) default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both."""
+    bound = 1.0 / np.sqrt(cin)
+    w = rs.uniform(-bound, bound, size=(cout, cin, 1)).astype(np.float32)
+    b = rs.uniform(-bound, bound, size=(cout,)).astype(np.float32)
+    return w, b
+
+
+def _kenc(rs, sd, prefix, inp_dim, layers, feature_dim):
+    """Dead parameters (reference GATs_SuperGlue.py:131-160); present so that a
+    reference checkpoint / state dict round-trips."""
+    chans = [inp_dim] + list(layers) + [feature_dim]
+    idx = 0
+    for i in range(1, len(chans)):
+        w, b = _conv(rs, chans[i], chans[i - 1])
+        if i == len(chans) - 1:
+            b[:] = 0.0
+        sd[f"{prefix}.encoder.{idx}.weight"] = w
+        sd[f"{prefix}.encoder.{idx}.bias"] = b
+        idx += 1
+        if i < len(chans) - 1:
+            idx += 2  # InstanceNorm1d (no params) + ReLU
+
+
+def make_state_dict(seed: int = 0, damped: bool = True, hparams: dict | None = None):
+    """Reference-keyed state dict (numpy fp32 arrays)."""
+    hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
+    d = hp["descriptor_dim"]
+    rs = np.random.RandomState(seed)
+    sd: dict[str, np.ndarray] = {}
+    _kenc(rs, sd, "kenc_2d", 3, hp["keypoints_encoder"], d)
+    _kenc(rs, sd, "kenc_3d", 4, hp["keypoints_encoder"], d)
+    for i, name in enumerate(GNN_LAYERS):
+        p = f"gnn.layers.{i}"
+        if name == "GATs":
+            std = 1.414 * np.sqrt(2.0 / (d + d))
+            sd[f"{p}.W"] = (rs.randn(d, d) * std).astype(np.float32)
+            std = 1.414 * np.sqrt(2.0 / (2 * d + 1))
+            sd[f"{p}.a"] = (rs.randn(2 * d, 1) * std).astype(np.float32)
+        else:
+            w, b = _conv(rs, d, d)
+            sd[f"{p}.attn.merge.weight"], sd[f"{p}.attn.merge.bias"] = w, b
+            for j in range(3):
+                w, b = _conv(rs, d, d)
+                sd[f"{p}.attn.proj.{j}.weight"], sd[f"{p}.attn.proj.{j}.bias"] = w, b
+            w, b = _conv(rs, 2 * d, 2 * d)
+            sd[f"{p}.mlp.0.weight"], sd[f"{p}.mlp.0.bias"] = w, b
+            w, b = _conv(rs, d, 2 * d)
+            b[:] = 0.0  # reference GATs_SuperGlue.py:109
+            if damped:
+                w *= 0.02
+            sd[f"{p}.mlp.3.weight"], sd[f"{p}.mlp.3.bias"] = w, b
+    w, b = _conv(rs, d, d)
+    if damped:
+        w = (np.eye(d, dtype=np.float32)[:, :, None] + 0.02 * w).astype(np.float32)
+    sd["final_proj.weight"], sd["final_proj.bias"] = w, b
+    sd["bin_score"] = np.array(1.0, dtype=np.float32)
+    return sd
+
+
+def _unit_cols(x: np.ndarray) -> np.ndarray:
+    return (x / np.linalg.norm(x, axis=0, keepdims=True)).astype(np.float32)
+
+
+def make_object(object_id: int, M: int, L: int = 8, d: int = D):
+    """Per-object constants: (descriptors3d_db [d, M], descriptors2d_db [d, M*L])."""
+    rs = np.random.RandomState(1000 + object_id)
+    db = _unit_cols(rs.randn(d, M))
+    leaves = _unit_cols(np.repeat(db, L, axis=1) + 0.02 * rs.randn(d, M * L))
+    return db, leaves
+
+
+def make_frame(frame_id: int, db: np.ndarray, N: int):
+    """Query descriptors [d, N]; first N//2 columns planted on db[:, perm]."""
+    d, M = db.shape
+    rs = np.random.RandomState(frame_id)
+    q = rs.randn(d, N)
+    n_plant = min(N // 2, M)
+    perm = rs.permutation(M)[:n_plant]
+    q[:, :n_plant] = db[:, perm] + 0.03 * rs.randn(d, n_plant)
+    return _unit_cols(q), perm
+
+
+def make_batch(object_id: int, frame_ids, N: int, M: int, L: int = 8):
+    """Reference-shaped input dict (numpy, batch-first, channel-first descriptors;
+    reference inference.py:80-94) for frames of ONE object."""
+    db, leaves = make_object(object_id, M, L)
+    qs = [make_frame(f, db, N)[0] for f in frame_ids]
+    B = len(qs)
+    return {
+        "keypoints2d": np.zeros((B, N, 2), np.float32),
+        "keypoints3d": np.zeros((B, M, 3), np.float32),
+        "descriptors2d_query": np.stack(qs, 0),
+        "descriptors3d_db": np.repeat(db[None], B, 0),
+        "descriptors2d_db": np.repeat(leaves[None], B, 0),
+    }
+
+
+def make_tracks(seed: int, M: int, d: int = D, max_len: int = 12):
+    """Variable-length multi-view tracks for the offline segmented mean
+    (reference feature_process.py:297-305): (descriptors [sum_len, d] f64, idxs [M])."""
+    rs = np.random.RandomState(seed)
+    idxs = rs.randint(1, max_len + 1, size=M).astype(np.int64)
+    desc = rs.randn(int(idxs.sum()), d)
+    return desc, idxs

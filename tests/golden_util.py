@@ -1,0 +1,31 @@
+"""Load a golden fixture (tests/golden/*.npz, made by make_golden.py from the
+reference module) and regenerate its seeded inputs."""
+import glob
+import os
+
+import numpy as np
+
+from onepose_b200 import synthetic
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FORWARD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                       if not os.path.basename(p).startswith(("empty", "mean_desc")))
+RELEASED_CASES = [c for c in FORWARD_CASES if not c.startswith(("noself", "lintrans", "additional"))]
+
+
+def load_case(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    for k, v in zip(g["meta_hp_keys"], g["meta_hp_vals"]):
+        hp[str(k)] = bool(v)
+    sd = synthetic.make_state_dict(int(g["meta_wseed"]), damped=bool(g["meta_damped"]), hparams=hp)
+    data = synthetic.make_batch(int(g["meta_obj"]), [int(f) for f in g["meta_frames"]],
+                                int(g["meta_N"]), int(g["meta_M"]), int(g["meta_L"]))
+    return g, hp, sd, data
+
+
+def conf_reference_view(g, conf):
+    """(reference conf values, same-shaped view of ``conf``) -- full or the stored sample."""
+    if "conf_matrix" in g:
+        return g["conf_matrix"], conf
+    return g["conf_sample"], conf[:, ::7, ::5]
