@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- query frames/sec of the GATsSPG 2D-3D matching forward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic input:
+``--frames`` (32) query frames of ONE object, N2D=1024, N3D=7000, L=8, D=256
+(BASELINE.json configs[2], the configuration the metric is quoted on).  With N>1
+(torchrun, one rank per GPU) every rank owns a different object and the same number
+of frames (object-sharded, weak scaling, no collective on the data path; one NCCL
+all_gather of per-rank records at the end -- SURVEY 8e).
+
+Printed JSON line (rank 0): see the contract in the task description; extra objects
+``roofline`` (dominant kernel = the tensor-core GEMM core, measured live with CUDA
+events around its launches through the library's profiling hook) and ``cpu_baseline``
+(the oracle port of the reference's CPU forward, timed on this box's host cores).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N2D, N3D, NLEAF, DIM = 1024, 7000, 8, 256
+METRIC = "query frames/sec at N2D=1024,N3D=7000"
+
+
+def algorithmic_flops_per_frame(N, M, L=NLEAF, D=DIM):
+    """each logical MMA counted once (it executes as 3 fp16 passes)."""
+    return 8 * 21 * (N + M) * D * D + 2 * (N + M) * D * D + 2 * N * M * D + 4 * (2 * M * D + 2 * M * (L + 1) * D)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"tflops": j["bf16_tflops_sustained"], "hbm_gbs": j["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def time_cpu_port(frames_budget_s, max_frames, n_warm=1):
+    """The oracle port of the reference CPU forward, B=1 per call (the reference's own calling
+    convention, inference.py:85-92), all host threads.  Returns (frames/s, per-frame seconds list)."""
+    from onepose_b200 import synthetic
+    from oracle import gats_spg_oracle as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict(0)
+    P = oracle.params_from_numpy(sd)
+    hp = synthetic.DEFAULT_HPARAMS
+    db, leaves = synthetic.make_object(0, N3D, NLEAF)
+    times = []
+    t_begin = time.time()
+    f = 0
+    while True:
+        q, _ = synthetic.make_frame(f, db, N2D)
+        data = {"keypoints2d": np.zeros((1, N2D, 2), np.float32), "keypoints3d": np.zeros((1, N3D, 3), np.float32),
+                "descriptors2d_query": q[None], "descriptors3d_db": db[None], "descriptors2d_db": leaves[None]}
+        data = {k: torch.from_numpy(v) for k, v in data.items()}
+        t0 = time.perf_counter()
+        oracle.forward(P, data, hp)
+        dt = time.perf_counter() - t0
+        if f >= n_warm:
+            times.append(dt)
+        f += 1
+        if len(times) >= max_frames or (times and time.time() - t_begin > frames_budget_s):
+            break
+    med = statistics.median(times)
+    return 1.0 / med, times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
+    reference cannot travel to the GPU box) on this box's host cores."""
+    if rank != 0:
+        return
+    per_step = []
+    from onepose_b200 import synthetic
+    from oracle import gats_spg_oracle as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict(0)
+    P = oracle.params_from_numpy(sd)
+    hp = synthetic.DEFAULT_HPARAMS
+    db, leaves = synthetic.make_object(0, N3D, NLEAF)
+
+    def one(fid):
+        q, _ = synthetic.make_frame(fid, db, N2D)
+        data = {"keypoints2d": np.zeros((1, N2D, 2), np.float32), "keypoints3d": np.zeros((1, N3D, 3), np.float32),
+                "descriptors2d_query": q[None], "descriptors3d_db": db[None], "descriptors2d_db": leaves[None]}
+        data = {k: torch.from_numpy(v) for k, v in data.items()}
+        t0 = time.perf_counter()
+        oracle.forward(P, data, hp)
+        return time.perf_counter() - t0
+
+    for w in range(args.warmup):
+        one(w)
+    for s in range(args.steps):
+        per_step.append(one(1000 + s))
+    total = sum(per_step)
+    fps = args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GATsSPG forward, N2D=1024 N3D=7000 L=8 D=256, 1 frame per step (B=1, reference calling convention)",
+                   "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} single-frame forwards of the oracle port (torch CPU fp32, all threads), cpu={cpu_model()}"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per step (batch of one object)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per GNN chunk (0 = library default)")
+    ap.add_argument("--backend", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from onepose_b200 import GATsSuperGlue, synthetic
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    model = GATsSuperGlue(hp, gemm_backend=args.backend).eval()
+    model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()})
+    model = model.to(dev)
+    if args.chunk:
+        model.set_chunk_frames(args.chunk)
+
+    B = args.frames
+    # object-sharded: rank r owns object r; frames are seeded per (rank, step-slot)
+    db, leaves = synthetic.make_object(rank, N3D, NLEAF)
+    n_slots = 4                                     # rotate distinct query batches (4 x 33.5 MB > L2 together with the 64 MB object)
+    q_host = []
+    for s in range(n_slots):
+        qs = np.stack([synthetic.make_frame(100000 * rank + 1000 * s + f, db, N2D)[0] for f in range(B)], 0)
+        q_host.append(torch.from_numpy(qs).pin_memory())
+    q_dev = [q.to(dev) for q in q_host]
+    model.set_object(torch.from_numpy(db).to(dev), torch.from_numpy(leaves).to(dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for w in range(args.warmup):
+        out = model.match_frames(q_dev[w % n_slots])
+    launches_per_step = model.launch_count()
+    n_match = int((out["matches0"] > -1).sum())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                       # L2 flush between timed iterations (outside the event pair)
+        ev[s][0].record()
+        out = model.match_frames(q_dev[s % n_slots])
+        ev[s][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    my_ms = sum(step_ms)
+    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end through the public host-buffer call ("e2e") ----------------
+    host_out = None
+    for w in range(2):
+        host_out = model.match_frames_host(q_host[w % n_slots], host_out)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    e2e_steps = args.steps
+    for s in range(e2e_steps):
+        host_out = model.match_frames_host(q_host[s % n_slots], host_out)   # H2D + forward + D2H + sync inside
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+    assert int((host_out["matches0"] > -1).sum()) > 0
+
+    # ---------------- roofline of the dominant kernel (GEMM core), measured live ----------------
+    model.set_profiling(True)
+    prof_runs = []
+    for s in range(3):
+        model.match_frames(q_dev[s % n_slots])
+        prof_runs.append(model.get_profile())
+    model.set_profiling(False)
+    prof = prof_runs[-1]
+    pk = peaks()
+    gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
+
+    # ---------------- per-rank records over NCCL (the path's only collective) ----------------
+    rec = torch.tensor([float(B * args.steps), my_ms, float(n_match)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allrec = [torch.zeros_like(rec) for _ in range(world)]
+        dist.all_gather(allrec, rec)
+    else:
+        allrec = [rec]
+    frames_total = sum(float(r[0]) for r in allrec)
+
+    if rank == 0:
+        fps = frames_total / (total_ms * 1e-3)
+        e2e_fps = (B * e2e_steps * world) / e2e_s
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 semantics via fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate" if args.backend == "tcgen05" else "f32 (SIMT cross-check core)",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic batch={B} frames of one object per GPU, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2])",
+                       "frames_per_step": B, "gemm_backend": args.backend,
+                       "l2": "256 MB buffer written between timed iterations (outside the event pair); query batches rotated",
+                       "sharding": "one object per rank, no data-path collective"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * DIM * N2D * 4,
+                    "d2h_bytes_per_step": B * (N2D + N3D) * 12,
+                    "note": "opb_forward_host: pinned H2D of query descriptors, forward incl. conf matrix on device, D2H of matches+scores, sync"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm core (all GEMM launches of a step)", "achieved": gemm_tflops, "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": gemm_tflops / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                         "gemm_ms_per_step": prof["gemm_ms"], "step_ms_profiled": prof["total_ms"], "gemm_share_of_step": prof["gemm_ms"] / prof["total_ms"],
+                         "gemm_launches_per_step": prof["gemm_launches"],
+                         "algorithmic_gflop_per_frame": algorithmic_flops_per_frame(N2D, N3D) / 1e9,
+                         "whole_step_tflops": algorithmic_flops_per_frame(N2D, N3D) * B / (total_ms / args.steps * 1e-3) / 1e12},
+            "matches_per_batch": n_match, "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_fps, times = time_cpu_port(frames_budget_s=20.0, max_frames=8)
+            line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{len(times)} single-frame forwards (B=1) of the oracle port at the same shape, torch CPU fp32, "
+                                              f"{os.cpu_count()} threads, median; cpu={cpu_model()}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+/*
+ * onepose_b200 -- C ABI of the B200-native GATsSPG 2D-3D matcher.
+ *
+ * The reference (zju3dv/OnePose) is pure Python and has no FFI; the boundary it
+ * exposes for this path is `GATsSuperGlue.forward(data) -> (pred, conf_matrix)`
+ * (reference src/models/GATsSPG_architectures/GATs_SuperGlue.py:179-241), reached
+ * through `LitModelGATsSPG.forward` (src/models/GATsSPG_lightning_model.py:36-37)
+ * from inference.py:146.  Each entry point below names the reference code it
+ * replaces.  All signatures are plain C: pointers, sizes, a cudaStream_t passed
+ * as void*.  No torch types.  Every function returns 0 on success or a negative
+ * OPB_E_* code; opb_last_error() gives the message.  No exceptions cross the ABI.
+ *
+ * Pointer ownership: inputs are borrowed and never written; outputs are caller
+ * allocated (device memory unless the name says _host).
+ */
+#ifndef ONEPOSE_B200_H_
+#define ONEPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPB_OK 0
+#define OPB_E_INVALID (-1)      /* bad argument / unsupported configuration        */
+#define OPB_E_CUDA (-2)         /* CUDA runtime / driver error                      */
+#define OPB_E_STATE (-3)        /* call order violated (weights / object missing)   */
+#define OPB_E_RANGE (-4)        /* activation left the fp16-split operand range     */
+#define OPB_E_NOT_IMPLEMENTED (-5)
+
+typedef struct opb_matcher opb_matcher; /* opaque */
+
+/* Hyper-parameters = the `hparams` mapping of GATsSuperGlue.__init__
+ * (GATs_SuperGlue.py:145-177; released values configs/experiment/train_GATsSPG.yaml:44-60). */
+typedef struct opb_config {
+  int32_t descriptor_dim;        /* 256 (only value supported)                         */
+  int32_t num_heads;             /* 4   (GATs_SuperGlue.py:43)                          */
+  float scale_factor;            /* 0.07 (GATs_SuperGlue.py:217)                        */
+  float match_threshold;         /* 0.2  (GATs_SuperGlue.py:227)                        */
+  int32_t include_self;          /* GATs.py:48                                          */
+  int32_t additional;            /* GATs.py:61                                          */
+  int32_t with_linear_transform; /* GATs.py:56 -- only 0 is implemented                */
+  int32_t device;                /* CUDA device ordinal                                 */
+  int32_t gemm_backend;          /* 0 = tcgen05 (product), 1 = SIMT fp32 cross-check (tests only) */
+} opb_config;
+
+/* Replaces GATsSuperGlue.__init__ (GATs_SuperGlue.py:145-177). */
+int opb_create(const opb_config* cfg, opb_matcher** out);
+void opb_destroy(opb_matcher* m);
+const char* opb_last_error(const opb_matcher* m); /* m may be NULL: last create error */
+
+/* Replaces nn.Module.load_state_dict for the keys of GATs_SuperGlue.py:
+ * `name` is the reference state-dict key ("gnn.layers.1.attn.proj.0.weight", ...),
+ * `data` a HOST fp32 array in the reference's own layout.  Dead parameters
+ * (kenc_*, bin_score) are accepted and ignored.  opb_finalize_weights() packs
+ * (head permutation, merge->mlp.0 folding, W.a folding, fp16 hi/lo split) and uploads. */
+int opb_load_weight(opb_matcher* m, const char* name, const float* data, size_t n_elems);
+int opb_finalize_weights(opb_matcher* m);
+
+/* Per-object constants = the tensors inference.py:113-130 builds once per sequence
+ * and pack_data (inference.py:80-94) re-uploads every frame:
+ *   desc3d_db  device fp32 [256, M]    (descriptors3d_db, channel-first)
+ *   desc2d_db  device fp32 [256, M*L]  (descriptors2d_db, column i*L+j = leaf j of point i; GATs.py:46) */
+int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_db,
+                   int32_t M, int32_t L, void* stream);
+
+/* Replaces GATsSuperGlue.forward (GATs_SuperGlue.py:179-241) for B query frames of
+ * the current object.  desc2d_query: device fp32 [B, 256, N] (channel-first, as in
+ * the reference).  Outputs (device): matches0 int64 [B,N], matches1 int64 [B,M],
+ * mscores0 fp32 [B,N], mscores1 fp32 [B,M]; conf fp32 [B,N,M] or NULL to skip
+ * materialising the confidence matrix.  Asynchronous on `stream`. */
+int opb_forward(opb_matcher* m, const float* desc2d_query, int32_t B, int32_t N,
+                int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                float* conf, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of the query descriptors,
+ * forward, D2H of matches/scores; returns after the stream has been synchronised.  The
+ * confidence matrix is always materialised on the device (the reference returns it) and copied
+ * to conf_host only if that is non-NULL (inference.py:146 discards it).  This is the
+ * end-to-end leg bench.py times. */
+int opb_forward_host(opb_matcher* m, const float* desc2d_query_host, int32_t B, int32_t N,
+                     int64_t* matches0_host, int64_t* matches1_host, float* mscores0_host,
+                     float* mscores1_host, float* conf_host, void* stream);
+
+/* Number of kernels opb_forward launched in its last call (bench.py "gpu_launches"). */
+int opb_last_launch_count(const opb_matcher* m);
+
+/* Measurement hook for bench.py: with profiling on, every GEMM launch of opb_forward is
+ * bracketed by CUDA events on the launch stream.  opb_get_profile() synchronises and returns the
+ * summed GEMM time, the ALGORITHMIC FLOPs those launches performed (2*valid_rows*n_out*K, each
+ * logical MMA counted once although it executes as 3 fp16 passes), their count, and the time of the
+ * whole forward (first to last kernel).  Profiling perturbs timing slightly: never on in timed runs. */
+int opb_set_profiling(opb_matcher* m, int32_t enable);
+int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms);
+
+/* Frames processed together through the GNN (L2-residency knob); 0 = default. */
+int opb_set_chunk_frames(opb_matcher* m, int32_t frames);
+
+/* Offline producer: segmented mean of multi-view descriptors
+ * (reference src/sfm/postprocess/feature_process.py:297-305 mean_descriptors, fp64):
+ * desc device f64 [sum(seg_len), D], seg_len device int64 [M] -> out device f64 [M, D]. */
+int opb_segmented_mean_f64(const double* desc, const int64_t* seg_len, int32_t M, int32_t D,
+                           double* out, void* stream);
+
+/* ---- test hooks (used by tests/ only; stable but not part of the drop-in surface) ---- */
+/* C[rows, n_out] (fp32, ld = n_out) = A . B^T with fp16-split operands, through the
+ * selected GEMM core.  a_hi/a_lo [rows, K], b_hi/b_lo [n_out, K]; rows % 128 == 0,
+ * K % 64 == 0, n_out % 128 == 0.  backend as opb_config.gemm_backend. */
+int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                   float* c, int32_t rows, int32_t n_out, int32_t K, int32_t backend, void* stream);
+/* fp32 [rows, cols] -> fp16 hi / lo(x2^11) planes. */
+int opb_debug_split(const float* x, void* hi, void* lo, size_t n, void* stream);
+/* Copy an internal activation buffer of the last forward to `out` (device fp32):
+ * which = 0: X [B*(n_pad+m_pad), 256] reconstructed from its planes. Returns rows via *rows. */
+int opb_debug_read(opb_matcher* m, int32_t which, float* out, size_t capacity_elems, int64_t* rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEPOSE_B200_H_ */

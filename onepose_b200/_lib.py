@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI in include/onepose_b200.h.
+
+There is deliberately NO fallback: if the shared library is missing or does not
+load, importing the matcher raises.  (The oracle under /oracle is test
+infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libonepose_b200.so")
+
+OPB_OK = 0
+ERRORS = {-1: "OPB_E_INVALID", -2: "OPB_E_CUDA", -3: "OPB_E_STATE", -4: "OPB_E_RANGE", -5: "OPB_E_NOT_IMPLEMENTED"}
+
+
+class OpbConfig(C.Structure):
+    _fields_ = [
+        ("descriptor_dim", C.c_int32), ("num_heads", C.c_int32), ("scale_factor", C.c_float),
+        ("match_threshold", C.c_float), ("include_self", C.c_int32), ("additional", C.c_int32),
+        ("with_linear_transform", C.c_int32), ("device", C.c_int32), ("gemm_backend", C.c_int32),
+    ]
+
+
+# every symbol include/onepose_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "opb_create": (C.c_int, [C.POINTER(OpbConfig), C.POINTER(_P)]),
+    "opb_destroy": (None, [_P]),
+    "opb_last_error": (C.c_char_p, [_P]),
+    "opb_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
+    "opb_finalize_weights": (C.c_int, [_P]),
+    "opb_set_object": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "opb_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "opb_forward_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "opb_last_launch_count": (C.c_int, [_P]),
+    "opb_set_chunk_frames": (C.c_int, [_P, C.c_int32]),
+    "opb_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "opb_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "opb_segmented_mean_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "opb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "opb_debug_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "opb_debug_read": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree CUDA library; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m onepose_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class OpbError(RuntimeError):
+    pass
+
+
+def check(rc: int, handle=None):
+    if rc == OPB_OK:
+        return
+    msg = load().opb_last_error(handle)
+    raise OpbError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")

@@ -1,0 +1,613 @@
+// C ABI of the B200-native GATsSPG matcher (see include/onepose_b200.h).
+// Host-side state: packed weights, per-object constants, chunk workspace, launch sequence.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/onepose_b200.h"
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_aux.cuh"
+
+namespace opb {
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need, bool zero = false) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return e;
+    bytes = need;
+    if (zero) e = cudaMemset(p, 0, need);
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PlaneBuf {
+  DevBuf hi, lo;
+  cudaError_t ensure(size_t elems, bool zero = false) {
+    cudaError_t e = hi.ensure(elems * sizeof(__half), zero);
+    if (e != cudaSuccess) return e;
+    return lo.ensure(elems * sizeof(__half), zero);
+  }
+  void release() { hi.release(); lo.release(); }
+  CPlanes c(int ld, size_t off_elems = 0) const { return CPlanes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
+  Planes m(int ld, size_t off_elems = 0) const { return Planes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
+};
+
+struct AttnLayerW {       // one AttentionPropagation (reference GATs_SuperGlue.py:104-113)
+  PlaneBuf wqkv;          // [768,256]  rows: Q | K | V, head-contiguous output channels
+  DevBuf bqkv;            // [768]
+  PlaneBuf w0a;           // [512,256]  mlp.0.weight[:, :256]
+  DevBuf w0m;             // fp32 [512,256] = mlp.0.weight[:, 256:] @ merge.weight (head-contiguous inputs)
+  DevBuf b0f;             // [512] = mlp.0.weight[:,256:] @ merge.bias + mlp.0.bias
+  PlaneBuf w1;            // [256,512]  mlp.3.weight
+  DevBuf b1;              // [256]
+};
+
+}  // namespace opb
+
+using namespace opb;
+
+struct opb_matcher {
+  opb_config cfg{};
+  std::string err;
+  std::map<std::string, std::vector<float>> host_w;
+  bool weights_ready = false;
+  bool object_ready = false;
+  // packed weights
+  AttnLayerW attn[8];
+  DevBuf wa2, wa3;        // [4][256] each (GATs: W a[:256], W a[256:])
+  PlaneBuf wf;            // final_proj [256,256]
+  DevBuf bf;
+  // per-object constants
+  int M = 0, Lf = 0, m_pad = 0;
+  DevBuf leaves;          // fp32 [M*Lf, 256] point-major
+  PlaneBuf db;            // [m_pad, 256]
+  DevBuf s2;              // [4][M*Lf]
+  // workspace (chunk)
+  int chunk_frames = 0;   // user override
+  int ws_frames = 0, ws_N = 0;
+  PlaneBuf x, qp, hn, pn, g;
+  DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
+  DevBuf range_flag;
+  // host-call staging
+  DevBuf st_q, st_m0, st_m1, st_s0, st_s1, st_conf;
+  Layout last_layout{};
+  // profiling (bench.py roofline leg)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<double> ev_flops;     // per GEMM launch
+  cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
+  int launches = 0;
+  int last_launches = 0;
+};
+
+namespace opb {
+
+int fail(opb_matcher* m, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (m) m->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(m, expr)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(m, OPB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static void split_host(const std::vector<double>& w, std::vector<__half>& hi, std::vector<__half>& lo) {
+  hi.resize(w.size());
+  lo.resize(w.size());
+  for (size_t i = 0; i < w.size(); ++i) {
+    float x = (float)w[i];
+    __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn((x - __half2float(h)) * kLoScale);
+  }
+}
+
+static int upload_planes(opb_matcher* m, PlaneBuf& dst, const std::vector<double>& w) {
+  std::vector<__half> hi, lo;
+  split_host(w, hi, lo);
+  CK(m, dst.ensure(w.size()));
+  CK(m, cudaMemcpy(dst.hi.p, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CK(m, cudaMemcpy(dst.lo.p, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int upload_f32(opb_matcher* m, DevBuf& dst, const std::vector<double>& w) {
+  std::vector<float> f(w.begin(), w.end());
+  CK(m, dst.ensure(f.size() * sizeof(float)));
+  CK(m, cudaMemcpy(dst.p, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static const std::vector<float>* find_w(opb_matcher* m, const std::string& key, size_t n) {
+  auto it = m->host_w.find(key);
+  if (it == m->host_w.end()) { fail(m, OPB_E_STATE, "missing weight '%s'", key.c_str()); return nullptr; }
+  if (it->second.size() != n) {
+    fail(m, OPB_E_INVALID, "weight '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), n);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+static cudaEvent_t next_event(opb_matcher* m) {
+  if (m->ev_used == m->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    m->ev_pool.push_back(e);
+  }
+  return m->ev_pool[m->ev_used++];
+}
+
+// One launch of the selected GEMM core producing fp32 C (+bias).  `flops` = algorithmic FLOPs.
+static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, double flops) {
+  int rc;
+  if (m->profiling) cudaEventRecord(next_event(m), st);
+  if (m->cfg.gemm_backend == 1) rc = launch_gemm_simt(p, st);
+  else rc = launch_gemm_tc_plain(p, st);
+  if (m->profiling) { cudaEventRecord(next_event(m), st); m->ev_flops.push_back(flops); }
+  m->launches++;
+  if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (rc=%d, backend=%d): %s", rc,
+                           m->cfg.gemm_backend, cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+static int ensure_workspace(opb_matcher* m, int frames, int N) {
+  if (frames <= m->ws_frames && N <= m->ws_N) return 0;
+  frames = frames > m->ws_frames ? frames : m->ws_frames;
+  N = N > m->ws_N ? N : m->ws_N;
+  const int n_pad = round_up(N, kTileRows);
+  const size_t R = (size_t)n_pad + m->m_pad;
+  const size_t rows = R * frames;
+  const size_t S = 2 * (size_t)frames;
+  const int max_slabs = (std::max(n_pad, m->m_pad) + kSlabRows - 1) / kSlabRows;
+  CK(m, m->x.ensure(rows * kD, true));
+  CK(m, m->qp.ensure(rows * kD, true));
+  CK(m, m->hn.ensure(rows * 512, true));
+  CK(m, m->pn.ensure(rows * kD, true));
+  CK(m, m->g.ensure(S * 512 * kD));
+  CK(m, m->c768.ensure(rows * 768 * sizeof(float)));
+  CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
+  CK(m, m->kvpart.ensure(S * kHeads * max_slabs * kKVPartial * sizeof(float)));
+  CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
+  CK(m, m->kmean.ensure(S * kD * sizeof(float)));
+  CK(m, m->statpart.ensure(rows / kTileRows * 512 * 2 * sizeof(float)));
+  CK(m, m->mu.ensure(S * 512 * sizeof(float)));
+  CK(m, m->rstd.ensure(S * 512 * sizeof(float)));
+  CK(m, m->score.ensure((size_t)frames * n_pad * m->m_pad * sizeof(float)));
+  CK(m, m->rowsum.ensure((size_t)frames * n_pad * sizeof(float)));
+  CK(m, m->colsum.ensure((size_t)frames * m->m_pad * sizeof(float)));
+  CK(m, m->rowbest.ensure((size_t)frames * n_pad * sizeof(unsigned long long)));
+  CK(m, m->colbest.ensure((size_t)frames * m->m_pad * sizeof(unsigned long long)));
+  CK(m, m->range_flag.ensure(sizeof(int), true));
+  m->ws_frames = frames;
+  m->ws_N = N;
+  return 0;
+}
+
+// GNN + tail for `fb` frames starting at frame f0 of the call.
+static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
+                         float* conf, cudaStream_t st) {
+  Layout L;
+  L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kTileRows); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
+  m->last_layout = L;
+  const int rows = L.rows();
+  const int S = L.segs();
+  const int tiles = rows / kTileRows;
+  const int max_slabs = (std::max(L.n_pad, L.m_pad) + kSlabRows - 1) / kSlabRows;
+  const double valid_rows = (double)fb * (N + L.M);
+  __half *xh = m->x.hi.as<__half>(), *xl = m->x.lo.as<__half>();
+  auto launched = [&]() { m->launches++; };
+
+  // inputs: query descriptors [fb,256,N] channel-first -> q segments; object rows -> d segments
+  transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, xh, xl, nullptr, L.R, 0);
+  launched();
+  broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->db.hi.as<__half>(), m->db.lo.as<__half>(), xh, xl, L);
+  launched();
+
+  int attn_idx = 0;
+  for (int layer = 0; layer < 12; ++layer) {
+    if (layer % 3 == 0) {
+      const int gi = layer / 3;
+      const long long warps = (long long)L.M * L.B;
+      gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+          xh, xl, L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+          m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
+      launched();
+      continue;
+    }
+    const int cross = (layer % 3 == 2) ? 1 : 0;
+    AttnLayerW& W = m->attn[attn_idx++];
+    // (1) q,k,v projections (GATs_SuperGlue.py:96-99), all three from the segment's own rows
+    GemmProblem p{};
+    p.L = L; p.batch = 1; p.rows = rows;
+    p.a1 = m->x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
+    p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
+    if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
+    // (2) linear-attention state of every segment (:71-78)
+    kv_state_partial<<<dim3(max_slabs, kHeads, S), 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, L, max_slabs, m->kvpart.as<float>());
+    launched();
+    kv_state_reduce<<<S * kHeads, 256, 0, st>>>(m->kvpart.as<float>(), L, max_slabs, m->kvmean.as<float>(), m->kmean.as<float>());
+    launched();
+    // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
+    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
+                                                                                  m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
+    launched();
+    // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
+    g_fold<<<dim3(512 / 32, S), 256, (kHeads * kDh * kDh + kD) * sizeof(float), st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross,
+                                                                                     m->g.hi.as<__half>(), m->g.lo.as<__half>());
+    launched();
+    // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
+    GemmProblem p2{};
+    p2.L = L; p2.batch = 1; p2.rows = rows;
+    p2.a1 = m->x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
+    p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
+    p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
+    if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
+    // (6) InstanceNorm statistics per segment (:126)
+    in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
+    launched();
+    in_stats_final<<<dim3(S, 2), 256, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+    launched();
+    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
+                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
+    launched();
+    // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64)
+    GemmProblem p3{};
+    p3.L = L; p3.batch = 1; p3.rows = rows;
+    p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
+    p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
+    if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
+    residual_update<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, xl, m->c768.as<float>(), (long long)rows * kD / 8);
+    launched();
+  }
+
+  // ---- tail (GATs_SuperGlue.py:209-237) ----
+  GemmProblem pf{};
+  pf.L = L; pf.batch = 1; pf.rows = rows;
+  pf.a1 = m->x.c(kD); pf.K1 = kD; pf.b1 = m->wf.c(kD); pf.n_out = 256;
+  pf.bias = m->bf.as<float>(); pf.c = m->c768.as<float>(); pf.ldc = 256;
+  if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
+  l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
+  launched();
+  // cos[b][n][m] = <P_q[n], P_d[m]>   (batched over frames)
+  GemmProblem ps{};
+  ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
+  ps.a1 = m->pn.c(kD); ps.K1 = kD; ps.b1 = m->pn.c(kD, (size_t)L.n_pad * kD);
+  ps.a_batch_rows = L.R; ps.b_batch_rows = L.R; ps.c_batch_elems = (long long)L.n_pad * L.m_pad;
+  ps.c = m->score.as<float>(); ps.ldc = L.m_pad;
+  if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
+  const float inv_scale = 1.f / m->cfg.scale_factor;
+  score_row_sums<<<(unsigned)(((long long)fb * N * 32 + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>());
+  launched();
+  score_col_sums<<<(unsigned)(((long long)fb * L.M + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
+  launched();
+  CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
+  CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
+  conf_argmax_simt<<<dim3((L.M + 127) / 128, (N + 31) / 32, fb), 128, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>(),
+                                                                              m->colsum.as<float>(), conf,
+                                                                              m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
+  launched();
+  mutual_match<<<fb, 256, 0, st>>>(m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>(), N, L.M, m->cfg.match_threshold,
+                                   reinterpret_cast<long long*>(m0), reinterpret_cast<long long*>(m1), s0, s1);
+  launched();
+  CK(m, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace opb
+
+// =========================================================================================
+extern "C" {
+
+int opb_create(const opb_config* cfg, opb_matcher** out) {
+  if (!cfg || !out) return fail(nullptr, OPB_E_INVALID, "null argument");
+  if (cfg->descriptor_dim != kD || cfg->num_heads != kHeads)
+    return fail(nullptr, OPB_E_INVALID, "only descriptor_dim=256, num_heads=4 are supported (got %d, %d)", cfg->descriptor_dim, cfg->num_heads);
+  if (cfg->with_linear_transform)
+    return fail(nullptr, OPB_E_NOT_IMPLEMENTED, "with_linear_transform=True is not implemented (released model uses False)");
+  if (!(cfg->scale_factor > 0.f)) return fail(nullptr, OPB_E_INVALID, "scale_factor must be > 0");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, OPB_E_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, OPB_E_INVALID, "device %d out of range", cfg->device);
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, OPB_E_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  e = cudaFuncSetAttribute(g_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kHeads * kDh * kDh + kD) * sizeof(float)));
+  if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaFuncSetAttribute(g_fold): %s", cudaGetErrorString(e));
+  auto* m = new opb_matcher();
+  m->cfg = *cfg;
+  *out = m;
+  return OPB_OK;
+}
+
+void opb_destroy(opb_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  for (auto& a : m->attn) { a.wqkv.release(); a.bqkv.release(); a.w0a.release(); a.w0m.release(); a.b0f.release(); a.w1.release(); a.b1.release(); }
+  DevBuf* bufs[] = {&m->wa2, &m->wa3, &m->bf, &m->leaves, &m->s2, &m->c768, &m->hid, &m->kvpart, &m->kvmean, &m->kmean, &m->statpart,
+                    &m->mu, &m->rstd, &m->score, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
+                    &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
+  for (auto* b : bufs) b->release();
+  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g};
+  for (auto* b : pb) b->release();
+  for (auto e : m->ev_pool) cudaEventDestroy(e);
+  if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }
+  delete m;
+}
+
+const char* opb_last_error(const opb_matcher* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int opb_load_weight(opb_matcher* m, const char* name, const float* data, size_t n) {
+  if (!m || !name || !data) return fail(m, OPB_E_INVALID, "null argument");
+  m->host_w[name] = std::vector<float>(data, data + n);
+  m->weights_ready = false;
+  return OPB_OK;
+}
+
+int opb_finalize_weights(opb_matcher* m) {
+  if (!m) return OPB_E_INVALID;
+  CK(m, cudaSetDevice(m->cfg.device));
+  // head-contiguous channel order: new c' = h*64 + d  <-  reference c = d*4 + h (GATs_SuperGlue.py:97)
+  int perm[kD];
+  for (int h = 0; h < kHeads; ++h)
+    for (int d = 0; d < kDh; ++d) perm[h * kDh + d] = d * kHeads + h;
+  std::vector<double> wa2(4 * kD), wa3(4 * kD);
+  int ai = 0;
+  for (int layer = 0; layer < 12; ++layer) {
+    const std::string p = "gnn.layers." + std::to_string(layer);
+    if (layer % 3 == 0) {
+      auto* W = find_w(m, p + ".W", kD * kD);
+      auto* a = find_w(m, p + ".a", 2 * kD);
+      if (!W || !a) return OPB_E_STATE;
+      const int gi = layer / 3;
+      for (int c = 0; c < kD; ++c) {  // h @ W @ a[:256] = h . (W a[:256])   (GATs.py:40,78-80)
+        double s2 = 0, s3 = 0;
+        for (int o = 0; o < kD; ++o) {
+          s2 += (double)(*W)[c * kD + o] * (double)(*a)[o];
+          s3 += (double)(*W)[c * kD + o] * (double)(*a)[kD + o];
+        }
+        wa2[gi * kD + c] = s2;
+        wa3[gi * kD + c] = s3;
+      }
+      continue;
+    }
+    AttnLayerW& A = m->attn[ai++];
+    const std::vector<float>*Wp[3], *bp[3];
+    for (int j = 0; j < 3; ++j) {
+      Wp[j] = find_w(m, p + ".attn.proj." + std::to_string(j) + ".weight", kD * kD);
+      bp[j] = find_w(m, p + ".attn.proj." + std::to_string(j) + ".bias", kD);
+      if (!Wp[j] || !bp[j]) return OPB_E_STATE;
+    }
+    auto* Wm = find_w(m, p + ".attn.merge.weight", kD * kD);
+    auto* bm = find_w(m, p + ".attn.merge.bias", kD);
+    auto* W0 = find_w(m, p + ".mlp.0.weight", 512 * 512);
+    auto* b0 = find_w(m, p + ".mlp.0.bias", 512);
+    auto* W1 = find_w(m, p + ".mlp.3.weight", kD * 512);
+    auto* b1 = find_w(m, p + ".mlp.3.bias", kD);
+    if (!Wm || !bm || !W0 || !b0 || !W1 || !b1) return OPB_E_STATE;
+    std::vector<double> wqkv(768 * kD), bqkv(768);
+    for (int j = 0; j < 3; ++j)
+      for (int c = 0; c < kD; ++c) {
+        for (int k = 0; k < kD; ++k) wqkv[((size_t)j * kD + c) * kD + k] = (*Wp[j])[(size_t)perm[c] * kD + k];
+        bqkv[j * kD + c] = (*bp[j])[perm[c]];
+      }
+    std::vector<double> w0a(512 * kD), w0m(512 * kD), b0f(512);
+    for (int c = 0; c < 512; ++c) {
+      for (int k = 0; k < kD; ++k) w0a[(size_t)c * kD + k] = (*W0)[(size_t)c * 512 + k];
+      double bacc = (*b0)[c];
+      for (int o = 0; o < kD; ++o) bacc += (double)(*W0)[(size_t)c * 512 + kD + o] * (double)(*bm)[o];
+      b0f[c] = bacc;
+      for (int k = 0; k < kD; ++k) {  // message channel k (head-contiguous) = reference channel perm[k]
+        double acc = 0;
+        for (int o = 0; o < kD; ++o) acc += (double)(*W0)[(size_t)c * 512 + kD + o] * (double)(*Wm)[(size_t)o * kD + perm[k]];
+        w0m[(size_t)c * kD + k] = acc;
+      }
+    }
+    std::vector<double> w1(W1->begin(), W1->end()), b1d(b1->begin(), b1->end());
+    if (int rc = upload_planes(m, A.wqkv, wqkv)) return rc;
+    if (int rc = upload_f32(m, A.bqkv, bqkv)) return rc;
+    if (int rc = upload_planes(m, A.w0a, w0a)) return rc;
+    if (int rc = upload_f32(m, A.w0m, w0m)) return rc;
+    if (int rc = upload_f32(m, A.b0f, b0f)) return rc;
+    if (int rc = upload_planes(m, A.w1, w1)) return rc;
+    if (int rc = upload_f32(m, A.b1, b1d)) return rc;
+  }
+  auto* Wf = find_w(m, "final_proj.weight", kD * kD);
+  auto* bfv = find_w(m, "final_proj.bias", kD);
+  if (!Wf || !bfv) return OPB_E_STATE;
+  if (int rc = upload_planes(m, m->wf, std::vector<double>(Wf->begin(), Wf->end()))) return rc;
+  if (int rc = upload_f32(m, m->bf, std::vector<double>(bfv->begin(), bfv->end()))) return rc;
+  if (int rc = upload_f32(m, m->wa2, wa2)) return rc;
+  if (int rc = upload_f32(m, m->wa3, wa3)) return rc;
+  m->weights_ready = true;
+  m->object_ready = false;  // s2 depends on the weights
+  return OPB_OK;
+}
+
+int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_db, int32_t M, int32_t Lf, void* stream) {
+  if (!m) return OPB_E_INVALID;
+  if (!m->weights_ready) return fail(m, OPB_E_STATE, "opb_set_object before opb_finalize_weights");
+  if (!desc3d_db || !desc2d_db || M <= 0 || Lf <= 0 || Lf > 32)
+    return fail(m, OPB_E_INVALID, "set_object: need M > 0 and 1 <= num_leaf <= 32 (got M=%d, L=%d)", M, Lf);
+  CK(m, cudaSetDevice(m->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m_pad = round_up(M, kTileRows);
+  if (m_pad != m->m_pad) { m->ws_frames = 0; m->ws_N = 0; }  // workspace depends on m_pad
+  m->M = M; m->Lf = Lf; m->m_pad = m_pad;
+  const long long n_leaf_rows = (long long)M * Lf;
+  CK(m, m->leaves.ensure((size_t)n_leaf_rows * kD * sizeof(float)));
+  CK(m, m->db.ensure((size_t)m_pad * kD));
+  CK(m, cudaMemsetAsync(m->db.hi.p, 0, (size_t)m_pad * kD * sizeof(__half), st));
+  CK(m, cudaMemsetAsync(m->db.lo.p, 0, (size_t)m_pad * kD * sizeof(__half), st));
+  CK(m, m->s2.ensure((size_t)4 * n_leaf_rows * sizeof(float)));
+  transpose_cf_to_rows<1><<<dim3((unsigned)((n_leaf_rows + 31) / 32), 1), dim3(32, 8), 0, st>>>(desc2d_db, (int)n_leaf_rows, 0, nullptr, nullptr,
+                                                                                           m->leaves.as<float>(), 0, 0);
+  transpose_cf_to_rows<0><<<dim3((M + 31) / 32, 1), dim3(32, 8), 0, st>>>(desc3d_db, M, 0, m->db.hi.as<__half>(), m->db.lo.as<__half>(), nullptr, 0, 0);
+  gats_leaf_logits<<<148 * 4, 256, 0, st>>>(m->leaves.as<float>(), n_leaf_rows, m->wa2.as<float>(), m->s2.as<float>());
+  CK(m, cudaGetLastError());
+  m->object_ready = true;
+  return OPB_OK;
+}
+
+int opb_set_chunk_frames(opb_matcher* m, int32_t frames) {
+  if (!m || frames < 0) return OPB_E_INVALID;
+  m->chunk_frames = frames;
+  return OPB_OK;
+}
+
+int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m0, int64_t* m1, float* s0, float* s1, float* conf,
+                void* stream) {
+  if (!m) return OPB_E_INVALID;
+  if (!m->weights_ready || !m->object_ready) return fail(m, OPB_E_STATE, "opb_forward needs weights and an object (finalize_weights, set_object)");
+  if (!q || !m0 || !m1 || !s0 || !s1 || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward: bad argument (B=%d, N=%d)", B, N);
+  CK(m, cudaSetDevice(m->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 4;
+  if (chunk > B) chunk = B;
+  if (int rc = ensure_workspace(m, chunk, N)) return rc;
+  m->launches = 0;
+  if (m->profiling) {
+    m->ev_used = 0;
+    m->ev_flops.clear();
+    if (!m->ev_fwd0) { cudaEventCreate(&m->ev_fwd0); cudaEventCreate(&m->ev_fwd1); }
+    cudaEventRecord(m->ev_fwd0, st);
+  }
+  for (int f0 = 0; f0 < B; f0 += chunk) {
+    const int fb = std::min(chunk, B - f0);
+    int rc = forward_chunk(m, q + (size_t)f0 * kD * N, N, fb, m0 + (size_t)f0 * N, m1 + (size_t)f0 * m->M, s0 + (size_t)f0 * N,
+                           s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st);
+    if (rc) return rc;
+  }
+  if (m->profiling) cudaEventRecord(m->ev_fwd1, st);
+  m->last_launches = m->launches;
+  return OPB_OK;
+}
+
+int opb_set_profiling(opb_matcher* m, int32_t enable) {
+  if (!m) return OPB_E_INVALID;
+  m->profiling = enable != 0;
+  m->ev_used = 0;
+  m->ev_flops.clear();
+  return OPB_OK;
+}
+
+int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms) {
+  if (!m || !m->ev_fwd1) return OPB_E_STATE;
+  CK(m, cudaEventSynchronize(m->ev_fwd1));
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < m->ev_flops.size(); ++i) {
+    float t = 0;
+    CK(m, cudaEventElapsedTime(&t, m->ev_pool[2 * i], m->ev_pool[2 * i + 1]));
+    ms += t;
+    fl += m->ev_flops[i];
+  }
+  float tot = 0;
+  CK(m, cudaEventElapsedTime(&tot, m->ev_fwd0, m->ev_fwd1));
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = (int32_t)m->ev_flops.size();
+  if (total_ms) *total_ms = tot;
+  return OPB_OK;
+}
+
+int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int64_t* m0h, int64_t* m1h, float* s0h, float* s1h, float* confh,
+                     void* stream) {
+  if (!m) return OPB_E_INVALID;
+  if (!m->object_ready) return fail(m, OPB_E_STATE, "opb_forward_host needs an object");
+  if (!qh || !m0h || !m1h || !s0h || !s1h || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward_host: bad argument");
+  CK(m, cudaSetDevice(m->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t M = m->M;
+  CK(m, m->st_q.ensure((size_t)B * kD * N * sizeof(float)));
+  CK(m, m->st_m0.ensure((size_t)B * N * sizeof(int64_t)));
+  CK(m, m->st_m1.ensure((size_t)B * M * sizeof(int64_t)));
+  CK(m, m->st_s0.ensure((size_t)B * N * sizeof(float)));
+  CK(m, m->st_s1.ensure((size_t)B * M * sizeof(float)));
+  CK(m, m->st_conf.ensure((size_t)B * N * M * sizeof(float)));  // conf is always materialised (reference returns it)
+  CK(m, cudaMemcpyAsync(m->st_q.p, qh, (size_t)B * kD * N * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = opb_forward(m, m->st_q.as<float>(), B, N, m->st_m0.as<int64_t>(), m->st_m1.as<int64_t>(), m->st_s0.as<float>(),
+                           m->st_s1.as<float>(), m->st_conf.as<float>(), stream))
+    return rc;
+  CK(m, cudaMemcpyAsync(m0h, m->st_m0.p, (size_t)B * N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(m, cudaMemcpyAsync(m1h, m->st_m1.p, (size_t)B * M * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(m, cudaMemcpyAsync(s0h, m->st_s0.p, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(m, cudaMemcpyAsync(s1h, m->st_s1.p, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (confh) CK(m, cudaMemcpyAsync(confh, m->st_conf.p, (size_t)B * N * M * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(m, cudaStreamSynchronize(st));
+  return OPB_OK;
+}
+
+int opb_last_launch_count(const opb_matcher* m) { return m ? m->last_launches : 0; }
+
+int opb_segmented_mean_f64(const double* desc, const int64_t* seg_len, int32_t M, int32_t D, double* out, void* stream) {
+  if (!desc || !seg_len || !out || M <= 0 || D <= 0) return OPB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long* offs = nullptr;
+  if (cudaMallocAsync(&offs, (size_t)M * sizeof(long long), st) != cudaSuccess) return OPB_E_CUDA;
+  exclusive_scan_i64_single<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(seg_len), offs, M);
+  segmented_mean_f64<<<(unsigned)(((long long)M * 32 + 255) / 256), 256, 0, st>>>(desc, reinterpret_cast<const long long*>(seg_len), offs, M, D, out);
+  cudaFreeAsync(offs, st);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
+}
+
+int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out, int32_t K,
+                   int32_t backend, void* stream) {
+  GemmProblem p{};
+  p.a1 = CPlanes{(const __half*)a_hi, (const __half*)a_lo, K};
+  p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
+  p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
+  p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
+  int rc = backend == 1 ? launch_gemm_simt(p, (cudaStream_t)stream) : launch_gemm_tc_plain(p, (cudaStream_t)stream);
+  return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
+}
+
+int opb_debug_split(const float* x, void* hi, void* lo, size_t n, void* stream) {
+  split_planes<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)hi, (__half*)lo, (long long)n);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
+}
+
+int opb_debug_read(opb_matcher* m, int32_t which, float* out, size_t cap, int64_t* rows, void* stream) {
+  if (!m || !out) return OPB_E_INVALID;
+  const Layout& L = m->last_layout;
+  if (which == 0) {
+    size_t n = (size_t)L.rows() * kD;
+    if (rows) *rows = L.rows();
+    if (n > cap) return fail(m, OPB_E_INVALID, "debug_read: capacity %zu < %zu", cap, n);
+    join_planes<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->x.hi.as<__half>(), m->x.lo.as<__half>(), out, (long long)n);
+    return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
+  }
+  return fail(m, OPB_E_INVALID, "debug_read: unknown buffer %d", which);
+}
+
+}  // extern "C"

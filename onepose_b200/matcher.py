@@ -1,0 +1,294 @@
+"""Drop-in ``GATsSuperGlue`` for the reference's 2D-3D matching forward.
+
+Mirrors reference ``src/models/GATsSPG_architectures/GATs_SuperGlue.py:143-241``:
+same constructor (``hparams`` mapping), same parameter names / shapes (so a
+reference ``state_dict`` -- or the ``matcher.*`` slice of a Lightning checkpoint
+-- loads verbatim, dead ``kenc_*`` / ``bin_score`` included), same
+``forward(data) -> (pred, conf_matrix)`` contract, including the bare-dict early
+return for empty inputs (:195-203) and ``pred`` = batch element 0 (:232-237).
+
+The arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/onepose_b200.h``; PyTorch only owns device memory and the stream.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+GNN_LAYERS = ["GATs", "self", "cross"] * 4          # GATs_SuperGlue.py:162
+_BACKENDS = {"tcgen05": 0, "simt": 1}
+
+
+class _GATsParams(nn.Module):
+    """Parameter holder of GraphAttentionLayer (reference GATs.py:25-28)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.W = nn.Parameter(torch.empty(dim, dim))
+        nn.init.xavier_normal_(self.W.data, gain=1.414)
+        self.a = nn.Parameter(torch.empty(2 * dim, 1))
+        nn.init.xavier_normal_(self.a.data, gain=1.414)
+
+
+class _AttnParams(nn.Module):
+    """MultiHeadedAttention parameters (GATs_SuperGlue.py:85-91): proj.* start as copies of merge."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.merge = nn.Conv1d(dim, dim, kernel_size=1)
+        self.proj = nn.ModuleList([deepcopy(self.merge) for _ in range(3)])
+
+
+def _mlp_params(channels):
+    """MLP (GATs_SuperGlue.py:116-128): convs sit at Sequential indices 0, 3, 6, ... ."""
+    mods = {}
+    for i in range(1, len(channels)):
+        mods[str(3 * (i - 1))] = nn.Conv1d(channels[i - 1], channels[i], kernel_size=1, bias=True)
+    return nn.ModuleDict(mods)
+
+
+class _PropagationParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.attn = _AttnParams(dim)
+        self.mlp = _mlp_params([2 * dim, 2 * dim, dim])
+        nn.init.constant_(self.mlp["3"].bias, 0.0)              # GATs_SuperGlue.py:109
+
+
+class _KencParams(nn.Module):
+    """Dead at inference (never called in the reference forward) but part of the checkpoint."""
+
+    def __init__(self, inp_dim, feature_dim, layers):
+        super().__init__()
+        chans = [inp_dim] + list(layers) + [feature_dim]
+        self.encoder = _mlp_params(chans)
+        nn.init.constant_(self.encoder[str(3 * (len(chans) - 2))].bias, 0.0)
+
+
+class _GnnParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.layers = nn.ModuleList(
+            [_GATsParams(dim) if i % 3 == 0 else _PropagationParams(dim) for i in range(len(GNN_LAYERS))])
+
+
+class GATsSuperGlue(nn.Module):
+    def __init__(self, hparams, gemm_backend: str = "tcgen05"):
+        super().__init__()
+        self.hparams = hparams
+        self.match_type = hparams["match_type"]
+        d = hparams["descriptor_dim"]
+        self.kenc_2d = _KencParams(3, d, hparams["keypoints_encoder"])
+        self.kenc_3d = _KencParams(4, d, hparams["keypoints_encoder"])
+        self.gnn = _GnnParams(d)
+        self.final_proj = nn.Conv1d(d, d, kernel_size=1, bias=True)
+        self.register_parameter("bin_score", nn.Parameter(torch.tensor(1.0)))
+        if gemm_backend not in _BACKENDS:
+            raise ValueError(f"gemm_backend must be one of {sorted(_BACKENDS)}")
+        self._backend = gemm_backend
+        self._lib = _lib.load()        # raises if the CUDA library is not built
+        self._handle = None
+        self._handle_device = None
+        self._weights_key = None
+        self._object_key = None
+        self._chunk_frames = 0
+        self.last_batched = None       # batched outputs of the last forward (all B frames)
+
+    # ------------------------------------------------------------------ handle / weights
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                self._lib.opb_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _ensure_handle(self, device: torch.device):
+        if self._handle is not None and self._handle_device == device:
+            return
+        if self._handle is not None:
+            self._lib.opb_destroy(self._handle)
+            self._handle = None
+        hp = self.hparams
+        cfg = _lib.OpbConfig(int(hp["descriptor_dim"]), 4, float(hp["scale_factor"]), float(hp["match_threshold"]),
+                             int(bool(hp["include_self"])), int(bool(hp["additional"])),
+                             int(bool(hp["with_linear_transform"])), device.index or 0, _BACKENDS[self._backend])
+        h = C.c_void_p()
+        _lib.check(self._lib.opb_create(C.byref(cfg), C.byref(h)))
+        self._handle, self._handle_device = h, device
+        self._weights_key = self._object_key = None
+        if self._chunk_frames:
+            _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
+
+    def _sync_weights(self):
+        key = tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
+        if key == self._weights_key:
+            return
+        for name, p in self.named_parameters():
+            w = p.detach().to("cpu", torch.float32).contiguous()
+            _lib.check(self._lib.opb_load_weight(self._handle, name.encode(), w.data_ptr(), w.numel()), self._handle)
+        _lib.check(self._lib.opb_finalize_weights(self._handle), self._handle)
+        self._weights_key = key
+        self._object_key = None
+
+    def set_chunk_frames(self, frames: int):
+        """Frames pushed through the GNN together (L2-residency knob of the C ABI)."""
+        self._chunk_frames = int(frames)
+        if self._handle is not None:
+            _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
+
+    # ------------------------------------------------------------------ fast API
+    def set_object(self, descriptors3d_db: torch.Tensor, descriptors2d_db: torch.Tensor):
+        """Upload per-object constants once (what inference.py:113-130 builds per sequence).
+        descriptors3d_db [256, M], descriptors2d_db [256, M*L], CUDA fp32."""
+        d3 = descriptors3d_db.float().contiguous()
+        d2 = descriptors2d_db.float().contiguous()
+        if not d3.is_cuda:
+            raise RuntimeError("onepose_b200 has no CPU path: tensors must be on a CUDA device")
+        self._ensure_handle(d3.device)
+        self._sync_weights()
+        M = d3.shape[1]
+        if M == 0 or d2.shape[1] % M:
+            raise ValueError(f"descriptors2d_db has {d2.shape[1]} columns, not a multiple of M={M}")
+        st = torch.cuda.current_stream(d3.device).cuda_stream
+        _lib.check(self._lib.opb_set_object(self._handle, d3.data_ptr(), d2.data_ptr(), M, d2.shape[1] // M, st),
+                   self._handle)
+        self._M = M
+        self._object_key = None
+
+    def match_frames(self, descriptors2d_query: torch.Tensor, return_conf: bool = True):
+        """B frames of the current object.  descriptors2d_query [B, 256, N] CUDA fp32.
+        Returns dict of batched tensors (matches0 [B,N] int64, ..., conf_matrix [B,N,M] or None)."""
+        q = descriptors2d_query.float().contiguous()
+        B, _, N = q.shape
+        M = self._M
+        dev = q.device
+        m0 = torch.empty(B, N, dtype=torch.int64, device=dev)
+        m1 = torch.empty(B, M, dtype=torch.int64, device=dev)
+        s0 = torch.empty(B, N, dtype=torch.float32, device=dev)
+        s1 = torch.empty(B, M, dtype=torch.float32, device=dev)
+        conf = torch.empty(B, N, M, dtype=torch.float32, device=dev) if return_conf else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self._lib.opb_forward(self._handle, q.data_ptr(), B, N, m0.data_ptr(), m1.data_ptr(), s0.data_ptr(),
+                                         s1.data_ptr(), conf.data_ptr() if conf is not None else None, st), self._handle)
+        return {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1, "conf_matrix": conf}
+
+    def match_frames_host(self, q_host: torch.Tensor, out: dict | None = None):
+        """End-to-end call on HOST buffers (bench.py e2e leg): pinned fp32 [B,256,N] in; matches /
+        scores copied back to pinned host tensors.  conf_matrix is computed on the device and stays
+        there (the reference caller discards it: inference.py:146)."""
+        B, _, N = q_host.shape
+        M = self._M
+        if out is None:
+            pin = dict(pin_memory=True)
+            out = {"matches0": torch.empty(B, N, dtype=torch.int64, **pin), "matches1": torch.empty(B, M, dtype=torch.int64, **pin),
+                   "matching_scores0": torch.empty(B, N, dtype=torch.float32, **pin),
+                   "matching_scores1": torch.empty(B, M, dtype=torch.float32, **pin)}
+        st = torch.cuda.current_stream(self._handle_device).cuda_stream
+        _lib.check(self._lib.opb_forward_host(self._handle, q_host.data_ptr(), B, N, out["matches0"].data_ptr(),
+                                              out["matches1"].data_ptr(), out["matching_scores0"].data_ptr(),
+                                              out["matching_scores1"].data_ptr(), None, st), self._handle)
+        return out
+
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib.opb_set_profiling(self._handle, int(enable)), self._handle)
+
+    def get_profile(self):
+        g, f, t = C.c_double(), C.c_double(), C.c_double()
+        n = C.c_int32()
+        _lib.check(self._lib.opb_get_profile(self._handle, C.byref(g), C.byref(f), C.byref(n), C.byref(t)), self._handle)
+        return {"gemm_ms": g.value, "gemm_flops": f.value, "gemm_launches": n.value, "total_ms": t.value}
+
+    def launch_count(self) -> int:
+        return int(self._lib.opb_last_launch_count(self._handle)) if self._handle is not None else 0
+
+    # ------------------------------------------------------------------ reference contract
+    @staticmethod
+    def _fingerprint(t: torch.Tensor):
+        v = t.reshape(t.shape[0], -1).view(torch.int32)
+        return torch.stack([v.sum(dim=1, dtype=torch.int64), (v[:, ::97].to(torch.int64) * 31).sum(dim=1)], 1)
+
+    @torch.no_grad()
+    def forward(self, data):
+        """Same keys / shapes as the reference (GATs_SuperGlue.py:180-190)."""
+        kpts2d, kpts3d = data["keypoints2d"].float(), data["keypoints3d"].float()
+        desc2d_query = data["descriptors2d_query"].float()
+        desc3d_db, desc2d_db = data["descriptors3d_db"].float(), data["descriptors2d_db"].float()
+
+        if kpts2d.shape[1] == 0 or kpts3d.shape[1] == 0:                  # :195-203 -- bare dict, int32
+            shape0, shape1 = kpts2d.shape[:-1], kpts3d.shape[:-1]
+            return {
+                "matches0": kpts2d.new_full(shape0, -1, dtype=torch.int)[0],
+                "matches1": kpts3d.new_full(shape1, -1, dtype=torch.int)[0],
+                "matching_scores0": kpts2d.new_zeros(shape0)[0],
+                "matching_scores1": kpts3d.new_zeros(shape1)[0],
+                "skip_train": True,
+            }
+        if self.match_type != "softmax":
+            raise NotImplementedError                                     # :238-239
+        if not desc2d_query.is_cuda:
+            raise RuntimeError("onepose_b200 has no CPU path: move the module and its inputs to a CUDA device")
+
+        B = desc2d_query.shape[0]
+        self._ensure_handle(desc2d_query.device)
+        self._sync_weights()
+        # per-object constants are re-sent by the caller every frame (inference.py:80-94); detect
+        # "same object as last call" by content so that they are packed once.
+        fp = torch.cat([self._fingerprint(desc3d_db), self._fingerprint(desc2d_db)], 1).cpu()
+        groups = []                                                       # runs of frames sharing an object
+        for b in range(B):
+            if groups and torch.equal(fp[b], fp[groups[-1][0]]):
+                groups[-1].append(b)
+            else:
+                groups.append([b])
+        outs = []
+        for g in groups:
+            key = (tuple(fp[g[0]].tolist()), tuple(desc3d_db.shape[1:]), tuple(desc2d_db.shape[1:]))
+            if key != self._object_key:
+                self.set_object(desc3d_db[g[0]], desc2d_db[g[0]])
+                self._object_key = key
+            outs.append(self.match_frames(desc2d_query[g[0]:g[-1] + 1]))
+        out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+        self.last_batched = out
+        pred = {
+            "matches0": out["matches0"][0],                               # :232-237: element 0 only
+            "matches1": out["matches1"][0],
+            "matching_scores0": out["matching_scores0"][0],
+            "matching_scores1": out["matching_scores1"][0],
+        }
+        return pred, out["conf_matrix"]
+
+
+class LitModelGATsSPG(nn.Module):
+    """Stand-in for the reference's Lightning wrapper (src/models/GATsSPG_lightning_model.py:15-37):
+    ``forward(x) = self.matcher(x)`` and a ``load_from_checkpoint`` that reads a Lightning ``.ckpt``
+    (``state_dict`` with ``matcher.*`` / ``extractor.*`` keys + ``hyper_parameters``) without
+    pytorch_lightning.  Training / validation steps are out of scope."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.hparams = dict(kwargs)
+        self.matcher = GATsSuperGlue(hparams=self.hparams)
+
+    def forward(self, x):
+        return self.matcher(x)
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        return self.eval()
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        model = cls(**hp)
+        sd = {k[len("matcher."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("matcher.")}
+        model.matcher.load_state_dict(sd, strict=True)
+        return model

@@ -115,8 +115,19 @@ def mean_desc_case():
     print("mean_descriptors:", avg.shape, avg.dtype)
 
 
+def state_dict_spec():
+    """Key names / shapes of the reference module's state dict (load_state_dict compatibility)."""
+    import json
+    m = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS))
+    spec = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_spec.json"), "w") as f:
+        json.dump(spec, f, indent=0)
+    print("state_dict_spec:", len(spec), "keys")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    state_dict_spec()
     for c in CASES:
         run_case(c)
     empty_case()

@@ -1,0 +1,91 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the module is
+state-dict compatible with the reference, host logic that needs no GPU."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from onepose_b200 import GATsSuperGlue, LitModelGATsSPG, _lib, synthetic
+from tests.golden_util import GOLDEN_DIR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "onepose_b200.h")).read()
+    declared = set(re.findall(r"\b(opb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_config_struct_matches_header():
+    header = open(os.path.join(ROOT, "include", "onepose_b200.h")).read()
+    body = re.search(r"typedef struct opb_config \{(.*?)\} opb_config;", header, re.S).group(1)
+    fields = re.findall(r"(?:int32_t|float)\s+(\w+);", body)
+    assert fields == [f[0] for f in _lib.OpbConfig._fields_]
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    lib = _lib.load()
+    cfg = _lib.OpbConfig(256, 4, 0.07, 0.2, 1, 0, 0, 0, 0)
+    h = C.c_void_p()
+    rc = lib.opb_create(C.byref(cfg), C.byref(h))
+    assert rc == -2 and b"no CPU path" in lib.opb_last_error(None)
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    spec = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_spec.json")))
+    m = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS))
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(spec.keys())
+    for k, shape in spec.items():
+        assert list(sd[k].shape) == shape, k
+    # the seeded synthetic state dict (reference key names) loads strictly
+    syn = synthetic.make_state_dict(0)
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in syn.items()}, strict=True)
+
+
+def test_empty_input_returns_reference_style_dict():
+    g = np.load(os.path.join(GOLDEN_DIR, "empty_n0_m96.npz"))
+    m = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS))
+    data = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(1, [11], 0, 96, 8).items()}
+    out = m(data)
+    assert isinstance(out, dict) and sorted(out.keys()) == list(g["keys"])
+    assert out["matches0"].dtype == torch.int32 and tuple(out["matches1"].shape) == g["matches1"].shape
+    assert (out["matches1"].numpy() == g["matches1"]).all() and out["skip_train"] is True
+
+
+def test_cpu_tensors_are_rejected():
+    m = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS))
+    data = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(1, [11], 16, 32, 8).items()}
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(data)
+
+
+def test_unsupported_match_type():
+    hp = dict(synthetic.DEFAULT_HPARAMS, match_type="sinkhorn")
+    m = GATsSuperGlue(hp)
+    data = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(1, [11], 16, 32, 8).items()}
+    with pytest.raises(NotImplementedError):
+        m(data)
+
+
+def test_lightning_checkpoint_standin(tmp_path):
+    hp = dict(synthetic.DEFAULT_HPARAMS, lr=1e-3)
+    syn = synthetic.make_state_dict(3)
+    ckpt = {"state_dict": {"matcher." + k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in syn.items()},
+            "hyper_parameters": hp}
+    ckpt["state_dict"]["extractor.conv1a.weight"] = torch.zeros(1)
+    path = tmp_path / "GATsSPG.ckpt"
+    torch.save(ckpt, path)
+    model = LitModelGATsSPG.load_from_checkpoint(str(path)).eval().freeze()
+    assert torch.equal(model.matcher.final_proj.weight, torch.from_numpy(syn["final_proj.weight"]))
+    assert not any(p.requires_grad for p in model.parameters())
