@@ -88,6 +88,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def cpu_threads():
+    """Threads for the CPU arm: all logical CPUs up to 32.  (Measured on the GPU box, 2x Xeon 8562Y+,
+    128 logical CPUs: torch's CPU backend is >10x SLOWER at 128 threads than at 32 on this op mix --
+    hyper-threads + two NUMA nodes -- so 'all it can use' is capped where it stops helping.)"""
+    return min(os.cpu_count() or 1, int(os.environ.get("OPB_CPU_THREADS", "32")))
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -103,7 +110,7 @@ def time_cpu_port(frames_budget_s, max_frames, n_warm=1):
     convention, inference.py:85-92), all host threads.  Returns (frames/s, per-frame seconds list)."""
     from onepose_b200 import synthetic
     from oracle import gats_spg_oracle as oracle
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     sd = synthetic.make_state_dict(0)
     P = oracle.params_from_numpy(sd)
     hp = synthetic.DEFAULT_HPARAMS
@@ -136,7 +143,7 @@ def run_reference(args, rank, world):
     per_step = []
     from onepose_b200 import synthetic
     from oracle import gats_spg_oracle as oracle
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     sd = synthetic.make_state_dict(0)
     P = oracle.params_from_numpy(sd)
     hp = synthetic.DEFAULT_HPARAMS
@@ -163,8 +170,8 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "GATsSPG forward, N2D=1024 N3D=7000 L=8 D=256, 1 frame per step (B=1, reference calling convention)",
                    "frames_per_step": 1},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{args.steps} single-frame forwards of the oracle port (torch CPU fp32, all threads), cpu={cpu_model()}"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": f"{args.steps} single-frame forwards of the oracle port (torch CPU fp32, {cpu_threads()} threads of {os.cpu_count()} logical CPUs), cpu={cpu_model()}"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -315,9 +322,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cpu_fps, times = time_cpu_port(frames_budget_s=20.0, max_frames=8)
-            line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                                     "sample": f"{len(times)} single-frame forwards (B=1) of the oracle port at the same shape, torch CPU fp32, "
-                                              f"{os.cpu_count()} threads, median; cpu={cpu_model()}"}
+                                              f"{cpu_threads()} threads of {os.cpu_count()} logical CPUs, median; cpu={cpu_model()}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

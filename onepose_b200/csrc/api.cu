@@ -462,7 +462,7 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
     return fail(m, OPB_E_INVALID, "set_object: need M > 0 and 1 <= num_leaf <= 32 (got M=%d, L=%d)", M, Lf);
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int m_pad = round_up(M, kTileRows);
+  const int m_pad = round_up(M, 256);   // the 3D side is the N dimension (256-wide tiles) of the score GEMM
   if (m_pad != m->m_pad) { m->ws_frames = 0; m->ws_N = 0; }  // workspace depends on m_pad
   m->M = M; m->Lf = Lf; m->m_pad = m_pad;
   const long long n_leaf_rows = (long long)M * Lf;

@@ -165,7 +165,7 @@ def test_gemm_cores_agree_and_match_fp64():
     from onepose_b200 import _lib
     lib = _lib.load()
     rs = np.random.RandomState(0)
-    for rows, n_out, K in [(128, 128, 64), (256, 256, 256), (384, 768, 256), (256, 512, 512), (1024, 7040, 256)]:
+    for rows, n_out, K in [(128, 256, 64), (256, 256, 256), (384, 768, 256), (256, 512, 512), (1024, 7168, 256)]:
         a = torch.from_numpy((rs.randn(rows, K) * np.exp(rs.randn(rows, 1))).astype(np.float32)).cuda()
         b = torch.from_numpy((rs.randn(n_out, K) / np.sqrt(K)).astype(np.float32)).cuda()
         planes = [torch.empty_like(a, dtype=torch.float16) for _ in range(2)] + [torch.empty_like(b, dtype=torch.float16) for _ in range(2)]
