@@ -123,12 +123,7 @@ int fail(opb_matcher* m, int code, const char* fmt, ...) {
 static void split_host(const std::vector<double>& w, std::vector<__half>& hi, std::vector<__half>& lo) {
   hi.resize(w.size());
   lo.resize(w.size());
-  for (size_t i = 0; i < w.size(); ++i) {
-    float x = (float)w[i];
-    __half h = __float2half_rn(x);
-    hi[i] = h;
-    lo[i] = __float2half_rn((x - __half2float(h)) * kLoScale);
-  }
+  for (size_t i = 0; i < w.size(); ++i) split_f32((float)w[i], hi[i], lo[i]);
 }
 
 static int upload_planes(opb_matcher* m, PlaneBuf& dst, const std::vector<double>& w) {
@@ -186,7 +181,6 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   const size_t R = (size_t)n_pad + m->m_pad;
   const size_t rows = R * frames;
   const size_t S = 2 * (size_t)frames;
-  const int max_slabs = (std::max(n_pad, m->m_pad) + kSlabRows - 1) / kSlabRows;
   CK(m, m->x.ensure(rows * kD, true));
   CK(m, m->qp.ensure(rows * kD, true));
   CK(m, m->hn.ensure(rows * 512, true));
@@ -194,7 +188,7 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->g.ensure(S * 512 * kD));
   CK(m, m->c768.ensure(rows * 768 * sizeof(float)));
   CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
-  CK(m, m->kvpart.ensure(S * kHeads * max_slabs * kKVPartial * sizeof(float)));
+  CK(m, m->kvpart.ensure(rows / kTileRows * kHeads * kKVPartial * sizeof(float)));
   CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
   CK(m, m->statpart.ensure(rows / kTileRows * 512 * 2 * sizeof(float)));
@@ -220,7 +214,6 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   const int rows = L.rows();
   const int S = L.segs();
   const int tiles = rows / kTileRows;
-  const int max_slabs = (std::max(L.n_pad, L.m_pad) + kSlabRows - 1) / kSlabRows;
   const double valid_rows = (double)fb * (N + L.M);
   __half *xh = m->x.hi.as<__half>(), *xl = m->x.lo.as<__half>();
   auto launched = [&]() { m->launches++; };
@@ -251,16 +244,16 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
     if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
     // (2) linear-attention state of every segment (:71-78)
-    kv_state_partial<<<dim3(max_slabs, kHeads, S), 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, L, max_slabs, m->kvpart.as<float>());
+    kv_state_partial<<<dim3(tiles, kHeads), 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, L, m->kvpart.as<float>());
     launched();
-    kv_state_reduce<<<S * kHeads, 256, 0, st>>>(m->kvpart.as<float>(), L, max_slabs, m->kvmean.as<float>(), m->kmean.as<float>());
+    kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
     launched();
     // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
     q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
                                                                                   m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
     launched();
     // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
-    g_fold<<<dim3(512 / 32, S), 256, (kHeads * kDh * kDh + kD) * sizeof(float), st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross,
+    g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross,
                                                                                      m->g.hi.as<__half>(), m->g.lo.as<__half>());
     launched();
     // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
@@ -273,7 +266,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     // (6) InstanceNorm statistics per segment (:126)
     in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
     launched();
-    in_stats_final<<<dim3(S, 2), 256, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+    in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
     launched();
     norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                     m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
@@ -306,7 +299,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   const float inv_scale = 1.f / m->cfg.scale_factor;
   score_row_sums<<<(unsigned)(((long long)fb * N * 32 + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>());
   launched();
-  score_col_sums<<<(unsigned)(((long long)fb * L.M + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
+  score_col_sums<<<dim3((L.M + 31) / 32, fb), dim3(32, 8), 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
   launched();
   CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
   CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
@@ -343,8 +336,6 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   if (prop.major != 10) return fail(nullptr, OPB_E_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
-  e = cudaFuncSetAttribute(g_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kHeads * kDh * kDh + kD) * sizeof(float)));
-  if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaFuncSetAttribute(g_fold): %s", cudaGetErrorString(e));
   auto* m = new opb_matcher();
   m->cfg = *cfg;
   *out = m;
@@ -589,6 +580,17 @@ int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const v
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
   int rc = backend == 1 ? launch_gemm_simt(p, (cudaStream_t)stream) : launch_gemm_tc_plain(p, (cudaStream_t)stream);
+  return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
+}
+
+int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out,
+                            int32_t K, long long* timeline, void* stream) {
+  GemmProblem p{};
+  p.a1 = CPlanes{(const __half*)a_hi, (const __half*)a_lo, K};
+  p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
+  p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
+  p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
+  int rc = launch_gemm_tc_plain(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 

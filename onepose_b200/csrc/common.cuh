@@ -10,8 +10,13 @@ constexpr int kD = 256;        // descriptor_dim
 constexpr int kHeads = 4;
 constexpr int kDh = 64;        // per-head dim
 constexpr int kTileRows = 128; // row tile of every GEMM; segments are padded to it
-constexpr float kLoScale = 2048.0f;          // lo plane carries (x - hi) * 2^11
-constexpr float kLoInv = 1.0f / 2048.0f;
+// fp16-split operand format: every plane pair carries a fixed 2^6 pre-scale,
+//   hi = fp16(64 x),  lo = fp16(64 x - hi)      =>  x = (hi + lo) / 64  to ~2^-22 relative
+// (the pre-scale keeps `lo` out of the fp16 subnormal range for |x| > ~2e-3; |x| < 1023 is
+// representable).  A product of two such operands carries 2^12, removed in the GEMM epilogue.
+constexpr float kPre = 64.0f;
+constexpr float kPreInv = 1.0f / 64.0f;
+constexpr float kProdInv = 1.0f / 4096.0f;
 constexpr float kHalfMax = 65504.0f;
 
 // Activation layout of one forward chunk: frame b owns rows
@@ -38,13 +43,13 @@ struct Layout {
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// fp32 -> (hi, lo) fp16 planes; x ~= hi + lo * 2^-11 to ~2^-22 relative.
-__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
+__host__ __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+  const float xs = x * kPre;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
 }
-__device__ __forceinline__ float join_f32(__half hi, __half lo) {
-  return fmaf(__half2float(lo), kLoInv, __half2float(hi));
+__host__ __device__ __forceinline__ float join_f32(__half hi, __half lo) {
+  return (__half2float(hi) + __half2float(lo)) * kPreInv;
 }
 // elu(x) + 1  (reference GATs_SuperGlue.py:71-72)
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : expf(x); }

@@ -22,6 +22,7 @@ struct GemmProblem {
   long long a_batch_rows, b_batch_rows, c_batch_elems;
   Layout L;
   const float* bias;     // [n_out] or nullptr
+  int elu_cols;          // output columns [0, elu_cols) get elu(x)+1 after the bias
   float* c;              // fp32 [rows, ldc]
   int ldc;
 };

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem p) {
       if (p.bias) {
         o.x += p.bias[c]; o.y += p.bias[c + 1]; o.z += p.bias[c + 2]; o.w += p.bias[c + 3];
       }
+      if (c < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
       *reinterpret_cast<float4*>(cz + (long long)r * p.ldc + c) = o;
     }
   }

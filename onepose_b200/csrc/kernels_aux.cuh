@@ -181,36 +181,30 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
 // Stage 1: block = (slab of kSlabRows rows, head, segment) -> partial sums (deterministic);
 // Stage 2: fixed-order reduction over slabs and the 1/m scale.
 // ---------------------------------------------------------------------------------------
-constexpr int kSlabRows = 1024;
 constexpr int kKVPartial = kDh * kDh + kDh;  // 64x64 KV + 64 Ksum
 
-__global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L, int max_slabs,
+// grid (row tiles, heads), block 256: one 128-row tile x one head -> partial[tile][h][4160]
+__global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
                                                         float* __restrict__ partial) {
-  const int slab = blockIdx.x, h = blockIdx.y, seg = blockIdx.z;
-  const int valid = L.seg_valid(seg);
-  const int r_begin = slab * kSlabRows;
-  float* out = partial + (((long long)seg * kHeads + h) * max_slabs + slab) * kKVPartial;
+  const int tile = blockIdx.x, h = blockIdx.y;
+  const int row0 = tile * kTileRows;
+  const int seg = L.seg_of_row(row0);
+  const int n_valid = min(kTileRows, L.seg_valid(seg) - (row0 - L.seg_start(seg)));   // >= 1 by construction, may be <= 0 for all-pad tiles
+  float* out = partial + ((long long)tile * kHeads + h) * kKVPartial;
   const int tid = threadIdx.x;
-  if (r_begin >= valid) {  // empty slab: still define the partial
-    for (int i = tid; i < kKVPartial; i += 256) out[i] = 0.f;
-    return;
-  }
-  const int r_end = min(valid, r_begin + kSlabRows);
   __shared__ float sK[32][kDh + 1];
   __shared__ float sV[32][kDh];
   const int d0 = (tid >> 4) * 4;   // 16x16 threads, 4x4 outputs each
   const int q0 = (tid & 15) * 4;
   float acc[4][4] = {};
   float ksum = 0.f;  // threads 0..63: column d = tid
-  const long long base = (long long)L.seg_start(seg);
-  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
-    // load 32 rows x 64 of K and V for this head
+  for (int r0 = 0; r0 < n_valid; r0 += 32) {
     for (int i = tid; i < 32 * kDh; i += 256) {
       int rr = i >> 6, c = i & 63;
       int r = r0 + rr;
       float kval = 0.f, vval = 0.f;
-      if (r < r_end) {
-        const float* rowp = kv + (base + r) * ld;
+      if (r < n_valid) {
+        const float* rowp = kv + (long long)(row0 + r) * ld;
         kval = elu1(rowp[k_off + h * kDh + c]);
         vval = rowp[v_off + h * kDh + c];
       }
@@ -241,21 +235,20 @@ __global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict_
   if (tid < kDh) out[kDh * kDh + tid] = ksum;
 }
 
-// grid (S*H), block 256
-__global__ void kv_state_reduce(const float* __restrict__ partial, Layout L, int max_slabs,
+// grid (S*H, 17), block 256: fixed-order sum over the segment's tiles, scaled by 1/m
+__global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
                                 float* __restrict__ kvmean /*[S][H][64][64]*/, float* __restrict__ kmean /*[S][H][64]*/) {
   const int sh = blockIdx.x;
-  const int seg = sh / kHeads;
-  const int valid = L.seg_valid(seg);
-  const int n_slabs = (valid + kSlabRows - 1) / kSlabRows;
-  const float inv_m = 1.f / (float)valid;
-  for (int i = threadIdx.x; i < kKVPartial; i += blockDim.x) {
-    float s = 0.f;
-    for (int sl = 0; sl < n_slabs; ++sl) s += partial[((long long)sh * max_slabs + sl) * kKVPartial + i];
-    s *= inv_m;
-    if (i < kDh * kDh) kvmean[(long long)sh * kDh * kDh + i] = s;
-    else kmean[(long long)sh * kDh + (i - kDh * kDh)] = s;
-  }
+  const int seg = sh / kHeads, h = sh % kHeads;
+  const int i = blockIdx.y * 256 + threadIdx.x;
+  if (i >= kKVPartial) return;
+  const int t0 = L.seg_start(seg) / kTileRows;
+  const int nt = (L.seg_valid(seg) + kTileRows - 1) / kTileRows;
+  float s = 0.f;
+  for (int t = 0; t < nt; ++t) s += partial[((long long)(t0 + t) * kHeads + h) * kKVPartial + i];
+  s *= 1.f / (float)L.seg_valid(seg);
+  if (i < kDh * kDh) kvmean[(long long)sh * kDh * kDh + i] = s;
+  else kmean[(long long)sh * kDh + (i - kDh * kDh)] = s;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -300,35 +293,43 @@ __global__ void q_scale_split(const float* __restrict__ q, int ldq, Layout L, in
 // Dynamic weight  G[s][c][h*64+d] = sum_q KVmean[src(s)][h][d][q] * W0m[c][h*64+q]
 // where W0m = mlp.0.weight[:, 256:] @ merge.weight (folded on the host), so that
 //   mlp.0([x ; merge(msg)]) = W0a x + G (Q')  + b   (GATs_SuperGlue.py:101,113,122).
-// grid (512/32, S), block 256 (thread = output column k = h*64+d). Output fp16-split planes.
+// Output fp16-split planes [S][512][256].
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) g_fold(const float* __restrict__ kvmean, const float* __restrict__ w0m /*[512][256]*/,
                                               Layout L, int cross, __half* __restrict__ g_hi, __half* __restrict__ g_lo) {
-  extern __shared__ float smem[];
-  float* sKVt = smem;                       // [h][q][d]  4*64*64
-  float* sW = smem + kHeads * kDh * kDh;    // [256]
-  const int seg = blockIdx.y;
+  // grid (512/64 c-chunks, heads, S); block 256 = 16x16 threads, 4(c) x 4(d) outputs each
+  __shared__ __align__(16) float sKVt[kDh][kDh + 4];   // [q][d]
+  __shared__ __align__(16) float sWt[kDh][kDh + 4];    // [q][c]
+  const int c0 = blockIdx.x * 64, h = blockIdx.y, seg = blockIdx.z;
   const int src = L.src_seg(seg, cross);
   const int tid = threadIdx.x;
-  const float* kvs = kvmean + (long long)src * kHeads * kDh * kDh;
-  for (int i = tid; i < kHeads * kDh * kDh; i += 256) {
-    int h = i >> 12, d = (i >> 6) & 63, qq = i & 63;
-    sKVt[(h * kDh + qq) * kDh + d] = kvs[i];
+  const float* kvs = kvmean + ((long long)src * kHeads + h) * kDh * kDh;   // [d][q]
+  for (int i = tid; i < kDh * kDh; i += 256) {
+    int a = i >> 6, b = i & 63;
+    sKVt[b][a] = kvs[i];                                        // (d=a, q=b)
+    sWt[b][a] = w0m[(long long)(c0 + a) * kD + h * kDh + b];    // (c=a, q=b)
   }
-  const int h = tid >> 6, d = tid & 63;
-  for (int cc = 0; cc < 32; ++cc) {
-    const int c = blockIdx.x * 32 + cc;
-    __syncthreads();
-    sW[tid] = w0m[(long long)c * kD + tid];
-    __syncthreads();
-    float acc = 0.f;
-#pragma unroll 16
-    for (int qq = 0; qq < kDh; ++qq) acc = fmaf(sKVt[(h * kDh + qq) * kDh + d], sW[h * kDh + qq], acc);
-    __half hh, ll;
-    split_f32(acc, hh, ll);
-    long long o = ((long long)seg * 512 + c) * kD + tid;
-    g_hi[o] = hh;
-    g_lo[o] = ll;
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4] = {};
+#pragma unroll 8
+  for (int q = 0; q < kDh; ++q) {
+    const float4 w = *reinterpret_cast<const float4*>(&sWt[q][ty * 4]);
+    const float4 k = *reinterpret_cast<const float4*>(&sKVt[q][tx * 4]);
+    const float wv[4] = {w.x, w.y, w.z, w.w}, kv4[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(wv[a], kv4[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const long long o = ((long long)seg * 512 + c0 + ty * 4 + a) * kD + h * kDh + tx * 4;
+    __half hh[4], ll[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) split_f32(acc[a][b], hh[b], ll[b]);
+    *reinterpret_cast<uint2*>(g_hi + o) = *reinterpret_cast<uint2*>(hh);
+    *reinterpret_cast<uint2*>(g_lo + o) = *reinterpret_cast<uint2*>(ll);
   }
 }
 
@@ -354,12 +355,12 @@ __global__ void in_stats_partial(const float* __restrict__ hid /*[rows,512]*/, L
   part[((long long)tile * 512 + c) * 2 + 1] = s2;
 }
 
-// grid (S, 2), block 256
+// grid (S, 8), block 64
 __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* __restrict__ mu, float* __restrict__ rstd) {
   const int seg = blockIdx.x;
-  const int c = blockIdx.y * 256 + threadIdx.x;
+  const int c = blockIdx.y * 64 + threadIdx.x;
   const int t0 = L.seg_start(seg) / kTileRows;
-  const int nt = L.seg_padded(seg) / kTileRows;
+  const int nt = (L.seg_valid(seg) + kTileRows - 1) / kTileRows;
   double s = 0.0, s2 = 0.0;
   for (int t = 0; t < nt; ++t) {
     s += (double)part[((long long)(t0 + t) * 512 + c) * 2 + 0];
@@ -474,15 +475,24 @@ __global__ void score_row_sums(const float* __restrict__ s, Layout L, float inv_
   acc = warp_sum(acc);
   if (lane == 0) rowsum[b * L.n_pad + n] = acc;
 }
-// Column sums: thread per (b, m), loop over n (coalesced across m).
+// Column sums: block = 32 columns x 8 row-groups (coalesced 128 B per warp-row), fixed-order combine.
+// grid (ceil(M/32), B), block (32, 8)
 __global__ void score_col_sums(const float* __restrict__ s, Layout L, float inv_scale, float* __restrict__ colsum /*[B][m_pad]*/) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)L.B * L.M) return;
-  const int b = (int)(idx / L.M), m = (int)(idx % L.M);
+  __shared__ float part[8][33];
+  const int b = blockIdx.y;
+  const int m = blockIdx.x * 32 + threadIdx.x;
   const float* col = s + (long long)b * L.n_pad * L.m_pad + m;
   float acc = 0.f;
-  for (int n = 0; n < L.N; ++n) acc += expf((col[(long long)n * L.m_pad] - 1.f) * inv_scale);
-  colsum[b * L.m_pad + m] = acc;
+  if (m < L.M)
+    for (int n = threadIdx.y; n < L.N; n += 8) acc += expf((col[(long long)n * L.m_pad] - 1.f) * inv_scale);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && m < L.M) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+    colsum[b * L.m_pad + m] = t;
+  }
 }
 
 // order-preserving pack of (positive float value, index) with lowest-index-wins ties

@@ -178,8 +178,8 @@ def test_gemm_cores_agree_and_match_fp64():
             assert rc == 0, (backend, rc)
             torch.cuda.synchronize()
             outs.append(c.cpu().double())
-        ah = planes[0].cpu().double() + planes[1].cpu().double() / 2048.0
-        bh = planes[2].cpu().double() + planes[3].cpu().double() / 2048.0
+        ah = (planes[0].cpu().double() + planes[1].cpu().double()) / 64.0
+        bh = (planes[2].cpu().double() + planes[3].cpu().double()) / 64.0
         ref = ah @ bh.T
         scale = float(ref.abs().max())
         e_tc = float((outs[0] - ref).abs().max()) / scale
