@@ -244,7 +244,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
     if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
     // (2) linear-attention state of every segment (:71-78)
-    kv_state_partial<<<dim3(tiles, kHeads), 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, L, m->kvpart.as<float>());
+    kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
     launched();
     kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
     launched();
@@ -584,13 +584,13 @@ int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const v
 }
 
 int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out,
-                            int32_t K, long long* timeline, void* stream) {
+                            int32_t K, long long* timeline, int32_t dbg, void* stream) {
   GemmProblem p{};
   p.a1 = CPlanes{(const __half*)a_hi, (const __half*)a_lo, K};
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  int rc = launch_gemm_tc_plain(p, (cudaStream_t)stream, timeline);
+  int rc = launch_gemm_tc_plain(p, (cudaStream_t)stream, timeline, dbg);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 

@@ -138,6 +138,7 @@ struct TcParams {
   const float* bias;
   int elu_cols;          // columns [0, elu_cols) get elu(x)+1 after the bias (K projection)
   long long* tl;         // optional timeline buffer (debug)
+  int dbg;               // debug variants (timeline tool): 1 = skip the TMA store, 2 = skip staging writes too
 };
 
 struct Maps {
@@ -262,13 +263,18 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
         uint32_t v[32];
+        const bool stamp = tl && leader && tc == 1 && c0 < 128;
+        if (stamp) tl[3 + (c0 >> 5) * 4] = clock64();
         tmem_ld32(lane_base + c0, v);
         tmem_ld_wait();
+        if (stamp) tl[4 + (c0 >> 5) * 4] = clock64();
         const int col0 = n_tile * BN + c0;
         uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
         // the TMA store that last read this staging buffer (2 chunks ago) must have finished reading
         if (leader) tma_store_wait_read<1>();
         epi_bar();
+        if (stamp) tl[5 + (c0 >> 5) * 4] = clock64();
+        if (!(p.dbg & 2)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
@@ -283,9 +289,11 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           if (col0 < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
           *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = o;
         }
+        }
         fence_async_smem();
         epi_bar();
-        if (leader) {
+        if (stamp) tl[6 + (c0 >> 5) * 4] = clock64();
+        if (leader && !(p.dbg & 1)) {
           tma_store_2d(&maps.out_f32, sb, col0, out_row0);
           tma_store_commit();
         }
@@ -358,7 +366,7 @@ int num_sms() {
 
 }  // namespace
 
-int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
+int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline, int dbg) {
   if (p.rows % BM || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.ldc % 4) return -1;
   if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
   static bool attr_done = false;
@@ -384,7 +392,7 @@ int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* t
   tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
-  tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline;
+  tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline; tp.dbg = dbg;
   const int total = tp.m_tiles * tp.n_tiles * tp.batch;
   const int grid = total < num_sms() ? total : num_sms();
   gemm_tc_kernel<<<grid, 256, kSmemBytes, stream>>>(mp, tp);

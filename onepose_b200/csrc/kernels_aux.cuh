@@ -183,56 +183,65 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
 // ---------------------------------------------------------------------------------------
 constexpr int kKVPartial = kDh * kDh + kDh;  // 64x64 KV + 64 Ksum
 
-// grid (row tiles, heads), block 256: one 128-row tile x one head -> partial[tile][h][4160]
-__global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
-                                                        float* __restrict__ partial) {
-  const int tile = blockIdx.x, h = blockIdx.y;
+// grid (row tiles), block 256 = 4 heads x (8 x 8 threads, 8(d) x 8(q) outputs each): one 128-row tile
+// -> partial[tile][h][64*64 + 64].  `k_activated`: K already holds elu(k)+1 (fused GEMM epilogue).
+__global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated,
+                                                        Layout L, float* __restrict__ partial) {
+  const int tile = blockIdx.x;
   const int row0 = tile * kTileRows;
   const int seg = L.seg_of_row(row0);
-  const int n_valid = min(kTileRows, L.seg_valid(seg) - (row0 - L.seg_start(seg)));   // >= 1 by construction, may be <= 0 for all-pad tiles
-  float* out = partial + ((long long)tile * kHeads + h) * kKVPartial;
+  const int n_valid = min(kTileRows, L.seg_valid(seg) - (row0 - L.seg_start(seg)));   // <= 0 for all-pad tiles
   const int tid = threadIdx.x;
-  __shared__ float sK[32][kDh + 1];
-  __shared__ float sV[32][kDh];
-  const int d0 = (tid >> 4) * 4;   // 16x16 threads, 4x4 outputs each
-  const int q0 = (tid & 15) * 4;
-  float acc[4][4] = {};
-  float ksum = 0.f;  // threads 0..63: column d = tid
-  for (int r0 = 0; r0 < n_valid; r0 += 32) {
-    for (int i = tid; i < 32 * kDh; i += 256) {
-      int rr = i >> 6, c = i & 63;
-      int r = r0 + rr;
-      float kval = 0.f, vval = 0.f;
-      if (r < n_valid) {
-        const float* rowp = kv + (long long)(row0 + r) * ld;
-        kval = elu1(rowp[k_off + h * kDh + c]);
-        vval = rowp[v_off + h * kDh + c];
+  const int h = tid >> 6, ty = (tid >> 3) & 7, tx = tid & 7;
+  __shared__ __align__(16) float sK[16][kD];
+  __shared__ __align__(16) float sV[16][kD];
+  float acc[8][8] = {};
+  float ks[8] = {};
+  for (int r0 = 0; r0 < n_valid; r0 += 16) {
+    // 16 rows x 256 K and V values: thread loads 4 float4 of each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;          // 0..1023 float4 slots
+      const int rr = idx >> 6, c4 = (idx & 63) * 4;
+      float4 kq = make_float4(0.f, 0.f, 0.f, 0.f), vq = kq;
+      if (r0 + rr < n_valid) {
+        const float* rowp = kv + (long long)(row0 + r0 + rr) * ld;
+        kq = *reinterpret_cast<const float4*>(rowp + k_off + c4);
+        vq = *reinterpret_cast<const float4*>(rowp + v_off + c4);
+        if (!k_activated) { kq.x = elu1(kq.x); kq.y = elu1(kq.y); kq.z = elu1(kq.z); kq.w = elu1(kq.w); }
       }
-      sK[rr][c] = kval;
-      sV[rr][c] = vval;
+      *reinterpret_cast<float4*>(&sK[rr][c4]) = kq;
+      *reinterpret_cast<float4*>(&sV[rr][c4]) = vq;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-      float kk[4], vv[4];
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 k0 = *reinterpret_cast<const float4*>(&sK[rr][h * kDh + ty * 8]);
+      const float4 k1 = *reinterpret_cast<const float4*>(&sK[rr][h * kDh + ty * 8 + 4]);
+      const float4 v0 = *reinterpret_cast<const float4*>(&sV[rr][h * kDh + tx * 8]);
+      const float4 v1 = *reinterpret_cast<const float4*>(&sV[rr][h * kDh + tx * 8 + 4]);
+      const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { kk[a] = sK[rr][d0 + a]; vv[a] = sV[rr][q0 + a]; }
+      for (int a = 0; a < 8; ++a) {
+        ks[a] += kk[a];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(kk[a], vv[c], acc[a][c]);
-    }
-    if (tid < kDh) {
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) ksum += sK[rr][tid];
+        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(kk[a], vv[c], acc[a][c]);
+      }
     }
     __syncthreads();
   }
+  float* out = partial + ((long long)tile * kHeads + h) * kKVPartial;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a) {
+    float* o = out + (ty * 8 + a) * kDh + tx * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+  }
+  if (tx == 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[(d0 + a) * kDh + q0 + c] = acc[a][c];
-  if (tid < kDh) out[kDh * kDh + tid] = ksum;
+    for (int a = 0; a < 8; ++a) out[kDh * kDh + ty * 8 + a] = ks[a];
+  }
 }
 
 // grid (S*H, 17), block 256: fixed-order sum over the segment's tiles, scaled by 1/m

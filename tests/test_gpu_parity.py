@@ -185,7 +185,8 @@ def test_gemm_cores_agree_and_match_fp64():
         e_tc = float((outs[0] - ref).abs().max()) / scale
         e_simt = float((outs[1] - ref).abs().max()) / scale
         print(f"gemm {rows}x{n_out}x{K}: rel err tcgen05 {e_tc:.2e}, simt {e_simt:.2e}")
-        assert e_simt < 2e-6 and e_tc < 2e-6
+        # the tensor core truncates (does not round) its fp32 accumulator: ~2^-25 relative per accumulation step
+        assert e_simt < 2e-6 and e_tc < 2e-6 + 1.2e-8 * K
         # the split itself represents fp32 to ~2^-22
         assert float((ah.float() - a.cpu()).abs().max() / a.abs().max()) < 2.0 ** -21
 
