@@ -16,6 +16,8 @@
 //   warps 4-7 epilogue       tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -25,15 +27,24 @@
 namespace opb {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;       // BK fp16 = 128 B = one SWIZZLE_128B row
+constexpr int BM = 128, BN = 256;
 constexpr int UMMA_K = 16;
-constexpr int kStages = 2;
-constexpr int kABytes = BM * BK * 2;             // 16 KB
-constexpr int kBBytes = BN * BK * 2;             // 32 KB
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
 constexpr int kStagingBytes = 16384;             // one 128-row x 128-B swizzled epilogue buffer
 constexpr int kNumStaging = 2;
-constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kMaxStages = 4;
+// K-block configuration: BK fp16 per smem row = one swizzle row (64: SWIZZLE_128B, 2 stages of 96 KB;
+// 32: SWIZZLE_64B, 4 stages of 48 KB -- same bytes in flight, finer-grained ring).
+template <int BK_>
+struct Cfg {
+  static constexpr int BK = BK_;
+  static constexpr int kStages = BK_ == 64 ? 2 : 4;
+  static constexpr int kABytes = BM * BK_ * 2;
+  static constexpr int kBBytes = BN * BK_ * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint64_t kLayoutType = BK_ == 64 ? 2 : 4;      // UMMA LayoutType: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr uint32_t kSBO = 8 * BK_ * 2;                   // bytes between 8-row groups
+};
 constexpr int kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 22;        // bounded waits: trap instead of hanging the GPU
 
@@ -107,18 +118,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 columns: thread t holds rows (t/4, t/4+8), column pairs 8i + 2(t%4) + {0,1}, i = 0..3:
+//   r[4i+0..1] = (row t/4, cols 8i+2(t%4)+{0,1}),  r[4i+2..3] = (row t/4+8, same columns)
+__device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
-//   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = 1024 B between 8-row groups
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+//   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = bytes between 8-row groups | swizzle mode
+template <typename C>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(C::kSBO >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= C::kLayoutType << 61;
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
@@ -138,6 +161,8 @@ struct TcParams {
   const float* bias;
   int elu_cols;          // columns [0, elu_cols) get elu(x)+1 after the bias (K projection)
   long long* tl;         // optional timeline buffer (debug)
+  const float* c_direct; // fp32 C base for the direct-store epilogue (c_direct != nullptr selects it)
+  int ldc;
   int dbg;               // debug variants (timeline tool): 1 = skip the TMA store, 2 = skip staging writes too
 };
 
@@ -146,7 +171,10 @@ struct Maps {
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128
 };
 
+template <int BK_>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
+  using C = Cfg<BK_>;
+  constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + kStages * kStageBytes;
@@ -233,9 +261,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + 2 * kABytes, sb_l = sb_h + kBBytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128 B swizzle row
-            const uint64_t ah = make_desc_sw128(sa_h + koff), al = make_desc_sw128(sa_l + koff);
-            const uint64_t bh = make_desc_sw128(sb_h + koff), bl = make_desc_sw128(sb_l + koff);
+            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
+            const uint64_t ah = make_desc<C>(sa_h + koff), al = make_desc<C>(sa_l + koff);
+            const uint64_t bh = make_desc<C>(sb_h + koff), bl = make_desc<C>(sb_l + koff);
             tc_mma_f16(d, ah, bh, kIdesc, (uint32_t)((kb | k) != 0));
             tc_mma_f16(d, ah, bl, kIdesc, 1u);
             tc_mma_f16(d, al, bh, kIdesc, 1u);
@@ -260,6 +288,39 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       const int out_row0 = z * p.c_batch_rows + m_tile * BM;
+      if (p.c_direct) {
+        // ---- direct register -> global stores (no smem: the UMMA operand reads saturate the smem port).
+        // 16x256b TMEM loads give each lane 2 adjacent columns of rows t/4 and t/4+8, so one warp-wide
+        // 8-byte store covers 8 rows x 32 contiguous bytes (full sectors).
+        float* cbase = const_cast<float*>(p.c_direct) + (long long)(out_row0 + q * 32) * p.ldc + (long long)n_tile * BN;
+        const int rr = lane >> 2, cc = (lane & 3) * 2;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32 + half * 16) << 16);
+          float* crow0 = cbase + (long long)(half * 16 + rr) * p.ldc + cc;
+          float* crow1 = crow0 + 8ll * p.ldc;
+#pragma unroll 2
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[16];
+            tmem_ld16x256_x4(taddr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = c0 + 8 * i;
+              float2 b2 = make_float2(0.f, 0.f);
+              if (p.bias) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + n_tile * BN + col + cc));
+              float2 o0, o1;
+              o0.x = fmaf(__uint_as_float(v[4 * i + 0]), kProdInv, b2.x);
+              o0.y = fmaf(__uint_as_float(v[4 * i + 1]), kProdInv, b2.y);
+              o1.x = fmaf(__uint_as_float(v[4 * i + 2]), kProdInv, b2.x);
+              o1.y = fmaf(__uint_as_float(v[4 * i + 3]), kProdInv, b2.y);
+              if (n_tile * BN + col < p.elu_cols) { o0.x = elu1(o0.x); o0.y = elu1(o0.y); o1.x = elu1(o1.x); o1.y = elu1(o1.y); }
+              *reinterpret_cast<float2*>(crow0 + col) = o0;
+              *reinterpret_cast<float2*>(crow1 + col) = o1;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
         uint32_t v[32];
@@ -298,6 +359,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           tma_store_commit();
         }
       }
+      }
       // all TMEM reads of this tile are complete (wait::ld above): hand the accumulator back
       tc_fence_before();
       __syncwarp();
@@ -333,6 +395,8 @@ EncodeFn get_encode() {
 // 2D row-major tensor [rows, ld] (cols used: `cols`), box = box_cols x box_rows with box_cols*esize = 128 B, SWIZZLE_128B.
 // Cached per (ptr, rows, cols, ld, box, dtype).
 bool make_map(CUtensorMap* out, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows, bool f32) {
+  const size_t esize0 = f32 ? 4 : 2;
+  const CUtensorMapSwizzle swz = (box_cols * esize0 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   static std::map<std::tuple<const void*, long long, int, int, int, int, bool>, CUtensorMap> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
@@ -347,7 +411,7 @@ bool make_map(CUtensorMap* out, const void* ptr, long long rows, int cols, int l
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   if (cache.size() > 4096) cache.clear();
   cache[key] = *out;
@@ -366,14 +430,18 @@ int num_sms() {
 
 }  // namespace
 
+static int g_bk = 0;   // 0 = not decided; 64 or 32 (env OPB_GEMM_BK for experiments)
+
 int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline, int dbg) {
-  if (p.rows % BM || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.ldc % 4) return -1;
-  if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -2;
-    attr_done = true;
+  if (!g_bk) {
+    const char* e = getenv("OPB_GEMM_BK");
+    g_bk = (e && atoi(e) == 64) ? 64 : 32;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
   }
+  const int BK = g_bk;
+  if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0 || p.ldc % 4) return -1;
+  if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
   const long long b1_rows = (long long)(p.batch - 1) * p.b_batch_rows + p.n_out;
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
@@ -393,9 +461,11 @@ int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* t
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline; tp.dbg = dbg;
+  tp.c_direct = (dbg & 4) ? nullptr : p.c; tp.ldc = p.ldc;   // dbg bit 2: use the smem-staged TMA-store epilogue instead
   const int total = tp.m_tiles * tp.n_tiles * tp.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<<<grid, 256, kSmemBytes, stream>>>(mp, tp);
+  if (BK == 64) gemm_tc_kernel<64><<<grid, 256, Cfg<64>::kSmemBytes, stream>>>(mp, tp);
+  else gemm_tc_kernel<32><<<grid, 256, Cfg<32>::kSmemBytes, stream>>>(mp, tp);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
