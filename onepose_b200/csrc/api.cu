@@ -177,7 +177,7 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   if (frames <= m->ws_frames && N <= m->ws_N) return 0;
   frames = frames > m->ws_frames ? frames : m->ws_frames;
   N = N > m->ws_N ? N : m->ws_N;
-  const int n_pad = round_up(N, kTileRows);
+  const int n_pad = round_up(N, kSegPad);
   const size_t R = (size_t)n_pad + m->m_pad;
   const size_t rows = R * frames;
   const size_t S = 2 * (size_t)frames;
@@ -209,7 +209,7 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
 static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
                          float* conf, cudaStream_t st) {
   Layout L;
-  L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kTileRows); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
+  L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kSegPad); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
   m->last_layout = L;
   const int rows = L.rows();
   const int S = L.segs();
@@ -453,7 +453,7 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
     return fail(m, OPB_E_INVALID, "set_object: need M > 0 and 1 <= num_leaf <= 32 (got M=%d, L=%d)", M, Lf);
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int m_pad = round_up(M, 256);   // the 3D side is the N dimension (256-wide tiles) of the score GEMM
+  const int m_pad = round_up(M, kSegPad);
   if (m_pad != m->m_pad) { m->ws_frames = 0; m->ws_N = 0; }  // workspace depends on m_pad
   m->M = M; m->Lf = Lf; m->m_pad = m_pad;
   const long long n_leaf_rows = (long long)M * Lf;

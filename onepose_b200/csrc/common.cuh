@@ -9,7 +9,8 @@ namespace opb {
 constexpr int kD = 256;        // descriptor_dim
 constexpr int kHeads = 4;
 constexpr int kDh = 64;        // per-head dim
-constexpr int kTileRows = 128; // row tile of every GEMM; segments are padded to it
+constexpr int kTileRows = 128; // row tile of every GEMM
+constexpr int kSegPad = 256;   // segments are padded to this: 2 row tiles (one cluster pair) / one 256-wide score tile
 // fp16-split operand format: every plane pair carries a fixed 2^6 pre-scale,
 //   hi = fp16(64 x),  lo = fp16(64 x - hi)      =>  x = (hi + lo) / 64  to ~2^-22 relative
 // (the pre-scale keeps `lo` out of the fp16 subnormal range for |x| > ~2e-3; |x| < 1023 is

@@ -82,6 +82,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)),
                "r"(c_inner), "r"(c_outer)
@@ -171,7 +191,10 @@ struct Maps {
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128
 };
 
-template <int BK_>
+// CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
+// cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
+// B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
+template <int BK_, int CL>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   using C = Cfg<BK_>;
   constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
@@ -186,13 +209,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb1 = p.K1 / BK, nkb = (p.K1 + p.K2) / BK;
-  const int tiles_per_batch = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_per_batch * p.batch;
+  // work unit = CL adjacent row tiles x one n-tile; this CTA takes row tile (CL*mgroup + crank)
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int units_per_batch = (p.m_tiles / CL) * p.n_tiles;
+  const int total_units = units_per_batch * p.batch;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
   long long* tl = p.tl ? p.tl + (long long)blockIdx.x * 64 : nullptr;
   if (tl && threadIdx.x == 0) tl[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,6 +233,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   if (tl && threadIdx.x == 0) tl[1] = clock64();
@@ -215,30 +242,36 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;   // k-block counter across all tiles of this CTA
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int z = t / tiles_per_batch, rem = t - z * tiles_per_batch;
-        const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
+      constexpr int kBHalf = kBBytes / CL;      // bytes of the B tile this CTA fetches (and multicasts)
+      constexpr int kBRowsLoad = BN / CL;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        const int z = u / units_per_batch, rem = u - z * units_per_batch;
+        const int m_tile = (rem / p.n_tiles) * CL + crank, n_tile = rem % p.n_tiles;
         const int row0 = m_tile * BM;
         const int a_row = (int)(z * p.a_batch_rows) + row0;
-        const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN;
-        const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;
-        const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN;
+        const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
+        const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // CL adjacent row tiles share a segment (segments are 256-row aligned)
+        const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN + crank * kBRowsLoad;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           mbar_expect_tx(&full_bar[s], kStageBytes);
-          if (kb < nkb1) {
-            tma_load_2d(st, &maps.a1h, &full_bar[s], kb * BK, a_row);
-            tma_load_2d(st + kABytes, &maps.a1l, &full_bar[s], kb * BK, a_row);
-            tma_load_2d(st + 2 * kABytes, &maps.b1h, &full_bar[s], kb * BK, b_row1);
-            tma_load_2d(st + 2 * kABytes + kBBytes, &maps.b1l, &full_bar[s], kb * BK, b_row1);
+          const bool first = kb < nkb1;
+          const int kc = first ? kb * BK : (kb - nkb1) * BK;
+          const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
+          const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
+          const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
+          const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
+          const int brow = first ? b_row1 : b_row2;
+          tma_load_2d(st, mah, &full_bar[s], kc, a_row);
+          tma_load_2d(st + kABytes, mal, &full_bar[s], kc, a_row);
+          if (CL == 1) {
+            tma_load_2d(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
+            tma_load_2d(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
           } else {
-            const int k2 = (kb - nkb1) * BK;
-            tma_load_2d(st, &maps.a2h, &full_bar[s], k2, a_row);
-            tma_load_2d(st + kABytes, &maps.a2l, &full_bar[s], k2, a_row);
-            tma_load_2d(st + 2 * kABytes, &maps.b2h, &full_bar[s], k2, b_row2);
-            tma_load_2d(st + 2 * kABytes + kBBytes, &maps.b2l, &full_bar[s], k2, b_row2);
+            tma_load_2d_mc(st + 2 * kABytes + crank * kBHalf, mbh, &full_bar[s], kc, brow, (uint16_t)0x3);
+            tma_load_2d_mc(st + 2 * kABytes + kBBytes + crank * kBHalf, mbl, &full_bar[s], kc, brow, (uint16_t)0x3);
           }
         }
       }
@@ -247,7 +280,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      for (int u = unit0; u < total_units; u += unit_step, ++tc) {
         const uint32_t buf = tc & 1;
         mbar_wait(&tmem_empty_bar[buf], ((tc >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
@@ -268,7 +301,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             tc_mma_f16(d, ah, bl, kIdesc, 1u);
             tc_mma_f16(d, al, bh, kIdesc, 1u);
           }
-          tc_commit(&empty_bar[s]);                 // frees the smem stage when these MMAs retire
+          if (CL == 1) tc_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
+          else tc_commit_mc(&empty_bar[s], (uint16_t)0x3);   // ... in BOTH CTAs (the peer multicasts into our stage)
         }
         tc_commit(&tmem_full_bar[buf]);             // accumulator complete
       }
@@ -279,9 +313,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     const int r_in_tile = q * 32 + lane;
     const bool leader = threadIdx.x == 128;
     uint32_t tc = 0, chunk_ctr = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
-      const int z = t / tiles_per_batch, rem = t - z * tiles_per_batch;
-      const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
+    for (int u = unit0; u < total_units; u += unit_step, ++tc) {
+      const int z = u / units_per_batch, rem = u - z * units_per_batch;
+      const int m_tile = (rem / p.n_tiles) * CL + crank, n_tile = rem % p.n_tiles;
       const uint32_t buf = tc & 1;
       mbar_wait(&tmem_full_bar[buf], (tc >> 1) & 1);
       if (tl && leader && tc < 8) tl[40 + 2 * tc] = clock64();
@@ -369,6 +403,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     if (leader) tma_store_wait_all();
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (tl && threadIdx.x == 0) { tl[2] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[63] = sm; }
   if (warp == 2) {
     tc_fence_after();
@@ -431,15 +466,21 @@ int num_sms() {
 }  // namespace
 
 static int g_bk = 0;   // 0 = not decided; 64 or 32 (env OPB_GEMM_BK for experiments)
+static int g_cluster = 2;
 
 int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline, int dbg) {
   if (!g_bk) {
     const char* e = getenv("OPB_GEMM_BK");
-    g_bk = (e && atoi(e) == 64) ? 64 : 32;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
+    g_bk = (e && atoi(e) == 32) ? 32 : 64;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
+    const char* c = getenv("OPB_GEMM_CLUSTER");
+    g_cluster = (c && atoi(c) == 1) ? 1 : 2;
   }
   const int BK = g_bk;
+  const int CL = (g_cluster == 2 && (p.rows / BM) % 2 == 0) ? 2 : 1;
   if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0 || p.ldc % 4) return -1;
   if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
@@ -447,10 +488,10 @@ int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* t
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
   Maps mp;
   bool ok = make_map(&mp.a1h, p.a1.hi, a_rows, p.K1, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, p.K1, p.a1.ld, BK, BM, false) &&
-            make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, BN, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, BN, false);
+            make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, BN / CL, false);
   if (ok && p.K2) {
     ok = make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false) &&
-         make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN, false);
+         make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false);
   } else if (ok) {
     mp.a2h = mp.a1h; mp.a2l = mp.a1l; mp.b2h = mp.b1h; mp.b2l = mp.b1l;
   }
@@ -462,10 +503,21 @@ int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* t
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline; tp.dbg = dbg;
   tp.c_direct = (dbg & 4) ? nullptr : p.c; tp.ldc = p.ldc;   // dbg bit 2: use the smem-staged TMA-store epilogue instead
-  const int total = tp.m_tiles * tp.n_tiles * tp.batch;
-  const int grid = total < num_sms() ? total : num_sms();
-  if (BK == 64) gemm_tc_kernel<64><<<grid, 256, Cfg<64>::kSmemBytes, stream>>>(mp, tp);
-  else gemm_tc_kernel<32><<<grid, 256, Cfg<32>::kSmemBytes, stream>>>(mp, tp);
+  const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
+  int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = BK == 64 ? Cfg<64>::kSmemBytes : Cfg<32>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le;
+  if (BK == 64) le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 1>, mp, tp);
+  else le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 2>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 1>, mp, tp);
+  if (le != cudaSuccess) return -2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
