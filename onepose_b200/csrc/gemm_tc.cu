@@ -34,12 +34,15 @@ constexpr int kNumStaging = 2;
 constexpr int kMaxStages = 4;
 // K-block configuration: BK fp16 per smem row = one swizzle row (64: SWIZZLE_128B, 2 stages of 96 KB;
 // 32: SWIZZLE_64B, 4 stages of 48 KB -- same bytes in flight, finer-grained ring).
-template <int BK_>
+// TWO = 2-CTA UMMA (cta_group::2): each CTA of a pair keeps only HALF of the B tile in its smem and the pair's
+// tensor cores share it, which cuts the per-SM smem traffic (UMMA operand reads + TMA fills) from 240 KB to
+// 160 KB per 64-wide K-block -- the smem port, not the tensor pipe, was the measured limit of the 1-CTA form.
+template <int BK_, bool TWO = false>
 struct Cfg {
   static constexpr int BK = BK_;
-  static constexpr int kStages = BK_ == 64 ? 2 : 4;
+  static constexpr int kStages = (BK_ == 64 ? 2 : 4) + (TWO ? (BK_ == 64 ? 1 : 2) : 0);
   static constexpr int kABytes = BM * BK_ * 2;
-  static constexpr int kBBytes = BN * BK_ * 2;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK_ * 2;     // B bytes resident per CTA
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint64_t kLayoutType = BK_ == 64 ? 2 : 4;      // UMMA LayoutType: SWIZZLE_128B / SWIZZLE_64B
@@ -93,6 +96,36 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+// ---- 2-CTA (cta_group::2) forms
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c_inner, int c_outer) {
+  // data lands in THIS CTA's smem; the transaction bytes are credited to the leader CTA's mbarrier (peer bit cleared)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta_rank)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -155,7 +188,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = bytes between 8-row groups | swizzle mode
 template <typename C>
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {   // C = Cfg<...>
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
@@ -166,6 +199,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -194,9 +228,10 @@ struct Maps {
 // CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
 // cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
 // B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
-template <int BK_, int CL>
+template <int BK_, int CL, bool TWO>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
-  using C = Cfg<BK_>;
+  static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
+  using C = Cfg<BK_, TWO>;
   constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -218,8 +253,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   if (tl && threadIdx.x == 0) tl[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], TWO ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -228,8 +263,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     prefetch_tmap(&maps.out_f32);
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -242,7 +282,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;   // k-block counter across all tiles of this CTA
-      constexpr int kBHalf = kBBytes / CL;      // bytes of the B tile this CTA fetches (and multicasts)
+      constexpr int kBHalf = TWO ? kBBytes : kBBytes / CL;      // bytes of the B tile this CTA fetches
       constexpr int kBRowsLoad = BN / CL;
       for (int u = unit0; u < total_units; u += unit_step) {
         const int z = u / units_per_batch, rem = u - z * units_per_batch;
@@ -256,7 +296,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
-          mbar_expect_tx(&full_bar[s], kStageBytes);
+          if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
+          else if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);     // leader arms for both CTAs' loads
           const bool first = kb < nkb1;
           const int kc = first ? kb * BK : (kb - nkb1) * BK;
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
@@ -264,6 +305,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
+          if (TWO) {
+            tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
+            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
+            tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
+            tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
+            continue;
+          }
           tma_load_2d(st, mah, &full_bar[s], kc, a_row);
           tma_load_2d(st + kABytes, mal, &full_bar[s], kc, a_row);
           if (CL == 1) {
@@ -277,8 +325,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (2-CTA mode: the leader CTA issues for the pair) =====================
+    if (lane == 0 && (!TWO || crank == 0)) {
       uint32_t it = 0, tc = 0;
       for (int u = unit0; u < total_units; u += unit_step, ++tc) {
         const uint32_t buf = tc & 1;
@@ -297,14 +345,22 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
             const uint64_t ah = make_desc<C>(sa_h + koff), al = make_desc<C>(sa_l + koff);
             const uint64_t bh = make_desc<C>(sb_h + koff), bl = make_desc<C>(sb_l + koff);
-            tc_mma_f16(d, ah, bh, kIdesc, (uint32_t)((kb | k) != 0));
-            tc_mma_f16(d, ah, bl, kIdesc, 1u);
-            tc_mma_f16(d, al, bh, kIdesc, 1u);
+            if (TWO) {
+              tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
+              tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
+              tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
+            } else {
+              tc_mma_f16(d, ah, bh, kIdesc, (uint32_t)((kb | k) != 0));
+              tc_mma_f16(d, ah, bl, kIdesc, 1u);
+              tc_mma_f16(d, al, bh, kIdesc, 1u);
+            }
           }
-          if (CL == 1) tc_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
-          else tc_commit_mc(&empty_bar[s], (uint16_t)0x3);   // ... in BOTH CTAs (the peer multicasts into our stage)
+          if (TWO) tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);   // frees the stage in both CTAs
+          else if (CL == 1) tc_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
+          else tc_commit_mc(&empty_bar[s], (uint16_t)0x3);        // ... in BOTH CTAs (the peer multicasts into our stage)
         }
-        tc_commit(&tmem_full_bar[buf]);             // accumulator complete
+        if (TWO) tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);   // accumulator halves complete in both CTAs
+        else tc_commit(&tmem_full_bar[buf]);                          // accumulator complete
       }
     }
   } else if (warp >= 4) {
@@ -397,7 +453,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       // all TMEM reads of this tile are complete (wait::ld above): hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (TWO && crank != 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
       if (tl && leader && tc < 8) tl[41 + 2 * tc] = clock64();
     }
     if (leader) tma_store_wait_all();
@@ -407,7 +466,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   if (tl && threadIdx.x == 0) { tl[2] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[63] = sm; }
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -466,21 +526,24 @@ int num_sms() {
 }  // namespace
 
 static int g_bk = 0;   // 0 = not decided; 64 or 32 (env OPB_GEMM_BK for experiments)
-static int g_cluster = 2;
+static int g_cluster = 3;
 
 int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline, int dbg) {
   if (!g_bk) {
     const char* e = getenv("OPB_GEMM_BK");
     g_bk = (e && atoi(e) == 32) ? 32 : 64;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
-    const char* c = getenv("OPB_GEMM_CLUSTER");
-    g_cluster = (c && atoi(c) == 1) ? 1 : 2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, true>::kSmemBytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
+    const char* c = getenv("OPB_GEMM_CLUSTER");     // 1 = no cluster, 2 = multicast B (1-CTA MMA), 3 = 2-CTA MMA (default)
+    g_cluster = c ? atoi(c) : 3;
+    if (g_cluster < 1 || g_cluster > 3) g_cluster = 3;
   }
   const int BK = g_bk;
-  const int CL = (g_cluster == 2 && (p.rows / BM) % 2 == 0) ? 2 : 1;
+  const bool even = (p.rows / BM) % 2 == 0;
+  const int CL = (g_cluster >= 2 && even) ? 2 : 1;
+  const bool TWO = g_cluster == 3 && even && BK == 64;
   if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0 || p.ldc % 4) return -1;
   if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
@@ -502,21 +565,22 @@ int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* t
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline; tp.dbg = dbg;
-  tp.c_direct = (dbg & 4) ? nullptr : p.c; tp.ldc = p.ldc;   // dbg bit 2: use the smem-staged TMA-store epilogue instead
+  tp.c_direct = (dbg & 4) ? p.c : nullptr; tp.ldc = p.ldc;   // dbg bit 2: direct register->global stores instead of staging + TMA store
   const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
   int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = BK == 64 ? Cfg<64>::kSmemBytes : Cfg<32>::kSmemBytes;
+  cfg.dynamicSmemBytes = TWO ? Cfg<64, true>::kSmemBytes : (BK == 64 ? Cfg<64>::kSmemBytes : Cfg<32>::kSmemBytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le;
-  if (BK == 64) le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 1>, mp, tp);
-  else le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 2>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 1>, mp, tp);
+  if (TWO) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2, true>, mp, tp);
+  else if (BK == 64) le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2, false>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 1, false>, mp, tp);
+  else le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 1, false>, mp, tp);
   if (le != cudaSuccess) return -2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
