@@ -95,6 +95,11 @@ int opb_last_launch_count(const opb_matcher* m);
 int opb_set_profiling(opb_matcher* m, int32_t enable);
 int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms);
 
+/* GNN layers 0 (GATs) and the 3D side of layer 1 (self) depend only on the per-object constants; by default they
+ * are evaluated once per opb_forward call and shared by its frames.  enable = 0 evaluates them per frame like the
+ * reference does (same results up to fp32 rounding; used by the tests). */
+int opb_set_hoist(opb_matcher* m, int32_t enable);
+
 /* Frames processed together through the GNN (L2-residency knob); 0 = default. */
 int opb_set_chunk_frames(opb_matcher* m, int32_t frames);
 

@@ -85,7 +85,8 @@ struct opb_matcher {
   // workspace (chunk)
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
-  PlaneBuf x, qp, hn, pn, g;
+  PlaneBuf x, qp, hn, pn, g, xo, xq;
+  bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
   DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
   // host-call staging
@@ -186,6 +187,8 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->hn.ensure(rows * 512, true));
   CK(m, m->pn.ensure(rows * kD, true));
   CK(m, m->g.ensure(S * 512 * kD));
+  CK(m, m->xo.ensure((size_t)m->m_pad * kD, true));
+  CK(m, m->xq.ensure((size_t)frames * n_pad * kD, true));
   CK(m, m->c768.ensure(rows * 768 * sizeof(float)));
   CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
   CK(m, m->kvpart.ensure(rows / kTileRows * kHeads * kKVPartial * sizeof(float)));
@@ -205,6 +208,83 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   return 0;
 }
 
+// One GATs layer on the 3D-point segments of `x` (layout L).
+static int run_gats(opb_matcher* m, const Layout& L, PlaneBuf& x, int gi, cudaStream_t st) {
+  const long long warps = (long long)L.M * L.B;
+  if (warps == 0) return 0;
+  gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+      x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+      m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
+  m->launches++;
+  return 0;
+}
+
+// One AttentionPropagation layer (reference GATs_SuperGlue.py:55-64, :104-113) on every segment of `x`:
+// both sides of all frames in ONE set of launches (the layer's weights are shared by the two sides).
+static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLayerW& W, int cross, cudaStream_t st) {
+  const int rows = L.rows();
+  const int S = L.segs();
+  const int tiles = rows / kTileRows;
+  const double valid_rows = (double)L.B * (L.N + L.M);
+  __half *xh = x.hi.as<__half>(), *xl = x.lo.as<__half>();
+  auto launched = [&]() { m->launches++; };
+  // (1) q,k,v projections (GATs_SuperGlue.py:96-99), all three from the segment's own rows
+  GemmProblem p{};
+  p.L = L; p.batch = 1; p.rows = rows;
+  p.a1 = x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
+  p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
+  if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
+  // (2) linear-attention state of every segment (:71-78)
+  kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+  launched();
+  kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
+  launched();
+  // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
+  q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
+                                                                                m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
+  launched();
+  // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
+  g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
+  launched();
+  // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
+  GemmProblem p2{};
+  p2.L = L; p2.batch = 1; p2.rows = rows;
+  p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
+  p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
+  p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
+  if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
+  // (6) InstanceNorm statistics per segment (:126)
+  in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
+  launched();
+  in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+  launched();
+  norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
+                                                                                  m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
+  launched();
+  // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64)
+  GemmProblem p3{};
+  p3.L = L; p3.batch = 1; p3.rows = rows;
+  p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
+  p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
+  if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
+  residual_update<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, xl, m->c768.as<float>(), (long long)rows * kD / 8);
+  launched();
+  return 0;
+}
+
+// Object prologue: GNN layers 0 (GATs) and the 3D side of layer 1 (self-attention) depend only on the per-object
+// constants (reference GATs_SuperGlue.py:50-54 and :60-64 with src1 = desc3d_db), not on the query frame.  They are
+// evaluated ONCE per opb_forward call -- on a single copy of the object's rows -- and shared by all frames of the
+// call instead of once per frame.  Result: m->xo = 3D-point state entering layer 2.
+static int object_prologue(opb_matcher* m, cudaStream_t st) {
+  Layout Lo;
+  Lo.B = 1; Lo.N = 0; Lo.M = m->M; Lo.n_pad = 0; Lo.m_pad = m->m_pad; Lo.R = m->m_pad;
+  CK(m, cudaMemcpyAsync(m->xo.hi.p, m->db.hi.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  CK(m, cudaMemcpyAsync(m->xo.lo.p, m->db.lo.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  if (int rc = run_gats(m, Lo, m->xo, 0, st)) return rc;
+  return run_attn_layer(m, Lo, m->xo, m->attn[0], /*cross=*/0, st);
+}
+
 // GNN + tail for `fb` frames starting at frame f0 of the call.
 static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
                          float* conf, cudaStream_t st) {
@@ -212,73 +292,42 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kSegPad); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
   m->last_layout = L;
   const int rows = L.rows();
-  const int S = L.segs();
-  const int tiles = rows / kTileRows;
   const double valid_rows = (double)fb * (N + L.M);
   __half *xh = m->x.hi.as<__half>(), *xl = m->x.lo.as<__half>();
   auto launched = [&]() { m->launches++; };
 
-  // inputs: query descriptors [fb,256,N] channel-first -> q segments; object rows -> d segments
-  transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, xh, xl, nullptr, L.R, 0);
-  launched();
-  broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->db.hi.as<__half>(), m->db.lo.as<__half>(), xh, xl, L);
-  launched();
+  int first_layer = 0;
+  if (m->hoist) {
+    // layer 1 (self) for the query side only, on a compact [fb*n_pad, 256] buffer; layer 0 does not touch queries
+    Layout Lq;
+    Lq.B = fb; Lq.N = N; Lq.M = 0; Lq.n_pad = L.n_pad; Lq.m_pad = 0; Lq.R = L.n_pad;
+    transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, m->xq.hi.as<__half>(), m->xq.lo.as<__half>(),
+                                                                             nullptr, Lq.R, 0);
+    launched();
+    if (int rc = run_attn_layer(m, Lq, m->xq, m->attn[0], 0, st)) return rc;
+    // assemble the full layout: query rows from xq, 3D rows from the object prologue
+    CK(m, cudaMemcpy2DAsync(xh, (size_t)L.R * kD * sizeof(__half), m->xq.hi.p, (size_t)L.n_pad * kD * sizeof(__half),
+                            (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
+    CK(m, cudaMemcpy2DAsync(xl, (size_t)L.R * kD * sizeof(__half), m->xq.lo.p, (size_t)L.n_pad * kD * sizeof(__half),
+                            (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
+    broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->xo.hi.as<__half>(), m->xo.lo.as<__half>(), xh, xl, L);
+    launched();
+    first_layer = 2;
+  } else {
+    // inputs: query descriptors [fb,256,N] channel-first -> q segments; object rows -> d segments
+    transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, xh, xl, nullptr, L.R, 0);
+    launched();
+    broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->db.hi.as<__half>(), m->db.lo.as<__half>(), xh, xl, L);
+    launched();
+  }
 
-  int attn_idx = 0;
-  for (int layer = 0; layer < 12; ++layer) {
+  for (int layer = first_layer; layer < 12; ++layer) {
     if (layer % 3 == 0) {
-      const int gi = layer / 3;
-      const long long warps = (long long)L.M * L.B;
-      gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-          xh, xl, L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
-          m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
-      launched();
-      continue;
+      if (int rc = run_gats(m, L, m->x, layer / 3, st)) return rc;
+    } else {
+      const int attn_idx = (layer / 3) * 2 + (layer % 3) - 1;
+      if (int rc = run_attn_layer(m, L, m->x, m->attn[attn_idx], (layer % 3 == 2) ? 1 : 0, st)) return rc;
     }
-    const int cross = (layer % 3 == 2) ? 1 : 0;
-    AttnLayerW& W = m->attn[attn_idx++];
-    // (1) q,k,v projections (GATs_SuperGlue.py:96-99), all three from the segment's own rows
-    GemmProblem p{};
-    p.L = L; p.batch = 1; p.rows = rows;
-    p.a1 = m->x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
-    p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
-    if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
-    // (2) linear-attention state of every segment (:71-78)
-    kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
-    launched();
-    kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
-    launched();
-    // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
-    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
-                                                                                  m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
-    launched();
-    // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
-    g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross,
-                                                                                     m->g.hi.as<__half>(), m->g.lo.as<__half>());
-    launched();
-    // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
-    GemmProblem p2{};
-    p2.L = L; p2.batch = 1; p2.rows = rows;
-    p2.a1 = m->x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
-    p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
-    p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
-    if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
-    // (6) InstanceNorm statistics per segment (:126)
-    in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
-    launched();
-    in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
-    launched();
-    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
-                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-    launched();
-    // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64)
-    GemmProblem p3{};
-    p3.L = L; p3.batch = 1; p3.rows = rows;
-    p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
-    p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
-    if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
-    residual_update<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, xl, m->c768.as<float>(), (long long)rows * kD / 8);
-    launched();
   }
 
   // ---- tail (GATs_SuperGlue.py:209-237) ----
@@ -350,7 +399,7 @@ void opb_destroy(opb_matcher* m) {
                     &m->mu, &m->rstd, &m->score, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
                     &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
   for (auto* b : bufs) b->release();
-  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g};
+  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq};
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }
@@ -471,6 +520,12 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
   return OPB_OK;
 }
 
+int opb_set_hoist(opb_matcher* m, int32_t enable) {
+  if (!m) return OPB_E_INVALID;
+  m->hoist = enable != 0;
+  return OPB_OK;
+}
+
 int opb_set_chunk_frames(opb_matcher* m, int32_t frames) {
   if (!m || frames < 0) return OPB_E_INVALID;
   m->chunk_frames = frames;
@@ -493,6 +548,9 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
     m->ev_flops.clear();
     if (!m->ev_fwd0) { cudaEventCreate(&m->ev_fwd0); cudaEventCreate(&m->ev_fwd1); }
     cudaEventRecord(m->ev_fwd0, st);
+  }
+  if (m->hoist) {
+    if (int rc = object_prologue(m, st)) return rc;
   }
   for (int f0 = 0; f0 < B; f0 += chunk) {
     const int fb = std::min(chunk, B - f0);

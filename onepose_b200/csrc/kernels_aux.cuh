@@ -255,7 +255,7 @@ __global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
   const int nt = (L.seg_valid(seg) + kTileRows - 1) / kTileRows;
   float s = 0.f;
   for (int t = 0; t < nt; ++t) s += partial[((long long)(t0 + t) * kHeads + h) * kKVPartial + i];
-  s *= 1.f / (float)L.seg_valid(seg);
+  s = L.seg_valid(seg) > 0 ? s * (1.f / (float)L.seg_valid(seg)) : 0.f;   // empty segment (object prologue / query-only pass)
   if (i < kDh * kDh) kvmean[(long long)sh * kDh * kDh + i] = s;
   else kmean[(long long)sh * kDh + (i - kDh * kDh)] = s;
 }
@@ -375,7 +375,7 @@ __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* 
     s += (double)part[((long long)(t0 + t) * 512 + c) * 2 + 0];
     s2 += (double)part[((long long)(t0 + t) * 512 + c) * 2 + 1];
   }
-  const double n = (double)L.seg_valid(seg);
+  const double n = (double)(L.seg_valid(seg) > 0 ? L.seg_valid(seg) : 1);
   const double mean = s / n;
   double var = s2 / n - mean * mean;
   if (var < 0.0) var = 0.0;

@@ -98,6 +98,7 @@ class GATsSuperGlue(nn.Module):
         self._weights_key = None
         self._object_key = None
         self._chunk_frames = 0
+        self._hoist = True
         self.last_batched = None       # batched outputs of the last forward (all B frames)
 
     # ------------------------------------------------------------------ handle / weights
@@ -124,6 +125,8 @@ class GATsSuperGlue(nn.Module):
         self._weights_key = self._object_key = None
         if self._chunk_frames:
             _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
+        if not self._hoist:
+            _lib.check(self._lib.opb_set_hoist(self._handle, 0), self._handle)
 
     def _sync_weights(self):
         key = tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
@@ -135,6 +138,12 @@ class GATsSuperGlue(nn.Module):
         _lib.check(self._lib.opb_finalize_weights(self._handle), self._handle)
         self._weights_key = key
         self._object_key = None
+
+    def set_hoist(self, enable: bool):
+        """Evaluate the frame-invariant GNN layers once per call (default) or per frame like the reference."""
+        self._hoist = bool(enable)
+        if self._handle is not None:
+            _lib.check(self._lib.opb_set_hoist(self._handle, int(self._hoist)), self._handle)
 
     def set_chunk_frames(self, frames: int):
         """Frames pushed through the GNN together (L2-residency knob of the C ABI)."""

@@ -205,6 +205,26 @@ def test_segmented_mean_matches_reference_golden():
     np.testing.assert_allclose(out.cpu().numpy(), g["avg"], rtol=0, atol=1e-15)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_object_prologue_hoisting_matches_per_frame_evaluation(backend):
+    """Layers 0-1 of the 3D side are frame-invariant: evaluating them once per call (default) must give the
+    same answer as evaluating them per frame like the reference (GATs_SuperGlue.py:50-64)."""
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    data = synthetic.make_batch(4, [1, 2, 3], 200, 500, 8)
+    ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+    outs = []
+    for hoist in (True, False):
+        m = _module(sd, hp, backend)
+        m.set_hoist(hoist)
+        m.set_chunk_frames(2)
+        m(_cuda(data))
+        _check_against(m.last_batched, ref, f"hoist={hoist}")
+        outs.append(m.last_batched)
+    assert float((outs[0]["conf_matrix"] - outs[1]["conf_matrix"]).abs().max()) <= 2e-6
+    assert torch.equal(outs[0]["matches0"], outs[1]["matches0"])
+
+
 def test_repeat_calls_are_deterministic():
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
