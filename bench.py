@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step (batch of one object)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per GNN chunk (0 = library default)")
-    ap.add_argument("--backend", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--backend", default="tcgen05", choices=["tcgen05", "simt", "tcgen05_unfused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -301,7 +301,7 @@ def main():
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 semantics via fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate" if args.backend == "tcgen05" else "f32 (SIMT cross-check core)",
+            "dtype": "f32 semantics via fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate" if args.backend != "simt" else "f32 (SIMT cross-check core)",
             "data": "synthetic",
             "config": {"workload": f"synthetic batch={B} frames of one object per GPU, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2])",
                        "frames_per_step": B, "gemm_backend": args.backend,

@@ -43,7 +43,8 @@ typedef struct opb_config {
   int32_t additional;            /* GATs.py:61                                          */
   int32_t with_linear_transform; /* GATs.py:56 -- only 0 is implemented                */
   int32_t device;                /* CUDA device ordinal                                 */
-  int32_t gemm_backend;          /* 0 = tcgen05 (product), 1 = SIMT fp32 cross-check (tests only) */
+  int32_t gemm_backend;          /* 0 = tcgen05 with fused epilogues (product); tests only: 1 = SIMT fp32 GEMM + unfused
+                                    helper kernels, 2 = tcgen05 GEMM + unfused helper kernels */
 } opb_config;
 
 /* Replaces GATsSuperGlue.__init__ (GATs_SuperGlue.py:145-177). */

@@ -85,7 +85,8 @@ struct opb_matcher {
   // workspace (chunk)
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
-  PlaneBuf x, qp, hn, pn, g, xo, xq;
+  PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
+  DevBuf kvpieces;
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
   DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
@@ -166,7 +167,7 @@ static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, doubl
   int rc;
   if (m->profiling) cudaEventRecord(next_event(m), st);
   if (m->cfg.gemm_backend == 1) rc = launch_gemm_simt(p, st);
-  else rc = launch_gemm_tc_plain(p, st);
+  else rc = launch_gemm_tc(p, st);
   if (m->profiling) { cudaEventRecord(next_event(m), st); m->ev_flops.push_back(flops); }
   m->launches++;
   if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (rc=%d, backend=%d): %s", rc,
@@ -194,7 +195,9 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->kvpart.ensure(rows / kTileRows * kHeads * kKVPartial * sizeof(float)));
   CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
-  CK(m, m->statpart.ensure(rows / kTileRows * 512 * 2 * sizeof(float)));
+  CK(m, m->statpart.ensure(rows / 32 * 512 * 2 * sizeof(float)));
+  CK(m, m->kvt.ensure(rows * 512, true));
+  CK(m, m->kvpieces.ensure(rows / 256 * 256 * 256 * sizeof(float)));
   CK(m, m->mu.ensure(S * 512 * sizeof(float)));
   CK(m, m->rstd.ensure(S * 512 * sizeof(float)));
   CK(m, m->score.ensure((size_t)frames * n_pad * m->m_pad * sizeof(float)));
@@ -228,6 +231,55 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   const double valid_rows = (double)L.B * (L.N + L.M);
   __half *xh = x.hi.as<__half>(), *xl = x.lo.as<__half>();
   auto launched = [&]() { m->launches++; };
+  if (m->cfg.gemm_backend == 0) {
+    // ---------------- fused tcgen05 pipeline ----------------
+    // (1) [K | V] projection; epilogue: elu+1 on K, pad rows zeroed, TRANSPOSED fp16-split planes kvt[512][rows]
+    GemmProblem pk{};
+    pk.L = L; pk.batch = 1; pk.rows = rows;
+    pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
+    pk.bias = W.bqkv.as<float>() + 256; pk.elu_cols = 256;
+    pk.epi = EPI_KVT; pk.out = m->kvt.m(rows);
+    if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD)) return rc;
+    // (2) linear-attention state on the tensor cores: per 256-row piece  K_piece^T V_piece  (reduction batched along rows)
+    GemmProblem ps{};
+    ps.batch = rows / 256; ps.rows = 256; ps.n_out = 256; ps.K1 = 256;
+    ps.a1 = m->kvt.c(rows); ps.b1 = m->kvt.c(rows, (size_t)256 * rows);
+    ps.a_batch_k = 256; ps.b_batch_k = 256;
+    ps.c = m->kvpieces.as<float>(); ps.ldc = 256; ps.c_batch_elems = 256 * 256; ps.epi = EPI_F32;
+    if (int rc = run_gemm(m, ps, st, 2.0 * valid_rows * kD * kDh)) return rc;
+    kv_reduce_pieces<<<dim3(S * kHeads, 16), 256, 0, st>>>(m->kvpieces.as<float>(), L, m->kvmean.as<float>());
+    launched();
+    kt_mean<<<dim3(kD, S), 128, 0, st>>>(m->kvt.hi.as<__half>(), m->kvt.lo.as<__half>(), rows, L, m->kmean.as<float>());
+    launched();
+    // (3) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
+    g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
+    launched();
+    // (4) q projection; epilogue: elu+1, per-head normaliser with the SOURCE segment's K mean -> Q' planes (:78-79)
+    GemmProblem pq{};
+    pq.L = L; pq.batch = 1; pq.rows = rows;
+    pq.a1 = x.c(kD); pq.K1 = kD; pq.b1 = W.wqkv.c(kD); pq.n_out = 256; pq.bias = W.bqkv.as<float>();
+    pq.epi = EPI_QSCALE; pq.kmean = m->kmean.as<float>(); pq.cross = cross; pq.out = m->qp.m(kD);
+    if (int rc = run_gemm(m, pq, st, 2.0 * valid_rows * 256 * kD)) return rc;
+    // (5) hidden = [x | Q'] . [W0a | G_seg]^T + b; epilogue also emits the InstanceNorm partial sums (:126)
+    GemmProblem p2{};
+    p2.L = L; p2.batch = 1; p2.rows = rows;
+    p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
+    p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
+    p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
+    p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
+    if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
+    in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+    launched();
+    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
+                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
+    launched();
+    // (6) delta = mlp.3(hn); epilogue: x += delta + bias, re-split, in place (:59/:64)
+    GemmProblem p3{};
+    p3.L = L; p3.batch = 1; p3.rows = rows;
+    p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256; p3.bias = W.b1.as<float>();
+    p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
+    return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
+  }
   // (1) q,k,v projections (GATs_SuperGlue.py:96-99), all three from the segment's own rows
   GemmProblem p{};
   p.L = L; p.batch = 1; p.rows = rows;
@@ -335,9 +387,14 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   pf.L = L; pf.batch = 1; pf.rows = rows;
   pf.a1 = m->x.c(kD); pf.K1 = kD; pf.b1 = m->wf.c(kD); pf.n_out = 256;
   pf.bias = m->bf.as<float>(); pf.c = m->c768.as<float>(); pf.ldc = 256;
-  if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
-  l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
-  launched();
+  if (m->cfg.gemm_backend == 0) {
+    pf.epi = EPI_L2NORM; pf.out = m->pn.m(kD);       // F.normalize fused into the final_proj epilogue (:209-213)
+    if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
+  } else {
+    if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
+    l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
+    launched();
+  }
   // cos[b][n][m] = <P_q[n], P_d[m]>   (batched over frames)
   GemmProblem ps{};
   ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
@@ -399,7 +456,8 @@ void opb_destroy(opb_matcher* m) {
                     &m->mu, &m->rstd, &m->score, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
                     &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
   for (auto* b : bufs) b->release();
-  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq};
+  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq, &m->kvt};
+  m->kvpieces.release();
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }
@@ -637,7 +695,7 @@ int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const v
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  int rc = backend == 1 ? launch_gemm_simt(p, (cudaStream_t)stream) : launch_gemm_tc_plain(p, (cudaStream_t)stream);
+  int rc = backend == 1 ? launch_gemm_simt(p, (cudaStream_t)stream) : launch_gemm_tc(p, (cudaStream_t)stream);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 
@@ -648,7 +706,8 @@ int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  int rc = launch_gemm_tc_plain(p, (cudaStream_t)stream, timeline, dbg);
+  (void)dbg;
+  int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 

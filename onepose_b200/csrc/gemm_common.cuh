@@ -13,6 +13,16 @@ namespace opb {
 // where seg = L.seg_of_row(row) -- per-frame/side dynamic weights (the G fold).
 // Batched form (score GEMM): batch z uses A rows offset z*a_batch_rows, B rows offset
 // z*b_batch_rows (B operand = activations of the same frame), C offset z*c_batch_elems.
+// Epilogue of the tcgen05 core (what happens to the accumulator tile before it leaves the SM):
+enum GemmEpilogue {
+  EPI_F32 = 0,        // c[rows, ldc] fp32 = acc (+bias) (elu+1 on columns < elu_cols)
+  EPI_F32_STATS = 1,  // EPI_F32 + InstanceNorm partial sums (sum, sum^2 per 32-row quarter and column) -> statpart
+  EPI_QSCALE = 2,     // Q' = elu1(acc+bias) / (elu1(.) . Kmean_src + 1e-6/m_src) per head -> out planes   (n_out = 256)
+  EPI_RESID = 3,      // out planes = resid planes + acc + bias  (x += delta, in place)                     (n_out = 256)
+  EPI_KVT = 4,        // [K | V] projection -> TRANSPOSED planes out[n_out channels][total rows]; elu+1 on K; pad rows zeroed
+  EPI_L2NORM = 5,     // F.normalize(acc + bias) over the 256 columns -> out planes                          (n_out = 256)
+};
+
 struct GemmProblem {
   CPlanes a1, a2, b1, b2;
   int K1, K2;
@@ -25,6 +35,14 @@ struct GemmProblem {
   int elu_cols;          // output columns [0, elu_cols) get elu(x)+1 after the bias
   float* c;              // fp32 [rows, ldc]
   int ldc;
+  // ---- tcgen05 core only ----
+  int epi;               // GemmEpilogue
+  Planes out;            // planes output (EPI_QSCALE / EPI_RESID / EPI_L2NORM: [rows, out.ld]; EPI_KVT: [n_out, out.ld = total rows])
+  CPlanes resid;         // EPI_RESID input planes [rows, 256]
+  const float* kmean;    // EPI_QSCALE: [S][256]
+  int cross;             // EPI_QSCALE: source segment selection
+  float* statpart;       // EPI_F32_STATS: [rows/32][n_out][2]
+  long long a_batch_k, b_batch_k;   // batched along the reduction dimension: batch z starts at column z*a_batch_k (KV state)
 };
 
 int launch_gemm_simt(const GemmProblem& p, cudaStream_t stream);

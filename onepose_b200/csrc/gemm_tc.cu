@@ -215,20 +215,25 @@ struct TcParams {
   const float* bias;
   int elu_cols;          // columns [0, elu_cols) get elu(x)+1 after the bias (K projection)
   long long* tl;         // optional timeline buffer (debug)
-  const float* c_direct; // fp32 C base for the direct-store epilogue (c_direct != nullptr selects it)
-  int ldc;
-  int dbg;               // debug variants (timeline tool): 1 = skip the TMA store, 2 = skip staging writes too
+  long long a_batch_k, b_batch_k;   // reduction-dimension offset per batch (KV-state GEMM)
+  // fused epilogues
+  const float* kmean;    // EPI_QSCALE
+  int cross;
+  const __half* x_hi;    // EPI_RESID (ld = 256)
+  const __half* x_lo;
+  float* statpart;       // EPI_F32_STATS
 };
 
 struct Maps {
   CUtensorMap a1h, a1l, a2h, a2l, b1h, b1l, b2h, b2l;   // loads
-  CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128
+  CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128 (SWIZZLE_128B)
+  CUtensorMap out_hi, out_lo;                             // store: planes, box 64 x 128 (SWIZZLE_128B); EPI_KVT: transposed, box 128 x 64 (no swizzle)
 };
 
 // CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
 // cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
 // B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
-template <int BK_, int CL, bool TWO>
+template <int BK_, int CL, bool TWO, int EPI>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
   using C = Cfg<BK_, TWO>;
@@ -260,7 +265,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a1h); prefetch_tmap(&maps.a1l); prefetch_tmap(&maps.b1h); prefetch_tmap(&maps.b1l);
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
-    prefetch_tmap(&maps.out_f32);
+    if (EPI == EPI_F32 || EPI == EPI_F32_STATS) prefetch_tmap(&maps.out_f32);
+    else { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
   if (warp == 2) {
     if (TWO) {
@@ -299,27 +305,28 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
           else if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);     // leader arms for both CTAs' loads
           const bool first = kb < nkb1;
-          const int kc = first ? kb * BK : (kb - nkb1) * BK;
+          const int kc = (first ? kb * BK : (kb - nkb1) * BK);
+          const int kca = kc + (int)(z * p.a_batch_k), kcb = kc + (int)(z * p.b_batch_k);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
           const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
           if (TWO) {
-            tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
-            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
-            tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
-            tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
+            tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
+            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
+            tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kcb, brow);
+            tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kcb, brow);
             continue;
           }
-          tma_load_2d(st, mah, &full_bar[s], kc, a_row);
-          tma_load_2d(st + kABytes, mal, &full_bar[s], kc, a_row);
+          tma_load_2d(st, mah, &full_bar[s], kca, a_row);
+          tma_load_2d(st + kABytes, mal, &full_bar[s], kca, a_row);
           if (CL == 1) {
-            tma_load_2d(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
-            tma_load_2d(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
+            tma_load_2d(st + 2 * kABytes, mbh, &full_bar[s], kcb, brow);
+            tma_load_2d(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kcb, brow);
           } else {
-            tma_load_2d_mc(st + 2 * kABytes + crank * kBHalf, mbh, &full_bar[s], kc, brow, (uint16_t)0x3);
-            tma_load_2d_mc(st + 2 * kABytes + kBBytes + crank * kBHalf, mbl, &full_bar[s], kc, brow, (uint16_t)0x3);
+            tma_load_2d_mc(st + 2 * kABytes + crank * kBHalf, mbh, &full_bar[s], kcb, brow, (uint16_t)0x3);
+            tma_load_2d_mc(st + 2 * kABytes + kBBytes + crank * kBHalf, mbl, &full_bar[s], kcb, brow, (uint16_t)0x3);
           }
         }
       }
@@ -378,77 +385,174 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       const int out_row0 = z * p.c_batch_rows + m_tile * BM;
-      if (p.c_direct) {
-        // ---- direct register -> global stores (no smem: the UMMA operand reads saturate the smem port).
-        // 16x256b TMEM loads give each lane 2 adjacent columns of rows t/4 and t/4+8, so one warp-wide
-        // 8-byte store covers 8 rows x 32 contiguous bytes (full sectors).
-        float* cbase = const_cast<float*>(p.c_direct) + (long long)(out_row0 + q * 32) * p.ldc + (long long)n_tile * BN;
-        const int rr = lane >> 2, cc = (lane & 3) * 2;
+      const int row0 = m_tile * BM;                               // within the batch
+      int n_valid = BM;                                           // valid rows of this tile (segment-aware launches)
+      int seg = 0;
+      if (p.L.R > 0) {
+        seg = p.L.seg_of_row(row0);
+        n_valid = p.L.seg_valid(seg) - (row0 - p.L.seg_start(seg));
+      }
+      if (EPI == EPI_F32 || EPI == EPI_F32_STATS) {
+        // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk, double-buffered staging
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32 + half * 16) << 16);
-          float* crow0 = cbase + (long long)(half * 16 + rr) * p.ldc + cc;
-          float* crow1 = crow0 + 8ll * p.ldc;
-#pragma unroll 2
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[16];
-            tmem_ld16x256_x4(taddr + c0, v);
-            tmem_ld_wait();
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
+          if (leader) tma_store_wait_read<1>();     // the store that last read this buffer (2 chunks ago) is done with it
+          epi_bar();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = c0 + 8 * i;
-              float2 b2 = make_float2(0.f, 0.f);
-              if (p.bias) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + n_tile * BN + col + cc));
-              float2 o0, o1;
-              o0.x = fmaf(__uint_as_float(v[4 * i + 0]), kProdInv, b2.x);
-              o0.y = fmaf(__uint_as_float(v[4 * i + 1]), kProdInv, b2.y);
-              o1.x = fmaf(__uint_as_float(v[4 * i + 2]), kProdInv, b2.x);
-              o1.y = fmaf(__uint_as_float(v[4 * i + 3]), kProdInv, b2.y);
-              if (n_tile * BN + col < p.elu_cols) { o0.x = elu1(o0.x); o0.y = elu1(o0.y); o1.x = elu1(o1.x); o1.y = elu1(o1.y); }
-              *reinterpret_cast<float2*>(crow0 + col) = o0;
-              *reinterpret_cast<float2*>(crow1 + col) = o1;
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = __uint_as_float(v[4 * j + 0]) * kProdInv;
+            o.y = __uint_as_float(v[4 * j + 1]) * kProdInv;
+            o.z = __uint_as_float(v[4 * j + 2]) * kProdInv;
+            o.w = __uint_as_float(v[4 * j + 3]) * kProdInv;
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             }
+            if (col0 < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
+            *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = o;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_f32, sb, col0, out_row0);
+            tma_store_commit();
+          }
+          if (EPI == EPI_F32_STATS) {
+            // InstanceNorm partial sums straight from the staged tile: thread = (32-row quarter, column)
+            const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;
+            float sum = 0.f, sq = 0.f;
+            const int r_end = min(32, n_valid - qq * 32);
+            for (int i = 0; i < r_end; ++i) {
+              const int r = qq * 32 + i;
+              const float x = *reinterpret_cast<const float*>(sb + stg_off(r, cc >> 2) + (cc & 3) * 4);
+              sum += x;
+              sq = fmaf(x, x, sq);
+            }
+            float2* dst = reinterpret_cast<float2*>(p.statpart) + ((long long)(out_row0 / 32 + qq) * p.n_out + col0 + cc);
+            *dst = make_float2(sum, sq);
+          }
+        }
+      } else if (EPI == EPI_KVT) {
+        // ---- [K | V] projection -> transposed fp16-split planes out[channel][row] (operands of the KV-state GEMM)
+        __half* st_hi = reinterpret_cast<__half*>(staging);
+        __half* st_lo = reinterpret_cast<__half*>(staging + kStagingBytes);
+        const bool row_ok = r_in_tile < n_valid;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_base + c0, v0);
+          tmem_ld32(lane_base + c0 + 32, v1);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          if (leader) tma_store_wait_read<0>();
+          epi_bar();
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            float x = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) * kProdInv + __ldg(p.bias + col0 + j);
+            if (col0 < p.elu_cols) x = elu1(x);
+            if (!row_ok) x = 0.f;                   // pad rows must not reach the K^T V reduction
+            __half h, l;
+            split_f32(x, h, l);
+            st_hi[j * BM + r_in_tile] = h;
+            st_lo[j * BM + r_in_tile] = l;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, st_hi, out_row0, col0);
+            tma_store_2d(&maps.out_lo, st_lo, out_row0, col0);
+            tma_store_commit();
           }
         }
       } else {
+        // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM
+        uint8_t* st_hi = staging;
+        uint8_t* st_lo = staging + kStagingBytes;
+        float inv_norm = 1.f;
+        if (EPI == EPI_L2NORM) {                    // F.normalize: first pass over the accumulator for the row norm
+          float ss = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
-        uint32_t v[32];
-        const bool stamp = tl && leader && tc == 1 && c0 < 128;
-        if (stamp) tl[3 + (c0 >> 5) * 4] = clock64();
-        tmem_ld32(lane_base + c0, v);
-        tmem_ld_wait();
-        if (stamp) tl[4 + (c0 >> 5) * 4] = clock64();
-        const int col0 = n_tile * BN + c0;
-        uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
-        // the TMA store that last read this staging buffer (2 chunks ago) must have finished reading
-        if (leader) tma_store_wait_read<1>();
-        epi_bar();
-        if (stamp) tl[5 + (c0 >> 5) * 4] = clock64();
-        if (!(p.dbg & 2)) {
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o;
-          o.x = __uint_as_float(v[4 * j + 0]) * kProdInv;
-          o.y = __uint_as_float(v[4 * j + 1]) * kProdInv;
-          o.z = __uint_as_float(v[4 * j + 2]) * kProdInv;
-          o.w = __uint_as_float(v[4 * j + 3]) * kProdInv;
-          if (p.bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            for (int j = 0; j < 32; ++j) {
+              const float x = fmaf(__uint_as_float(v[j]), kProdInv, __ldg(p.bias + c0 + j));
+              ss = fmaf(x, x, ss);
+            }
           }
-          if (col0 < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
-          *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = o;
+          inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
         }
+        int src = 0;
+        float eps_m = 0.f;
+        if (EPI == EPI_QSCALE) {
+          src = p.L.src_seg(seg, p.cross);
+          eps_m = 1e-6f / (float)max(p.L.seg_valid(src), 1);
         }
-        fence_async_smem();
-        epi_bar();
-        if (stamp) tl[6 + (c0 >> 5) * 4] = clock64();
-        if (leader && !(p.dbg & 1)) {
-          tma_store_2d(&maps.out_f32, sb, col0, out_row0);
-          tma_store_commit();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_base + c0, v0);
+          tmem_ld32(lane_base + c0 + 32, v1);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          float x[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) x[j] = fmaf(__uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]), kProdInv, __ldg(p.bias + col0 + j));
+          if (EPI == EPI_QSCALE) {
+            // one 64-column chunk = one head (head-contiguous channels); the row's head dot product is thread-local
+            const float* km = p.kmean + (long long)src * kD + col0;
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { x[j] = elu1(x[j]); dot = fmaf(x[j], __ldg(km + j), dot); }
+            const float zf = 1.f / (dot + eps_m);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) x[j] *= zf;
+          } else if (EPI == EPI_RESID) {
+            const long long g = (long long)(out_row0 + r_in_tile) * kD + col0;
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {
+              const uint4 uh = *reinterpret_cast<const uint4*>(p.x_hi + g + j8 * 8);
+              const uint4 ul = *reinterpret_cast<const uint4*>(p.x_lo + g + j8 * 8);
+              const __half* hh = reinterpret_cast<const __half*>(&uh);
+              const __half* hl = reinterpret_cast<const __half*>(&ul);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[j8 * 8 + e] += join_f32(hh[e], hl[e]);
+            }
+          } else {  // EPI_L2NORM
+#pragma unroll
+            for (int j = 0; j < 64; ++j) x[j] *= inv_norm;
+          }
+          if (leader) tma_store_wait_read<0>();
+          epi_bar();
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            uint4 oh, ol;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __half h, l;
+              split_f32(x[j8 * 8 + e], h, l);
+              reinterpret_cast<__half*>(&oh)[e] = h;
+              reinterpret_cast<__half*>(&ol)[e] = l;
+            }
+            *reinterpret_cast<uint4*>(st_hi + stg_off(r_in_tile, j8)) = oh;
+            *reinterpret_cast<uint4*>(st_lo + stg_off(r_in_tile, j8)) = ol;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, st_hi, col0, out_row0);
+            tma_store_2d(&maps.out_lo, st_lo, col0, out_row0);
+            tma_store_commit();
+          }
         }
-      }
       }
       // all TMEM reads of this tile are complete (wait::ld above): hand the accumulator back
       tc_fence_before();
@@ -487,12 +591,13 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// 2D row-major tensor [rows, ld] (cols used: `cols`), box = box_cols x box_rows with box_cols*esize = 128 B, SWIZZLE_128B.
-// Cached per (ptr, rows, cols, ld, box, dtype).
-bool make_map(CUtensorMap* out, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows, bool f32) {
-  const size_t esize0 = f32 ? 4 : 2;
-  const CUtensorMapSwizzle swz = (box_cols * esize0 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  static std::map<std::tuple<const void*, long long, int, int, int, int, bool>, CUtensorMap> cache;
+// 2D row-major tensor [rows, ld] (cols used: `cols`), box = box_cols x box_rows.  Swizzle follows the box row
+// width (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B, anything else -> none).  Cached per (ptr, shape, box, dtype).
+bool make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32) {
+  const size_t esize = f32 ? 4 : 2;
+  const size_t row_bytes = box_cols * esize;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  static std::map<std::tuple<const void*, long long, long long, long long, int, int, bool>, CUtensorMap> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   auto key = std::make_tuple(ptr, rows, cols, ld, box_cols, box_rows, f32);
@@ -500,7 +605,6 @@ bool make_map(CUtensorMap* out, const void* ptr, long long rows, int cols, int l
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeFn enc = get_encode();
   if (!enc) return false;
-  const size_t esize = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -523,64 +627,98 @@ int num_sms() {
   return n;
 }
 
+template <int CL, bool TWO, int EPI>
+cudaError_t launch_variant(const cudaLaunchConfig_t& cfg0, const Maps& mp, const TcParams& tp) {
+  static bool attr_done = false;
+  auto* kern = gemm_tc_kernel<64, CL, TWO, EPI>;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, TWO>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = cfg0;
+  cfg.dynamicSmemBytes = Cfg<64, TWO>::kSmemBytes;
+  return cudaLaunchKernelEx(&cfg, kern, mp, tp);
+}
+
 }  // namespace
 
-static int g_bk = 0;   // 0 = not decided; 64 or 32 (env OPB_GEMM_BK for experiments)
-static int g_cluster = 3;
+static int g_cluster = 0;   // 0 = undecided; 1 = no cluster, 2 = multicast B (1-CTA MMA), 3 = 2-CTA MMA (default)
 
-int launch_gemm_tc_plain(const GemmProblem& p, cudaStream_t stream, long long* timeline, int dbg) {
-  if (!g_bk) {
-    const char* e = getenv("OPB_GEMM_BK");
-    g_bk = (e && atoi(e) == 32) ? 32 : 64;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, true>::kSmemBytes) != cudaSuccess) return -2;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<32, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes) != cudaSuccess) return -2;
-    const char* c = getenv("OPB_GEMM_CLUSTER");     // 1 = no cluster, 2 = multicast B (1-CTA MMA), 3 = 2-CTA MMA (default)
+int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
+  if (!g_cluster) {
+    const char* c = getenv("OPB_GEMM_CLUSTER");
     g_cluster = c ? atoi(c) : 3;
     if (g_cluster < 1 || g_cluster > 3) g_cluster = 3;
   }
-  const int BK = g_bk;
+  constexpr int BK = 64;
   const bool even = (p.rows / BM) % 2 == 0;
   const int CL = (g_cluster >= 2 && even) ? 2 : 1;
-  const bool TWO = g_cluster == 3 && even && BK == 64;
-  if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0 || p.ldc % 4) return -1;
-  if (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc) return -1;
+  const bool TWO = g_cluster == 3 && even;
+  if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0) return -1;
+  if (p.epi != EPI_F32 && !TWO) return -1;                       // fused epilogues exist for the 2-CTA form only
+  if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM) && p.n_out != BN) return -1;
+  const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
+  if (f32_out && (p.ldc % 4 || (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc))) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
   const long long b1_rows = (long long)(p.batch - 1) * p.b_batch_rows + p.n_out;
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
+  const long long a_cols = (long long)(p.batch - 1) * p.a_batch_k + p.K1, b_cols = (long long)(p.batch - 1) * p.b_batch_k + p.K1;
   Maps mp;
-  bool ok = make_map(&mp.a1h, p.a1.hi, a_rows, p.K1, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, p.K1, p.a1.ld, BK, BM, false) &&
-            make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, BN / CL, false);
+  bool ok = make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false) &&
+            make_map(&mp.b1h, p.b1.hi, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false);
   if (ok && p.K2) {
     ok = make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false) &&
          make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false);
   } else if (ok) {
     mp.a2h = mp.a1h; mp.a2l = mp.a1l; mp.b2h = mp.b1h; mp.b2l = mp.b1l;
   }
-  ok = ok && make_map(&mp.out_f32, p.c, (long long)p.batch * p.rows, p.n_out, p.ldc, 32, BM, true);
+  const long long out_rows = (long long)p.batch * p.rows;
+  if (f32_out) {
+    ok = ok && make_map(&mp.out_f32, p.c, out_rows, p.n_out, p.ldc, 32, BM, true);
+    mp.out_hi = mp.out_f32; mp.out_lo = mp.out_f32;
+  } else if (p.epi == EPI_KVT) {
+    // transposed planes [n_out channels][out.ld = total rows]; box = 128 rows (inner) x 64 channels
+    ok = ok && make_map(&mp.out_hi, p.out.hi, p.n_out, out_rows, p.out.ld, BM, 64, false) && make_map(&mp.out_lo, p.out.lo, p.n_out, out_rows, p.out.ld, BM, 64, false);
+    mp.out_f32 = mp.out_hi;
+  } else {
+    ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, p.n_out, p.out.ld, 64, BM, false) && make_map(&mp.out_lo, p.out.lo, out_rows, p.n_out, p.out.ld, 64, BM, false);
+    mp.out_f32 = mp.out_hi;
+  }
   if (!ok) return -2;
   TcParams tp{};
   tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
-  tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline; tp.dbg = dbg;
-  tp.c_direct = (dbg & 4) ? p.c : nullptr; tp.ldc = p.ldc;   // dbg bit 2: direct register->global stores instead of staging + TMA store
+  tp.a_batch_k = p.a_batch_k; tp.b_batch_k = p.b_batch_k;
+  tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline;
+  tp.kmean = p.kmean; tp.cross = p.cross; tp.x_hi = p.resid.hi; tp.x_lo = p.resid.lo; tp.statpart = p.statpart;
   const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
-  int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
+  const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = TWO ? Cfg<64, true>::kSmemBytes : (BK == 64 ? Cfg<64>::kSmemBytes : Cfg<32>::kSmemBytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le;
-  if (TWO) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2, true>, mp, tp);
-  else if (BK == 64) le = CL == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 2, false>, mp, tp) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<64, 1, false>, mp, tp);
-  else le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32, 1, false>, mp, tp);
+  if (TWO) {
+    switch (p.epi) {
+      case EPI_F32: le = launch_variant<2, true, EPI_F32>(cfg, mp, tp); break;
+      case EPI_F32_STATS: le = launch_variant<2, true, EPI_F32_STATS>(cfg, mp, tp); break;
+      case EPI_QSCALE: le = launch_variant<2, true, EPI_QSCALE>(cfg, mp, tp); break;
+      case EPI_RESID: le = launch_variant<2, true, EPI_RESID>(cfg, mp, tp); break;
+      case EPI_KVT: le = launch_variant<2, true, EPI_KVT>(cfg, mp, tp); break;
+      case EPI_L2NORM: le = launch_variant<2, true, EPI_L2NORM>(cfg, mp, tp); break;
+      default: return -1;
+    }
+  } else if (CL == 2) {
+    le = launch_variant<2, false, EPI_F32>(cfg, mp, tp);
+  } else {
+    le = launch_variant<1, false, EPI_F32>(cfg, mp, tp);
+  }
   if (le != cudaSuccess) return -2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

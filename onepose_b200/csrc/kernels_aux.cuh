@@ -260,6 +260,47 @@ __global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
   else kmean[(long long)sh * kDh + (i - kDh * kDh)] = s;
 }
 
+// Tensor-core path of the linear-attention state.  The [K | V] projection epilogue (EPI_KVT) leaves
+// K^T (elu+1 applied) and V^T as fp16-split planes kvt[512][rows] with pad rows zeroed; one batched-K GEMM
+// then yields, per 256-row piece, part[piece][256 (K channel)][256 (V channel)] = K_piece^T V_piece.
+// kv_reduce_pieces: fixed-order sum over the pieces of a segment, diagonal head blocks only, 1/m scale.
+// grid (S*H, 16), block 256
+__global__ void kv_reduce_pieces(const float* __restrict__ part, Layout L, float* __restrict__ kvmean /*[S][H][64][64]*/) {
+  const int sh = blockIdx.x;
+  const int seg = sh / kHeads, h = sh % kHeads;
+  const int i = blockIdx.y * 256 + threadIdx.x;      // d*64 + q
+  const int d = i >> 6, q = i & 63;
+  const int p0 = L.seg_start(seg) / 256;
+  const int np = (L.seg_valid(seg) + 255) / 256;
+  float s = 0.f;
+  for (int t = 0; t < np; ++t) s += part[((long long)(p0 + t) * 256 + h * kDh + d) * 256 + h * kDh + q];
+  kvmean[(long long)sh * kDh * kDh + i] = L.seg_valid(seg) > 0 ? s * (1.f / (float)L.seg_valid(seg)) : 0.f;
+}
+// Kmean[s][c] = (1/m) sum over the segment's rows of K^T[c][row]  (pad rows are zero).  grid (256, S), block 128
+__global__ void kt_mean(const __half* __restrict__ kt_hi, const __half* __restrict__ kt_lo, long long rows_total, Layout L,
+                        float* __restrict__ kmean /*[S][256]*/) {
+  __shared__ float red[128];
+  const int c = blockIdx.x, seg = blockIdx.y;
+  const long long base = (long long)c * rows_total + L.seg_start(seg);
+  const int n = L.seg_padded(seg);
+  float acc = 0.f;
+  for (int r = threadIdx.x * 8; r < n; r += 128 * 8) {
+    const uint4 uh = *reinterpret_cast<const uint4*>(kt_hi + base + r);
+    const uint4 ul = *reinterpret_cast<const uint4*>(kt_lo + base + r);
+    const __half* hh = reinterpret_cast<const __half*>(&uh);
+    const __half* hl = reinterpret_cast<const __half*>(&ul);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += join_f32(hh[e], hl[e]);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) kmean[seg * kD + c] = L.seg_valid(seg) > 0 ? red[0] / (float)L.seg_valid(seg) : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------
 // Q' = elu1(q) / (elu1(q) . Kmean_src + 1e-6/m_src)  per head  (GATs_SuperGlue.py:71,78-79
 // with the /m, *m of :75,:79 folded into the means).  q: fp32 [rows, ldq] (cols 0..255,
@@ -345,35 +386,40 @@ __global__ void __launch_bounds__(256) g_fold(const float* __restrict__ kvmean, 
 // ---------------------------------------------------------------------------------------
 // InstanceNorm1d(512) statistics over the valid rows of each segment
 // (reference GATs_SuperGlue.py:126: no affine, biased variance, eps 1e-5).
-// Stage 1: per 128-row tile and channel: sum, sum of squares (fp32).  grid (tiles, 4), block 128.
+// Stage 1: per 32-row quarter and channel: sum, sum of squares (fp32) -- written by the fused GEMM epilogue
+// (EPI_F32_STATS) or by in_stats_partial (grid (tiles, 4), block 128) on the unfused path.
 // Stage 2: per (segment, channel): fixed-order fp64 combine -> mean, rstd.
 // ---------------------------------------------------------------------------------------
-__global__ void in_stats_partial(const float* __restrict__ hid /*[rows,512]*/, Layout L, float* __restrict__ part /*[tiles][512][2]*/) {
+__global__ void in_stats_partial(const float* __restrict__ hid /*[rows,512]*/, Layout L, float* __restrict__ part /*[rows/32][512][2]*/) {
   const int tile = blockIdx.x;
   const int c = blockIdx.y * 128 + threadIdx.x;
   const int row0 = tile * kTileRows;
   const int seg = L.seg_of_row(row0);
-  const int n_valid = min(kTileRows, L.seg_valid(seg) - (row0 - L.seg_start(seg)));
-  float s = 0.f, s2 = 0.f;
-  for (int r = 0; r < n_valid; ++r) {
-    float v = hid[(long long)(row0 + r) * 512 + c];
-    s += v;
-    s2 = fmaf(v, v, s2);
+  const int n_valid = L.seg_valid(seg) - (row0 - L.seg_start(seg));
+  for (int qq = 0; qq < 4; ++qq) {
+    float s = 0.f, s2 = 0.f;
+    const int r_end = min(32, n_valid - qq * 32);
+    for (int i = 0; i < r_end; ++i) {
+      float v = hid[(long long)(row0 + qq * 32 + i) * 512 + c];
+      s += v;
+      s2 = fmaf(v, v, s2);
+    }
+    part[((long long)(tile * 4 + qq) * 512 + c) * 2 + 0] = s;
+    part[((long long)(tile * 4 + qq) * 512 + c) * 2 + 1] = s2;
   }
-  part[((long long)tile * 512 + c) * 2 + 0] = s;
-  part[((long long)tile * 512 + c) * 2 + 1] = s2;
 }
 
-// grid (S, 8), block 64
+// grid (S, 8), block 64: fixed-order fp64 combine of the 32-row partials of a segment -> mean, rstd
 __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* __restrict__ mu, float* __restrict__ rstd) {
   const int seg = blockIdx.x;
   const int c = blockIdx.y * 64 + threadIdx.x;
-  const int t0 = L.seg_start(seg) / kTileRows;
-  const int nt = (L.seg_valid(seg) + kTileRows - 1) / kTileRows;
+  const int q0 = L.seg_start(seg) / 32;
+  const int nq = (L.seg_valid(seg) + 31) / 32;
   double s = 0.0, s2 = 0.0;
-  for (int t = 0; t < nt; ++t) {
-    s += (double)part[((long long)(t0 + t) * 512 + c) * 2 + 0];
-    s2 += (double)part[((long long)(t0 + t) * 512 + c) * 2 + 1];
+  for (int t = 0; t < nq; ++t) {
+    const float2 v = reinterpret_cast<const float2*>(part)[(long long)(q0 + t) * 512 + c];
+    s += (double)v.x;
+    s2 += (double)v.y;
   }
   const double n = (double)(L.seg_valid(seg) > 0 ? L.seg_valid(seg) : 1);
   const double mean = s / n;

@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib
 
 GNN_LAYERS = ["GATs", "self", "cross"] * 4          # GATs_SuperGlue.py:162
-_BACKENDS = {"tcgen05": 0, "simt": 1}
+_BACKENDS = {"tcgen05": 0, "simt": 1, "tcgen05_unfused": 2}   # 1, 2: cross-check paths used by the tests
 
 
 class _GATsParams(nn.Module):

@@ -15,7 +15,7 @@ from tests.golden_util import RELEASED_CASES, conf_reference_view, load_case
 pytestmark = pytest.mark.gpu
 
 CONF_TOL = 1e-4          # north_star tolerance
-BACKENDS = ["tcgen05", "simt"]
+BACKENDS = ["tcgen05", "simt", "tcgen05_unfused"]
 
 
 def _module(sd, hp, backend):
