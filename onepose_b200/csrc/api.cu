@@ -16,6 +16,8 @@
 
 namespace opb {
 
+constexpr int kKvtPad = 192;   // halves; keeps 128-B alignment, breaks the 2^k row stride of the transposed K/V planes
+
 static thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -196,7 +198,7 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
   CK(m, m->statpart.ensure(rows / 32 * 512 * 2 * sizeof(float)));
-  CK(m, m->kvt.ensure(rows * 512, true));
+  CK(m, m->kvt.ensure((rows + kKvtPad) * 512, true));
   CK(m, m->kvpieces.ensure(rows / 256 * 256 * 256 * sizeof(float)));
   CK(m, m->mu.ensure(S * 512 * sizeof(float)));
   CK(m, m->rstd.ensure(S * 512 * sizeof(float)));
@@ -238,18 +240,19 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
     pk.L = L; pk.batch = 1; pk.rows = rows;
     pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
     pk.bias = W.bqkv.as<float>() + 256; pk.elu_cols = 256;
-    pk.epi = EPI_KVT; pk.out = m->kvt.m(rows);
+    const int kvt_ld = rows + kKvtPad;               // row stride of the transposed planes: NOT a power of two
+    pk.epi = EPI_KVT; pk.out = m->kvt.m(kvt_ld);
     if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD)) return rc;
     // (2) linear-attention state on the tensor cores: per 256-row piece  K_piece^T V_piece  (reduction batched along rows)
     GemmProblem ps{};
     ps.batch = rows / 256; ps.rows = 256; ps.n_out = 256; ps.K1 = 256;
-    ps.a1 = m->kvt.c(rows); ps.b1 = m->kvt.c(rows, (size_t)256 * rows);
+    ps.a1 = m->kvt.c(kvt_ld); ps.b1 = m->kvt.c(kvt_ld, (size_t)256 * kvt_ld);
     ps.a_batch_k = 256; ps.b_batch_k = 256;
     ps.c = m->kvpieces.as<float>(); ps.ldc = 256; ps.c_batch_elems = 256 * 256; ps.epi = EPI_F32;
     if (int rc = run_gemm(m, ps, st, 2.0 * valid_rows * kD * kDh)) return rc;
     kv_reduce_pieces<<<dim3(S * kHeads, 16), 256, 0, st>>>(m->kvpieces.as<float>(), L, m->kvmean.as<float>());
     launched();
-    kt_mean<<<dim3(kD, S), 128, 0, st>>>(m->kvt.hi.as<__half>(), m->kvt.lo.as<__half>(), rows, L, m->kmean.as<float>());
+    kt_mean<<<dim3(kD, S), 128, 0, st>>>(m->kvt.hi.as<__half>(), m->kvt.lo.as<__half>(), kvt_ld, L, m->kmean.as<float>());
     launched();
     // (3) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
     g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
@@ -268,7 +271,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
     p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
     p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
     if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
-    in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+    in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
     launched();
     norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                     m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
@@ -308,7 +311,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   // (6) InstanceNorm statistics per segment (:126)
   in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
   launched();
-  in_stats_final<<<dim3(S, 8), 64, 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
+  in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
   launched();
   norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                   m->hn.hi.as<__half>(), m->hn.lo.as<__half>());

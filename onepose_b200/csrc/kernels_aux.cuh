@@ -409,24 +409,34 @@ __global__ void in_stats_partial(const float* __restrict__ hid /*[rows,512]*/, L
   }
 }
 
-// grid (S, 8), block 64: fixed-order fp64 combine of the 32-row partials of a segment -> mean, rstd
+// grid (S, 16), block (32 channels, 8 slices): fixed-order fp64 combine of the 32-row partials of a segment -> mean, rstd
 __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* __restrict__ mu, float* __restrict__ rstd) {
+  __shared__ double sh[8][32][2];
   const int seg = blockIdx.x;
-  const int c = blockIdx.y * 64 + threadIdx.x;
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  const int slice = threadIdx.y;
   const int q0 = L.seg_start(seg) / 32;
   const int nq = (L.seg_valid(seg) + 31) / 32;
   double s = 0.0, s2 = 0.0;
-  for (int t = 0; t < nq; ++t) {
+  for (int t = slice; t < nq; t += 8) {
     const float2 v = reinterpret_cast<const float2*>(part)[(long long)(q0 + t) * 512 + c];
     s += (double)v.x;
     s2 += (double)v.y;
   }
-  const double n = (double)(L.seg_valid(seg) > 0 ? L.seg_valid(seg) : 1);
-  const double mean = s / n;
-  double var = s2 / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mu[seg * 512 + c] = (float)mean;
-  rstd[seg * 512 + c] = (float)(1.0 / sqrt(var + 1e-5));
+  sh[slice][threadIdx.x][0] = s;
+  sh[slice][threadIdx.x][1] = s2;
+  __syncthreads();
+  if (slice == 0) {
+    s = 0.0; s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += sh[k][threadIdx.x][0]; s2 += sh[k][threadIdx.x][1]; }
+    const double n = (double)(L.seg_valid(seg) > 0 ? L.seg_valid(seg) : 1);
+    const double mean = s / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mu[seg * 512 + c] = (float)mean;
+    rstd[seg * 512 + c] = (float)(1.0 / sqrt(var + 1e-5));
+  }
 }
 
 // HN = ReLU((hid - mu) * rstd) -> fp16-split planes [rows, 512].  One thread = 8 channels.
