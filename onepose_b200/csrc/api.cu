@@ -16,8 +16,6 @@
 
 namespace opb {
 
-constexpr int kKvtPad = 192;   // halves; keeps 128-B alignment, breaks the 2^k row stride of the transposed K/V planes
-
 static thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -88,7 +86,7 @@ struct opb_matcher {
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
   PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
-  DevBuf kvpieces;
+  DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
   DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
@@ -198,12 +196,15 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
   CK(m, m->statpart.ensure(rows / 32 * 512 * 2 * sizeof(float)));
-  CK(m, m->kvt.ensure((rows + kKvtPad) * 512, true));
+  CK(m, m->kvt.ensure(rows * 512, true));
+  CK(m, m->ksum_part.ensure(rows / 32 * 256 * sizeof(float)));
   CK(m, m->kvpieces.ensure(rows / 256 * 256 * 256 * sizeof(float)));
   CK(m, m->mu.ensure(S * 512 * sizeof(float)));
   CK(m, m->rstd.ensure(S * 512 * sizeof(float)));
   CK(m, m->score.ensure((size_t)frames * n_pad * m->m_pad * sizeof(float)));
   CK(m, m->rowsum.ensure((size_t)frames * n_pad * sizeof(float)));
+  CK(m, m->rowsum_part.ensure((size_t)frames * (m->m_pad / 256) * n_pad * sizeof(float)));
+  CK(m, m->colsum_part.ensure((size_t)frames * (n_pad / 32) * m->m_pad * sizeof(float)));
   CK(m, m->colsum.ensure((size_t)frames * m->m_pad * sizeof(float)));
   CK(m, m->rowbest.ensure((size_t)frames * n_pad * sizeof(unsigned long long)));
   CK(m, m->colbest.ensure((size_t)frames * m->m_pad * sizeof(unsigned long long)));
@@ -235,24 +236,24 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   auto launched = [&]() { m->launches++; };
   if (m->cfg.gemm_backend == 0) {
     // ---------------- fused tcgen05 pipeline ----------------
-    // (1) [K | V] projection; epilogue: elu+1 on K, pad rows zeroed, TRANSPOSED fp16-split planes kvt[512][rows]
+    // (1) [K | V] projection; epilogue: elu+1 on K, pad rows zeroed -> fp16-split planes kv[rows, 512], plus the
+    //     per-32-row column sums of K (for the K mean)
     GemmProblem pk{};
     pk.L = L; pk.batch = 1; pk.rows = rows;
     pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
     pk.bias = W.bqkv.as<float>() + 256; pk.elu_cols = 256;
-    const int kvt_ld = rows + kKvtPad;               // row stride of the transposed planes: NOT a power of two
-    pk.epi = EPI_KVT; pk.out = m->kvt.m(kvt_ld);
+    pk.epi = EPI_KV; pk.out = m->kvt.m(512); pk.statpart = m->ksum_part.as<float>();
     if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD)) return rc;
-    // (2) linear-attention state on the tensor cores: per 256-row piece  K_piece^T V_piece  (reduction batched along rows)
+    // (2) linear-attention state on the tensor cores (:77): per 256-row piece  K_piece^T V_piece, reading the row-major
+    //     planes as MN-major UMMA operands (reduction index = row)
     GemmProblem ps{};
-    ps.batch = rows / 256; ps.rows = 256; ps.n_out = 256; ps.K1 = 256;
-    ps.a1 = m->kvt.c(kvt_ld); ps.b1 = m->kvt.c(kvt_ld, (size_t)256 * kvt_ld);
+    ps.batch = rows / 256; ps.rows = 256; ps.n_out = 256; ps.K1 = 256; ps.mn_major = 1;
+    ps.a1 = m->kvt.c(512); ps.b1 = m->kvt.c(512, 256);
     ps.a_batch_k = 256; ps.b_batch_k = 256;
     ps.c = m->kvpieces.as<float>(); ps.ldc = 256; ps.c_batch_elems = 256 * 256; ps.epi = EPI_F32;
     if (int rc = run_gemm(m, ps, st, 2.0 * valid_rows * kD * kDh)) return rc;
-    kv_reduce_pieces<<<dim3(S * kHeads, 16), 256, 0, st>>>(m->kvpieces.as<float>(), L, m->kvmean.as<float>());
-    launched();
-    kt_mean<<<dim3(kD, S), 128, 0, st>>>(m->kvt.hi.as<__half>(), m->kvt.lo.as<__half>(), kvt_ld, L, m->kmean.as<float>());
+    kv_reduce_pieces<<<dim3(S * kHeads, 17), 256, 0, st>>>(m->kvpieces.as<float>(), m->ksum_part.as<float>(), L, m->kvmean.as<float>(),
+                                                          m->kmean.as<float>());
     launched();
     // (3) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
     g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
@@ -398,6 +399,26 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
     launched();
   }
+  const float inv_scale = 1.f / m->cfg.scale_factor;
+  if (m->cfg.gemm_backend == 0) {
+    // ---- fused tail: two passes of the batched score GEMM, nothing N x M ever read back
+    const int n_tiles = L.m_pad / 256, q_groups = L.n_pad / 32;
+    GemmProblem ps{};
+    ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
+    ps.a1 = m->pn.c(kD); ps.K1 = kD; ps.b1 = m->pn.c(kD, (size_t)L.n_pad * kD);
+    ps.a_batch_rows = L.R; ps.b_batch_rows = L.R;
+    ps.inv_scale = inv_scale;
+    ps.epi = EPI_SCORE_SUMS; ps.rowsum_part = m->rowsum_part.as<float>(); ps.colsum_part = m->colsum_part.as<float>();
+    if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
+    score_sums_finalize<<<dim3((L.n_pad + L.m_pad + 255) / 256, fb), 256, 0, st>>>(m->rowsum_part.as<float>(), m->colsum_part.as<float>(), L, n_tiles,
+                                                                                  q_groups, m->rowsum.as<float>(), m->colsum.as<float>());
+    launched();
+    CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
+    CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
+    ps.epi = EPI_SCORE_CONF; ps.inv_rowsum = m->rowsum.as<float>(); ps.inv_colsum = m->colsum.as<float>();
+    ps.conf = conf; ps.rowbest = m->rowbest.as<unsigned long long>(); ps.colbest = m->colbest.as<unsigned long long>();
+    if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
+  } else {
   // cos[b][n][m] = <P_q[n], P_d[m]>   (batched over frames)
   GemmProblem ps{};
   ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
@@ -405,7 +426,6 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   ps.a_batch_rows = L.R; ps.b_batch_rows = L.R; ps.c_batch_elems = (long long)L.n_pad * L.m_pad;
   ps.c = m->score.as<float>(); ps.ldc = L.m_pad;
   if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
-  const float inv_scale = 1.f / m->cfg.scale_factor;
   score_row_sums<<<(unsigned)(((long long)fb * N * 32 + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>());
   launched();
   score_col_sums<<<dim3((L.M + 31) / 32, fb), dim3(32, 8), 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
@@ -416,6 +436,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
                                                                               m->colsum.as<float>(), conf,
                                                                               m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
   launched();
+  }
   mutual_match<<<fb, 256, 0, st>>>(m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>(), N, L.M, m->cfg.match_threshold,
                                    reinterpret_cast<long long*>(m0), reinterpret_cast<long long*>(m1), s0, s1);
   launched();
@@ -460,7 +481,7 @@ void opb_destroy(opb_matcher* m) {
                     &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
   for (auto* b : bufs) b->release();
   PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq, &m->kvt};
-  m->kvpieces.release();
+  m->kvpieces.release(); m->rowsum_part.release(); m->colsum_part.release(); m->ksum_part.release();
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }

@@ -21,6 +21,11 @@ enum GemmEpilogue {
   EPI_RESID = 3,      // out planes = resid planes + acc + bias  (x += delta, in place)                     (n_out = 256)
   EPI_KVT = 4,        // [K | V] projection -> TRANSPOSED planes out[n_out channels][total rows]; elu+1 on K; pad rows zeroed
   EPI_L2NORM = 5,     // F.normalize(acc + bias) over the 256 columns -> out planes                          (n_out = 256)
+  // dual-softmax tail on the batched score GEMM (one batch = one frame; rows = queries, columns = 3D points):
+  EPI_SCORE_SUMS = 6, // e = exp((cos-1)/scale): per-tile row sums and per-32-row column sums -> rowsum_part / colsum_part
+  EPI_SCORE_CONF = 7, // conf = e^2 / (rowsum*colsum) -> conf [B,N,M] (optional) + packed row / column arg-max (atomicMax)
+  EPI_KV = 8,         // [K | V] projection -> row-major planes out[rows, 512]; elu+1 on K; pad rows zeroed; per-32-row column
+                      // sums of K -> statpart [rows/32][256] (K mean of the linear attention)
 };
 
 struct GemmProblem {
@@ -43,6 +48,17 @@ struct GemmProblem {
   int cross;             // EPI_QSCALE: source segment selection
   float* statpart;       // EPI_F32_STATS: [rows/32][n_out][2]
   long long a_batch_k, b_batch_k;   // batched along the reduction dimension: batch z starts at column z*a_batch_k (KV state)
+  int mn_major;                     // operands are [K, rows]-shaped row-major tensors (reduction index = tensor ROW): the KV-state
+                                    // GEMM  C[256,256] = K_piece^T . V_piece  reads the row-major K/V planes directly (UMMA MN-major)
+  // EPI_SCORE_*: L gives N, M, n_pad, m_pad
+  float inv_scale;
+  float* rowsum_part;               // [B][n_out/256][n_pad]
+  float* colsum_part;               // [B][rows/32][m_pad]
+  const float* inv_rowsum;          // [B][n_pad]
+  const float* inv_colsum;          // [B][m_pad]
+  float* conf;                      // [B][N][M] or nullptr
+  unsigned long long* rowbest;      // [B][N]
+  unsigned long long* colbest;      // [B][M]
 };
 
 int launch_gemm_simt(const GemmProblem& p, cudaStream_t stream);

@@ -140,6 +140,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(c_inner), "r"(c_outer)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -197,9 +202,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {   // C = Cfg
   d |= C::kLayoutType << 61;
   return d;
 }
+// MN-major, SWIZZLE_128B operand: atoms of 64 (MN, contiguous 128 B) x 8 (K rows); LBO = bytes between MN atoms
+// (here 8 KB: one 64-channel x 64-row TMA box per atom column), SBO = 1024 B between the 8-row K atoms.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
+constexpr uint32_t kIdesc2MN = kIdesc2 | (1u << 15) | (1u << 16);                                           // A and B MN-major
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -221,7 +238,18 @@ struct TcParams {
   int cross;
   const __half* x_hi;    // EPI_RESID (ld = 256)
   const __half* x_lo;
-  float* statpart;       // EPI_F32_STATS
+  float* statpart;       // EPI_F32_STATS / EPI_KV
+  int mn_major;
+  // EPI_SCORE_*
+  float inv_scale;
+  float* rowsum_part;
+  float* colsum_part;
+  const float* inv_rowsum;
+  const float* inv_colsum;
+  float* conf;
+  int conf_tma;          // 1: conf goes out through the 3-D tensor map (M % 4 == 0), 0: per-thread stores
+  unsigned long long* rowbest;
+  unsigned long long* colbest;
 };
 
 struct Maps {
@@ -265,8 +293,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a1h); prefetch_tmap(&maps.a1l); prefetch_tmap(&maps.b1h); prefetch_tmap(&maps.b1l);
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
-    if (EPI == EPI_F32 || EPI == EPI_F32_STATS) prefetch_tmap(&maps.out_f32);
-    else { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
+    if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF) prefetch_tmap(&maps.out_f32);
+    else if (EPI != EPI_SCORE_SUMS) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
   if (warp == 2) {
     if (TWO) {
@@ -312,6 +340,18 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
+          if (TWO && p.mn_major) {
+            // operands are row-major [reduction row][channel] planes: box = 64 channels x 64 rows, two boxes per 128 channels
+            const int ach = m_tile * BM, bch = n_tile * BN + crank * kBRowsLoad;
+#pragma unroll
+            for (int bx = 0; bx < 2; ++bx) {
+              tma_load_2d_2sm(st + bx * 8192, mah, &full_bar[s], ach + bx * 64, kca);
+              tma_load_2d_2sm(st + kABytes + bx * 8192, mal, &full_bar[s], ach + bx * 64, kca);
+              tma_load_2d_2sm(st + 2 * kABytes + bx * 8192, mbh, &full_bar[s], bch + bx * 64, kcb);
+              tma_load_2d_2sm(st + 2 * kABytes + kBBytes + bx * 8192, mbl, &full_bar[s], bch + bx * 64, kcb);
+            }
+            continue;
+          }
           if (TWO) {
             tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
             tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
@@ -352,7 +392,14 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
             const uint64_t ah = make_desc<C>(sa_h + koff), al = make_desc<C>(sa_l + koff);
             const uint64_t bh = make_desc<C>(sb_h + koff), bl = make_desc<C>(sb_l + koff);
-            if (TWO) {
+            if (TWO && p.mn_major) {
+              const uint32_t ko = k * 2048;         // 16 reduction rows = two 8-row atoms
+              const uint64_t mah_ = make_desc_mn(sa_h + ko), mal_ = make_desc_mn(sa_l + ko);
+              const uint64_t mbh_ = make_desc_mn(sb_h + ko), mbl_ = make_desc_mn(sb_l + ko);
+              tc_mma_f16_2sm(d, mah_, mbh_, kIdesc2MN, (uint32_t)((kb | k) != 0));
+              tc_mma_f16_2sm(d, mah_, mbl_, kIdesc2MN, 1u);
+              tc_mma_f16_2sm(d, mal_, mbh_, kIdesc2MN, 1u);
+            } else if (TWO) {
               tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
               tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
               tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
@@ -438,6 +485,84 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             *dst = make_float2(sum, sq);
           }
         }
+      } else if (EPI == EPI_SCORE_SUMS || EPI == EPI_SCORE_CONF) {
+        // ---- dual-softmax tail (reference GATs_SuperGlue.py:217-223).  Unit-norm operands: cos <= 1, so with the fixed
+        // shift  e = exp((cos - 1)/scale)  softmax(s,1)*softmax(s,2) = e^2 / (colsum*rowsum)  needs no running max.
+        const int N = p.L.N, M = p.L.M;
+        const int row = row0 + r_in_tile;                          // query index inside frame z
+        const bool row_ok = row < N;
+        const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31; // column-pass role: (32-row quarter, column)
+        float rs = 0.f;                                            // SUMS: row sum over this tile's columns
+        float irs = 0.f;
+        unsigned long long rbest = 0ull;
+        if (EPI == EPI_SCORE_CONF && row_ok) irs = __ldg(p.inv_rowsum + (long long)z * p.L.n_pad + row);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
+          if (EPI == EPI_SCORE_CONF && p.conf_tma) {
+            if (leader) tma_store_wait_read<1>();
+            epi_bar();
+          }
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = row_ok && (col0 + j) < M;
+            const float e = ok ? expf((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
+            if (EPI == EPI_SCORE_SUMS) {
+              o[j] = e;
+              rs += e;
+            } else {
+              const float ics = ok ? __ldg(p.inv_colsum + (long long)z * p.L.m_pad + col0 + j) : 0.f;
+              const float c = (e * irs) * (e * ics);
+              o[j] = c;
+              if (ok) {
+                const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(col0 + j));
+                rbest = pk > rbest ? pk : rbest;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          if (EPI == EPI_SCORE_CONF && p.conf && !p.conf_tma && row_ok) {
+            float* dst = p.conf + ((long long)z * N + row) * M + col0;
+            for (int j = 0; j < 32 && col0 + j < M; ++j) dst[j] = o[j];
+          }
+          if (EPI == EPI_SCORE_CONF && p.conf_tma) fence_async_smem();
+          epi_bar();
+          if (EPI == EPI_SCORE_CONF && p.conf_tma && p.conf && leader) {
+            tma_store_3d(&maps.out_f32, sb, col0, row0, z);       // rows >= N and columns >= M are clipped by the tensor map
+            tma_store_commit();
+          }
+          // column pass over the staged 128 x 32 chunk
+          const int col = col0 + cc;
+          if (col < M) {
+            if (EPI == EPI_SCORE_SUMS) {
+              float sum = 0.f;
+#pragma unroll 8
+              for (int i = 0; i < 32; ++i) sum += *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
+              p.colsum_part[((long long)z * (p.m_tiles * 4) + m_tile * 4 + qq) * p.L.m_pad + col] = sum;
+            } else {
+              unsigned long long cbest = 0ull;
+              const int r_end = min(32, N - (row0 + qq * 32));
+              for (int i = 0; i < r_end; ++i) {
+                const float c = *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
+                const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row0 + qq * 32 + i));
+                cbest = pk > cbest ? pk : cbest;
+              }
+              if (cbest) atomicMax(p.colbest + (long long)z * M + col, cbest);
+            }
+          }
+        }
+        if (EPI == EPI_SCORE_SUMS) {
+          p.rowsum_part[((long long)z * p.n_tiles + n_tile) * p.L.n_pad + row] = rs;
+        } else if (row_ok && rbest) {
+          atomicMax(p.rowbest + (long long)z * N + row, rbest);
+        }
       } else if (EPI == EPI_KVT) {
         // ---- [K | V] projection -> transposed fp16-split planes out[channel][row] (operands of the KV-state GEMM)
         __half* st_hi = reinterpret_cast<__half*>(staging);
@@ -471,7 +596,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           }
         }
       } else {
-        // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM
+        // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM / EPI_KV
         uint8_t* st_hi = staging;
         uint8_t* st_lo = staging + kStagingBytes;
         float inv_norm = 1.f;
@@ -526,6 +651,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[j8 * 8 + e] += join_f32(hh[e], hl[e]);
             }
+          } else if (EPI == EPI_KV) {
+            const bool row_ok = r_in_tile < n_valid;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              if (col0 < p.elu_cols) x[j] = elu1(x[j]);
+              if (!row_ok) x[j] = 0.f;              // pad rows must not reach the K^T V reduction or the K mean
+            }
           } else {  // EPI_L2NORM
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= inv_norm;
@@ -551,6 +683,21 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             tma_store_2d(&maps.out_hi, st_hi, col0, out_row0);
             tma_store_2d(&maps.out_lo, st_lo, col0, out_row0);
             tma_store_commit();
+          }
+          if (EPI == EPI_KV && col0 < p.elu_cols) {
+            // K mean of the linear attention: per-32-row column sums of elu1(K) from the staged planes
+            const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;       // thread = (quarter, column pair)
+            float s0 = 0.f, s1 = 0.f;
+            for (int i = 0; i < 32; ++i) {
+              const int r = qq * 32 + i;
+              const uint32_t off = stg_off(r, cc >> 2) + (cc & 3) * 4;        // two adjacent halves = columns 2cc, 2cc+1
+              const __half2 h2 = *reinterpret_cast<const __half2*>(st_hi + off);
+              const __half2 l2 = *reinterpret_cast<const __half2*>(st_lo + off);
+              s0 += join_f32(__low2half(h2), __low2half(l2));
+              s1 += join_f32(__high2half(h2), __high2half(l2));
+            }
+            float2* dst = reinterpret_cast<float2*>(p.statpart + (long long)(out_row0 / 32 + qq) * 256 + col0 + 2 * cc);
+            *dst = make_float2(s0, s1);
           }
         }
       }
@@ -617,6 +764,19 @@ bool make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols,
   return true;
 }
 
+// conf [B][N][M] fp32 as a 3-D tensor (box 32 x 128 x 1, SWIZZLE_128B): a 128-row tile that hangs over the end of a
+// frame (rows >= N) or of a row (columns >= M) is clipped by the hardware.  Needs M % 4 == 0 (16-byte global strides).
+bool make_map3(CUtensorMap* out, const float* ptr, int M, int N, int B) {
+  EncodeFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)M * 4, (cuuint64_t)M * N * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -658,14 +818,24 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0) return -1;
   if (p.epi != EPI_F32 && !TWO) return -1;                       // fused epilogues exist for the 2-CTA form only
   if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM) && p.n_out != BN) return -1;
+  if (p.mn_major && (!TWO || p.K2)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
+  const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
+  int conf_tma = 0;
   if (f32_out && (p.ldc % 4 || (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc))) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
   const long long b1_rows = (long long)(p.batch - 1) * p.b_batch_rows + p.n_out;
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
   const long long a_cols = (long long)(p.batch - 1) * p.a_batch_k + p.K1, b_cols = (long long)(p.batch - 1) * p.b_batch_k + p.K1;
   Maps mp;
-  bool ok = make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false) &&
+  bool ok;
+  if (p.mn_major) {
+    // row-major [reduction rows, channels] planes; box = 64 channels x 64 rows
+    const long long k_rows = (long long)(p.batch - 1) * p.a_batch_k + p.K1;
+    ok = make_map(&mp.a1h, p.a1.hi, k_rows, p.rows, p.a1.ld, 64, 64, false) && make_map(&mp.a1l, p.a1.lo, k_rows, p.rows, p.a1.ld, 64, 64, false) &&
+         make_map(&mp.b1h, p.b1.hi, k_rows, p.n_out, p.b1.ld, 64, 64, false) && make_map(&mp.b1l, p.b1.lo, k_rows, p.n_out, p.b1.ld, 64, 64, false);
+  } else
+  ok = make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false) &&
             make_map(&mp.b1h, p.b1.hi, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false);
   if (ok && p.K2) {
     ok = make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false) &&
@@ -677,6 +847,11 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (f32_out) {
     ok = ok && make_map(&mp.out_f32, p.c, out_rows, p.n_out, p.ldc, 32, BM, true);
     mp.out_hi = mp.out_f32; mp.out_lo = mp.out_f32;
+  } else if (score) {
+    mp.out_f32 = mp.a1h; mp.out_hi = mp.a1h; mp.out_lo = mp.a1h;
+    if (p.epi == EPI_SCORE_CONF && p.conf && p.L.M % 4 == 0) {
+      conf_tma = make_map3(&mp.out_f32, p.conf, p.L.M, p.L.N, p.batch) ? 1 : 0;
+    }
   } else if (p.epi == EPI_KVT) {
     // transposed planes [n_out channels][out.ld = total rows]; box = 128 rows (inner) x 64 channels
     ok = ok && make_map(&mp.out_hi, p.out.hi, p.n_out, out_rows, p.out.ld, BM, 64, false) && make_map(&mp.out_lo, p.out.lo, p.n_out, out_rows, p.out.ld, BM, 64, false);
@@ -692,6 +867,9 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.a_batch_k = p.a_batch_k; tp.b_batch_k = p.b_batch_k;
   tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline;
+  tp.inv_scale = p.inv_scale; tp.rowsum_part = p.rowsum_part; tp.colsum_part = p.colsum_part; tp.inv_rowsum = p.inv_rowsum;
+  tp.inv_colsum = p.inv_colsum; tp.conf = p.conf; tp.conf_tma = conf_tma; tp.rowbest = p.rowbest; tp.colbest = p.colbest;
+  tp.mn_major = p.mn_major;
   tp.kmean = p.kmean; tp.cross = p.cross; tp.x_hi = p.resid.hi; tp.x_lo = p.resid.lo; tp.statpart = p.statpart;
   const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
   const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
@@ -712,6 +890,9 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
       case EPI_RESID: le = launch_variant<2, true, EPI_RESID>(cfg, mp, tp); break;
       case EPI_KVT: le = launch_variant<2, true, EPI_KVT>(cfg, mp, tp); break;
       case EPI_L2NORM: le = launch_variant<2, true, EPI_L2NORM>(cfg, mp, tp); break;
+      case EPI_SCORE_SUMS: le = launch_variant<2, true, EPI_SCORE_SUMS>(cfg, mp, tp); break;
+      case EPI_SCORE_CONF: le = launch_variant<2, true, EPI_SCORE_CONF>(cfg, mp, tp); break;
+      case EPI_KV: le = launch_variant<2, true, EPI_KV>(cfg, mp, tp); break;
       default: return -1;
     }
   } else if (CL == 2) {

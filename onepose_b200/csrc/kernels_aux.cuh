@@ -263,42 +263,32 @@ __global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
 // Tensor-core path of the linear-attention state.  The [K | V] projection epilogue (EPI_KVT) leaves
 // K^T (elu+1 applied) and V^T as fp16-split planes kvt[512][rows] with pad rows zeroed; one batched-K GEMM
 // then yields, per 256-row piece, part[piece][256 (K channel)][256 (V channel)] = K_piece^T V_piece.
-// kv_reduce_pieces: fixed-order sum over the pieces of a segment, diagonal head blocks only, 1/m scale.
-// grid (S*H, 16), block 256
-__global__ void kv_reduce_pieces(const float* __restrict__ part, Layout L, float* __restrict__ kvmean /*[S][H][64][64]*/) {
+// kv_reduce_pieces: fixed-order sum over the pieces of a segment, diagonal head blocks only, 1/m scale; the last
+// y-block of each (segment, head) combines the per-32-row K column sums (EPI_KV epilogue) into Kmean.
+// grid (S*H, 17), block 256
+__global__ void kv_reduce_pieces(const float* __restrict__ part, const float* __restrict__ ksum_part /*[rows/32][256]*/, Layout L,
+                                 float* __restrict__ kvmean /*[S][H][64][64]*/, float* __restrict__ kmean /*[S][256]*/) {
   const int sh = blockIdx.x;
   const int seg = sh / kHeads, h = sh % kHeads;
+  const int valid = L.seg_valid(seg);
+  const float inv_m = valid > 0 ? 1.f / (float)valid : 0.f;
+  if (blockIdx.y == 16) {
+    if (threadIdx.x < kDh) {
+      const int c = h * kDh + threadIdx.x;
+      const int q0 = L.seg_start(seg) / 32, nq = (valid + 31) / 32;
+      float s = 0.f;
+      for (int t = 0; t < nq; ++t) s += ksum_part[(long long)(q0 + t) * 256 + c];
+      kmean[seg * kD + c] = s * inv_m;
+    }
+    return;
+  }
   const int i = blockIdx.y * 256 + threadIdx.x;      // d*64 + q
   const int d = i >> 6, q = i & 63;
   const int p0 = L.seg_start(seg) / 256;
-  const int np = (L.seg_valid(seg) + 255) / 256;
+  const int np = (valid + 255) / 256;
   float s = 0.f;
   for (int t = 0; t < np; ++t) s += part[((long long)(p0 + t) * 256 + h * kDh + d) * 256 + h * kDh + q];
-  kvmean[(long long)sh * kDh * kDh + i] = L.seg_valid(seg) > 0 ? s * (1.f / (float)L.seg_valid(seg)) : 0.f;
-}
-// Kmean[s][c] = (1/m) sum over the segment's rows of K^T[c][row]  (pad rows are zero).  grid (256, S), block 128
-__global__ void kt_mean(const __half* __restrict__ kt_hi, const __half* __restrict__ kt_lo, long long rows_total, Layout L,
-                        float* __restrict__ kmean /*[S][256]*/) {
-  __shared__ float red[128];
-  const int c = blockIdx.x, seg = blockIdx.y;
-  const long long base = (long long)c * rows_total + L.seg_start(seg);
-  const int n = L.seg_padded(seg);
-  float acc = 0.f;
-  for (int r = threadIdx.x * 8; r < n; r += 128 * 8) {
-    const uint4 uh = *reinterpret_cast<const uint4*>(kt_hi + base + r);
-    const uint4 ul = *reinterpret_cast<const uint4*>(kt_lo + base + r);
-    const __half* hh = reinterpret_cast<const __half*>(&uh);
-    const __half* hl = reinterpret_cast<const __half*>(&ul);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc += join_f32(hh[e], hl[e]);
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) kmean[seg * kD + c] = L.seg_valid(seg) > 0 ? red[0] / (float)L.seg_valid(seg) : 0.f;
+  kvmean[(long long)sh * kDh * kDh + i] = s * inv_m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -557,6 +547,26 @@ __global__ void score_col_sums(const float* __restrict__ s, Layout L, float inv_
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
     colsum[b * L.m_pad + m] = t;
+  }
+}
+
+// Fused tail, stage between the two score-GEMM passes: fixed-order sums of the per-tile partials -> 1/rowsum, 1/colsum.
+// grid (ceil((n_pad + m_pad)/256), B), block 256
+__global__ void score_sums_finalize(const float* __restrict__ rowsum_part, const float* __restrict__ colsum_part, Layout L, int n_tiles,
+                                    int q_groups, float* __restrict__ inv_rowsum, float* __restrict__ inv_colsum) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < L.n_pad) {
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += rowsum_part[((long long)b * n_tiles + t) * L.n_pad + i];
+    inv_rowsum[b * L.n_pad + i] = i < L.N ? 1.f / s : 0.f;
+  } else if (i - L.n_pad < L.m_pad) {
+    const int m = i - L.n_pad;
+    const int qv = (L.N + 31) / 32;                     // quarters that hold valid query rows
+    float s = 0.f;
+    if (m < L.M)
+      for (int t = 0; t < qv && t < q_groups; ++t) s += colsum_part[((long long)b * q_groups + t) * L.m_pad + m];
+    inv_colsum[b * L.m_pad + m] = m < L.M ? 1.f / s : 0.f;
   }
 }
 
