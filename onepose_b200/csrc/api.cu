@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -98,6 +99,7 @@ struct opb_matcher {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<double> ev_flops;     // per GEMM launch
+  std::vector<int> ev_tag;          // per GEMM launch: epi*1000000 + n_out*100 + (K/64)  (OPB_PROFILE_DUMP)
   cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
   int launches = 0;
   int last_launches = 0;
@@ -168,7 +170,11 @@ static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, doubl
   if (m->profiling) cudaEventRecord(next_event(m), st);
   if (m->cfg.gemm_backend == 1) rc = launch_gemm_simt(p, st);
   else rc = launch_gemm_tc(p, st);
-  if (m->profiling) { cudaEventRecord(next_event(m), st); m->ev_flops.push_back(flops); }
+  if (m->profiling) {
+    cudaEventRecord(next_event(m), st);
+    m->ev_flops.push_back(flops);
+    m->ev_tag.push_back(p.epi * 1000000 + (p.mn_major ? 500000 : 0) + (p.n_out > 999 ? 999 : p.n_out) * 100 + (p.K1 + p.K2) / 64);
+  }
   m->launches++;
   if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (rc=%d, backend=%d): %s", rc,
                            m->cfg.gemm_backend, cudaGetErrorString(cudaGetLastError()));
@@ -628,6 +634,7 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (m->profiling) {
     m->ev_used = 0;
     m->ev_flops.clear();
+    m->ev_tag.clear();
     if (!m->ev_fwd0) { cudaEventCreate(&m->ev_fwd0); cudaEventCreate(&m->ev_fwd1); }
     cudaEventRecord(m->ev_fwd0, st);
   }
@@ -665,6 +672,20 @@ int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t
   }
   float tot = 0;
   CK(m, cudaEventElapsedTime(&tot, m->ev_fwd0, m->ev_fwd1));
+  if (getenv("OPB_PROFILE_DUMP")) {
+    std::map<int, std::pair<double, std::pair<double, int>>> agg;
+    for (size_t i = 0; i < m->ev_flops.size(); ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, m->ev_pool[2 * i], m->ev_pool[2 * i + 1]);
+      auto& a = agg[m->ev_tag[i]];
+      a.first += t; a.second.first += m->ev_flops[i]; a.second.second++;
+    }
+    fprintf(stderr, "[opb profile] forward %.3f ms, GEMM %.3f ms\n", tot, ms);
+    for (auto& kv : agg)
+      fprintf(stderr, "[opb profile] epi %d%s n_out %3d K %4d: %3d launches %8.3f ms  %7.1f TFLOP/s algorithmic\n", kv.first / 1000000,
+              (kv.first / 500000) % 2 ? " (mn)" : "", (kv.first % 500000) / 100, (kv.first % 100) * 64, kv.second.second.second, kv.second.first,
+              kv.second.second.first / (kv.second.first * 1e-3) / 1e12);
+  }
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_flops) *gemm_flops = fl;
   if (gemm_launches) *gemm_launches = (int32_t)m->ev_flops.size();

@@ -220,6 +220,8 @@ constexpr uint32_t kIdesc2MN = kIdesc2 | (1u << 15) | (1u << 16);               
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+// same for a 128-row x 64-B SWIZZLE_64B buffer (16-byte chunk j in 0..3): Swizzle<2,4,3> = address bits [4,6) ^= bits [7,9)
+__device__ __forceinline__ uint32_t stg64_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
 struct TcParams {
   int K1, K2;            // reduction split (multiples of BK)
@@ -255,7 +257,7 @@ struct TcParams {
 struct Maps {
   CUtensorMap a1h, a1l, a2h, a2l, b1h, b1l, b2h, b2l;   // loads
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128 (SWIZZLE_128B)
-  CUtensorMap out_hi, out_lo;                             // store: planes, box 64 x 128 (SWIZZLE_128B); EPI_KVT: transposed, box 128 x 64 (no swizzle)
+  CUtensorMap out_hi, out_lo;                             // store: planes, box 32 x 128 (SWIZZLE_64B); EPI_KVT: transposed, box 128 x 64 (no swizzle)
 };
 
 // CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
@@ -597,8 +599,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         }
       } else {
         // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM / EPI_KV
-        uint8_t* st_hi = staging;
-        uint8_t* st_lo = staging + kStagingBytes;
         float inv_norm = 1.f;
         if (EPI == EPI_L2NORM) {                    // F.normalize: first pass over the accumulator for the row norm
           float ss = 0.f;
@@ -662,42 +662,45 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= inv_norm;
           }
-          if (leader) tma_store_wait_read<0>();
-          epi_bar();
+          // two 32-column sub-chunks; each has its own (hi, lo) pair of 8 KB SWIZZLE_64B staging buffers, so the TMA
+          // store of one sub-chunk drains while the next is being written (same 32 KB of staging as the fp32 path)
 #pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            uint4 oh, ol;
+          for (int sc = 0; sc < 2; ++sc, ++chunk_ctr) {
+            uint8_t* sh = staging + (chunk_ctr & 1) * 8192;
+            uint8_t* sl = staging + kStagingBytes + (chunk_ctr & 1) * 8192;
+            if (leader) tma_store_wait_read<1>();
+            epi_bar();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __half h, l;
-              split_f32(x[j8 * 8 + e], h, l);
-              reinterpret_cast<__half*>(&oh)[e] = h;
-              reinterpret_cast<__half*>(&ol)[e] = l;
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 oh, ol;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                __half h, l;
+                split_f32(x[sc * 32 + j8 * 8 + e], h, l);
+                reinterpret_cast<__half*>(&oh)[e] = h;
+                reinterpret_cast<__half*>(&ol)[e] = l;
+              }
+              *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
+              *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
             }
-            *reinterpret_cast<uint4*>(st_hi + stg_off(r_in_tile, j8)) = oh;
-            *reinterpret_cast<uint4*>(st_lo + stg_off(r_in_tile, j8)) = ol;
-          }
-          fence_async_smem();
-          epi_bar();
-          if (leader) {
-            tma_store_2d(&maps.out_hi, st_hi, col0, out_row0);
-            tma_store_2d(&maps.out_lo, st_lo, col0, out_row0);
-            tma_store_commit();
-          }
-          if (EPI == EPI_KV && col0 < p.elu_cols) {
-            // K mean of the linear attention: per-32-row column sums of elu1(K) from the staged planes
-            const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;       // thread = (quarter, column pair)
-            float s0 = 0.f, s1 = 0.f;
-            for (int i = 0; i < 32; ++i) {
-              const int r = qq * 32 + i;
-              const uint32_t off = stg_off(r, cc >> 2) + (cc & 3) * 4;        // two adjacent halves = columns 2cc, 2cc+1
-              const __half2 h2 = *reinterpret_cast<const __half2*>(st_hi + off);
-              const __half2 l2 = *reinterpret_cast<const __half2*>(st_lo + off);
-              s0 += join_f32(__low2half(h2), __low2half(l2));
-              s1 += join_f32(__high2half(h2), __high2half(l2));
+            fence_async_smem();
+            epi_bar();
+            if (leader) {
+              tma_store_2d(&maps.out_hi, sh, col0 + sc * 32, out_row0);
+              tma_store_2d(&maps.out_lo, sl, col0 + sc * 32, out_row0);
+              tma_store_commit();
             }
-            float2* dst = reinterpret_cast<float2*>(p.statpart + (long long)(out_row0 / 32 + qq) * 256 + col0 + 2 * cc);
-            *dst = make_float2(s0, s1);
+            if (EPI == EPI_KV && col0 < p.elu_cols) {
+              // K mean of the linear attention: per-32-row column sums of elu1(K) from the staged planes
+              const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;       // thread = (quarter, column)
+              float s0 = 0.f;
+#pragma unroll 8
+              for (int i = 0; i < 32; ++i) {
+                const uint32_t off = stg64_off(qq * 32 + i, cc >> 3) + (cc & 7) * 2;
+                s0 += join_f32(*reinterpret_cast<const __half*>(sh + off), *reinterpret_cast<const __half*>(sl + off));
+              }
+              p.statpart[(long long)(out_row0 / 32 + qq) * 256 + col0 + sc * 32 + cc] = s0;
+            }
           }
         }
       }
@@ -857,7 +860,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     ok = ok && make_map(&mp.out_hi, p.out.hi, p.n_out, out_rows, p.out.ld, BM, 64, false) && make_map(&mp.out_lo, p.out.lo, p.n_out, out_rows, p.out.ld, BM, 64, false);
     mp.out_f32 = mp.out_hi;
   } else {
-    ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, p.n_out, p.out.ld, 64, BM, false) && make_map(&mp.out_lo, p.out.lo, out_rows, p.n_out, p.out.ld, 64, BM, false);
+    ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, p.n_out, p.out.ld, 32, BM, false) && make_map(&mp.out_lo, p.out.lo, out_rows, p.n_out, p.out.ld, 32, BM, false);
     mp.out_f32 = mp.out_hi;
   }
   if (!ok) return -2;
