@@ -96,6 +96,11 @@ int opb_last_launch_count(const opb_matcher* m);
 int opb_set_profiling(opb_matcher* m, int32_t enable);
 int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms);
 
+/* Which element-wise consumers ride in the GEMM epilogues (gemm_backend 0 only): 0 = none, 1 = those that measured
+ * faster in-stream on B200 (InstanceNorm partial sums, residual add, L2 normalise; default), 2 = all (K/V planes +
+ * tensor-core KV state, Q scaling, dual-softmax tail).  All levels give the same results to fp32 rounding. */
+int opb_set_fuse_level(opb_matcher* m, int32_t level);
+
 /* GNN layers 0 (GATs) and the 3D side of layer 1 (self) depend only on the per-object constants; by default they
  * are evaluated once per opb_forward call and shared by its frames.  enable = 0 evaluates them per frame like the
  * reference does (same results up to fp32 rounding; used by the tests). */

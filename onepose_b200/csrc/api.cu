@@ -88,6 +88,8 @@ struct opb_matcher {
   int ws_frames = 0, ws_N = 0;
   PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
   DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
+  int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
+                         // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
   DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
@@ -98,8 +100,8 @@ struct opb_matcher {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  std::vector<double> ev_flops;     // per GEMM launch
-  std::vector<int> ev_tag;          // per GEMM launch: epi*1000000 + n_out*100 + (K/64)  (OPB_PROFILE_DUMP)
+  std::vector<double> ev_flops;     // per profiled launch (0 for the helper kernels)
+  std::vector<std::string> ev_name; // per profiled launch; an event is recorded AFTER every launch, durations = consecutive differences
   cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
   int launches = 0;
   int last_launches = 0;
@@ -164,16 +166,24 @@ static cudaEvent_t next_event(opb_matcher* m) {
   return m->ev_pool[m->ev_used++];
 }
 
-// One launch of the selected GEMM core producing fp32 C (+bias).  `flops` = algorithmic FLOPs.
+// Profiling (bench.py roofline leg): one event after every launch on the stream; a launch's time is the difference to the
+// previous event (so it includes any launch gap in front of it).
+static void prof_mark(opb_matcher* m, cudaStream_t st, const char* name, double flops) {
+  if (!m->profiling) return;
+  cudaEventRecord(next_event(m), st);
+  m->ev_flops.push_back(flops);
+  m->ev_name.push_back(name);
+}
+
+// One launch of the selected GEMM core.  `flops` = algorithmic FLOPs.
 static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, double flops) {
   int rc;
-  if (m->profiling) cudaEventRecord(next_event(m), st);
   if (m->cfg.gemm_backend == 1) rc = launch_gemm_simt(p, st);
   else rc = launch_gemm_tc(p, st);
   if (m->profiling) {
-    cudaEventRecord(next_event(m), st);
-    m->ev_flops.push_back(flops);
-    m->ev_tag.push_back(p.epi * 1000000 + (p.mn_major ? 500000 : 0) + (p.n_out > 999 ? 999 : p.n_out) * 100 + (p.K1 + p.K2) / 64);
+    char tag[96];
+    snprintf(tag, sizeof tag, "gemm epi%d%s n%d k%d", p.epi, p.mn_major ? "mn" : "", p.n_out, p.K1 + p.K2);
+    prof_mark(m, st, tag, flops);
   }
   m->launches++;
   if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (rc=%d, backend=%d): %s", rc,
@@ -228,6 +238,7 @@ static int run_gats(opb_matcher* m, const Layout& L, PlaneBuf& x, int gi, cudaSt
       x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
       m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
   m->launches++;
+  prof_mark(m, st, "gats_aggregate", 0.0);
   return 0;
 }
 
@@ -239,9 +250,9 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   const int tiles = rows / kTileRows;
   const double valid_rows = (double)L.B * (L.N + L.M);
   __half *xh = x.hi.as<__half>(), *xl = x.lo.as<__half>();
-  auto launched = [&]() { m->launches++; };
-  if (m->cfg.gemm_backend == 0) {
-    // ---------------- fused tcgen05 pipeline ----------------
+  auto launched = [&](const char* name = "aux") { m->launches++; prof_mark(m, st, name, 0.0); };
+  if (m->cfg.gemm_backend == 0 && m->fuse >= 2) {
+    // ---------------- fully fused tcgen05 pipeline ----------------
     // (1) [K | V] projection; epilogue: elu+1 on K, pad rows zeroed -> fp16-split planes kv[rows, 512], plus the
     //     per-32-row column sums of K (for the K mean)
     GemmProblem pk{};
@@ -260,10 +271,10 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
     if (int rc = run_gemm(m, ps, st, 2.0 * valid_rows * kD * kDh)) return rc;
     kv_reduce_pieces<<<dim3(S * kHeads, 17), 256, 0, st>>>(m->kvpieces.as<float>(), m->ksum_part.as<float>(), L, m->kvmean.as<float>(),
                                                           m->kmean.as<float>());
-    launched();
+    launched("kv_reduce_pieces");
     // (3) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
     g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
-    launched();
+    launched("g_fold");
     // (4) q projection; epilogue: elu+1, per-head normaliser with the SOURCE segment's K mean -> Q' planes (:78-79)
     GemmProblem pq{};
     pq.L = L; pq.batch = 1; pq.rows = rows;
@@ -279,10 +290,10 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
     p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
     if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
     in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
-    launched();
+    launched("in_stats_final");
     norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                     m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-    launched();
+    launched("norm_relu_split");
     // (6) delta = mlp.3(hn); epilogue: x += delta + bias, re-split, in place (:59/:64)
     GemmProblem p3{};
     p3.L = L; p3.batch = 1; p3.rows = rows;
@@ -297,40 +308,51 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
   if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)
-  kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
-  launched();
+  if (m->cfg.gemm_backend == 1)   // SIMT cross-check path keeps the plain FFMA kernel
+    kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+  else
+    kv_state_partial_mma<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+  launched("kv_state_partial");
   kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
-  launched();
+  launched("kv_state_reduce");
   // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
   q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
                                                                                 m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
-  launched();
+  launched("q_scale_split");
   // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
   g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
-  launched();
+  launched("g_fold");
   // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
+  const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
   GemmProblem p2{};
   p2.L = L; p2.batch = 1; p2.rows = rows;
   p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
   p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
   p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
+  if (fuse1) { p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>(); }   // InstanceNorm partial sums in the epilogue
   if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
   // (6) InstanceNorm statistics per segment (:126)
-  in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
-  launched();
+  if (!fuse1) {
+    in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
+    launched("in_stats_partial");
+  }
   in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
-  launched();
+  launched("in_stats_final");
   norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                   m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-  launched();
+  launched("norm_relu_split");
   // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64)
   GemmProblem p3{};
   p3.L = L; p3.batch = 1; p3.rows = rows;
   p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
   p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
+  if (fuse1) {                                       // residual add + re-split in the epilogue, in place
+    p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
+    return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
+  }
   if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
   residual_update<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, xl, m->c768.as<float>(), (long long)rows * kD / 8);
-  launched();
+  launched("residual_update");
   return 0;
 }
 
@@ -356,7 +378,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   const int rows = L.rows();
   const double valid_rows = (double)fb * (N + L.M);
   __half *xh = m->x.hi.as<__half>(), *xl = m->x.lo.as<__half>();
-  auto launched = [&]() { m->launches++; };
+  auto launched = [&](const char* name = "aux") { m->launches++; prof_mark(m, st, name, 0.0); };
 
   int first_layer = 0;
   if (m->hoist) {
@@ -365,7 +387,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     Lq.B = fb; Lq.N = N; Lq.M = 0; Lq.n_pad = L.n_pad; Lq.m_pad = 0; Lq.R = L.n_pad;
     transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, m->xq.hi.as<__half>(), m->xq.lo.as<__half>(),
                                                                              nullptr, Lq.R, 0);
-    launched();
+    launched("transpose_cf_to_rows");
     if (int rc = run_attn_layer(m, Lq, m->xq, m->attn[0], 0, st)) return rc;
     // assemble the full layout: query rows from xq, 3D rows from the object prologue
     CK(m, cudaMemcpy2DAsync(xh, (size_t)L.R * kD * sizeof(__half), m->xq.hi.p, (size_t)L.n_pad * kD * sizeof(__half),
@@ -373,14 +395,14 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     CK(m, cudaMemcpy2DAsync(xl, (size_t)L.R * kD * sizeof(__half), m->xq.lo.p, (size_t)L.n_pad * kD * sizeof(__half),
                             (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
     broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->xo.hi.as<__half>(), m->xo.lo.as<__half>(), xh, xl, L);
-    launched();
+    launched("broadcast_object_rows");
     first_layer = 2;
   } else {
     // inputs: query descriptors [fb,256,N] channel-first -> q segments; object rows -> d segments
     transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, xh, xl, nullptr, L.R, 0);
-    launched();
+    launched("transpose_cf_to_rows");
     broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->db.hi.as<__half>(), m->db.lo.as<__half>(), xh, xl, L);
-    launched();
+    launched("broadcast_object_rows");
   }
 
   for (int layer = first_layer; layer < 12; ++layer) {
@@ -397,16 +419,16 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   pf.L = L; pf.batch = 1; pf.rows = rows;
   pf.a1 = m->x.c(kD); pf.K1 = kD; pf.b1 = m->wf.c(kD); pf.n_out = 256;
   pf.bias = m->bf.as<float>(); pf.c = m->c768.as<float>(); pf.ldc = 256;
-  if (m->cfg.gemm_backend == 0) {
+  if (m->cfg.gemm_backend == 0 && m->fuse >= 1) {
     pf.epi = EPI_L2NORM; pf.out = m->pn.m(kD);       // F.normalize fused into the final_proj epilogue (:209-213)
     if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
   } else {
     if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
     l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
-    launched();
+    launched("l2_normalize_split");
   }
   const float inv_scale = 1.f / m->cfg.scale_factor;
-  if (m->cfg.gemm_backend == 0) {
+  if (m->cfg.gemm_backend == 0 && m->fuse >= 2) {
     // ---- fused tail: two passes of the batched score GEMM, nothing N x M ever read back
     const int n_tiles = L.m_pad / 256, q_groups = L.n_pad / 32;
     GemmProblem ps{};
@@ -418,7 +440,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
     score_sums_finalize<<<dim3((L.n_pad + L.m_pad + 255) / 256, fb), 256, 0, st>>>(m->rowsum_part.as<float>(), m->colsum_part.as<float>(), L, n_tiles,
                                                                                   q_groups, m->rowsum.as<float>(), m->colsum.as<float>());
-    launched();
+    launched("score_sums_finalize");
     CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
     CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
     ps.epi = EPI_SCORE_CONF; ps.inv_rowsum = m->rowsum.as<float>(); ps.inv_colsum = m->colsum.as<float>();
@@ -433,19 +455,19 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   ps.c = m->score.as<float>(); ps.ldc = L.m_pad;
   if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
   score_row_sums<<<(unsigned)(((long long)fb * N * 32 + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>());
-  launched();
+  launched("score_row_sums");
   score_col_sums<<<dim3((L.M + 31) / 32, fb), dim3(32, 8), 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
-  launched();
+  launched("score_col_sums");
   CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
   CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
   conf_argmax_simt<<<dim3((L.M + 127) / 128, (N + 31) / 32, fb), 128, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>(),
                                                                               m->colsum.as<float>(), conf,
                                                                               m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
-  launched();
+  launched("conf_argmax_simt");
   }
   mutual_match<<<fb, 256, 0, st>>>(m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>(), N, L.M, m->cfg.match_threshold,
                                    reinterpret_cast<long long*>(m0), reinterpret_cast<long long*>(m1), s0, s1);
-  launched();
+  launched("mutual_match");
   CK(m, cudaGetLastError());
   return 0;
 }
@@ -474,6 +496,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   if (prop.major != 10) return fail(nullptr, OPB_E_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   auto* m = new opb_matcher();
   m->cfg = *cfg;
+  if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
   *out = m;
   return OPB_OK;
 }
@@ -608,6 +631,12 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
   return OPB_OK;
 }
 
+int opb_set_fuse_level(opb_matcher* m, int32_t level) {
+  if (!m || level < 0 || level > 2) return OPB_E_INVALID;
+  m->fuse = level;
+  return OPB_OK;
+}
+
 int opb_set_hoist(opb_matcher* m, int32_t enable) {
   if (!m) return OPB_E_INVALID;
   m->hoist = enable != 0;
@@ -634,7 +663,7 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (m->profiling) {
     m->ev_used = 0;
     m->ev_flops.clear();
-    m->ev_tag.clear();
+    m->ev_name.clear();
     if (!m->ev_fwd0) { cudaEventCreate(&m->ev_fwd0); cudaEventCreate(&m->ev_fwd1); }
     cudaEventRecord(m->ev_fwd0, st);
   }
@@ -657,6 +686,7 @@ int opb_set_profiling(opb_matcher* m, int32_t enable) {
   m->profiling = enable != 0;
   m->ev_used = 0;
   m->ev_flops.clear();
+  m->ev_name.clear();
   return OPB_OK;
 }
 
@@ -664,31 +694,26 @@ int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t
   if (!m || !m->ev_fwd1) return OPB_E_STATE;
   CK(m, cudaEventSynchronize(m->ev_fwd1));
   double ms = 0, fl = 0;
+  int n_gemm = 0;
+  std::map<std::string, std::pair<double, std::pair<double, int>>> agg;
   for (size_t i = 0; i < m->ev_flops.size(); ++i) {
     float t = 0;
-    CK(m, cudaEventElapsedTime(&t, m->ev_pool[2 * i], m->ev_pool[2 * i + 1]));
-    ms += t;
-    fl += m->ev_flops[i];
+    CK(m, cudaEventElapsedTime(&t, i == 0 ? m->ev_fwd0 : m->ev_pool[i - 1], m->ev_pool[i]));
+    if (m->ev_flops[i] > 0) { ms += t; fl += m->ev_flops[i]; ++n_gemm; }
+    auto& a = agg[m->ev_name[i]];
+    a.first += t; a.second.first += m->ev_flops[i]; a.second.second++;
   }
   float tot = 0;
   CK(m, cudaEventElapsedTime(&tot, m->ev_fwd0, m->ev_fwd1));
   if (getenv("OPB_PROFILE_DUMP")) {
-    std::map<int, std::pair<double, std::pair<double, int>>> agg;
-    for (size_t i = 0; i < m->ev_flops.size(); ++i) {
-      float t = 0;
-      cudaEventElapsedTime(&t, m->ev_pool[2 * i], m->ev_pool[2 * i + 1]);
-      auto& a = agg[m->ev_tag[i]];
-      a.first += t; a.second.first += m->ev_flops[i]; a.second.second++;
-    }
-    fprintf(stderr, "[opb profile] forward %.3f ms, GEMM %.3f ms\n", tot, ms);
+    fprintf(stderr, "[opb profile] forward %.3f ms, GEMM %.3f ms in %d launches\n", tot, ms, n_gemm);
     for (auto& kv : agg)
-      fprintf(stderr, "[opb profile] epi %d%s n_out %3d K %4d: %3d launches %8.3f ms  %7.1f TFLOP/s algorithmic\n", kv.first / 1000000,
-              (kv.first / 500000) % 2 ? " (mn)" : "", (kv.first % 500000) / 100, (kv.first % 100) * 64, kv.second.second.second, kv.second.first,
-              kv.second.second.first / (kv.second.first * 1e-3) / 1e12);
+      fprintf(stderr, "[opb profile] %-28s %4d launches %8.3f ms %5.1f%%  %7.1f TFLOP/s algorithmic\n", kv.first.c_str(), kv.second.second.second,
+              kv.second.first, 100.0 * kv.second.first / tot, kv.second.second.first / (kv.second.first * 1e-3) / 1e12);
   }
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_flops) *gemm_flops = fl;
-  if (gemm_launches) *gemm_launches = (int32_t)m->ev_flops.size();
+  if (gemm_launches) *gemm_launches = (int32_t)n_gemm;
   if (total_ms) *total_ms = tot;
   return OPB_OK;
 }

@@ -99,6 +99,7 @@ class GATsSuperGlue(nn.Module):
         self._object_key = None
         self._chunk_frames = 0
         self._hoist = True
+        self._fuse = None
         self.last_batched = None       # batched outputs of the last forward (all B frames)
 
     # ------------------------------------------------------------------ handle / weights
@@ -127,6 +128,8 @@ class GATsSuperGlue(nn.Module):
             _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
         if not self._hoist:
             _lib.check(self._lib.opb_set_hoist(self._handle, 0), self._handle)
+        if self._fuse is not None:
+            _lib.check(self._lib.opb_set_fuse_level(self._handle, self._fuse), self._handle)
 
     def _sync_weights(self):
         key = tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
@@ -138,6 +141,12 @@ class GATsSuperGlue(nn.Module):
         _lib.check(self._lib.opb_finalize_weights(self._handle), self._handle)
         self._weights_key = key
         self._object_key = None
+
+    def set_fuse_level(self, level: int):
+        """0 / 1 / 2: how much element-wise work rides in the GEMM epilogues (see opb_set_fuse_level)."""
+        self._fuse = int(level)
+        if self._handle is not None:
+            _lib.check(self._lib.opb_set_fuse_level(self._handle, self._fuse), self._handle)
 
     def set_hoist(self, enable: bool):
         """Evaluate the frame-invariant GNN layers once per call (default) or per frame like the reference."""

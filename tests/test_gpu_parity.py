@@ -225,6 +225,19 @@ def test_object_prologue_hoisting_matches_per_frame_evaluation(backend):
     assert torch.equal(outs[0]["matches0"], outs[1]["matches0"])
 
 
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_fuse_levels_agree(level):
+    """Every epilogue-fusion level of the tcgen05 path gives the oracle's answer."""
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    data = synthetic.make_batch(6, [3, 4, 5], 333, 700, 8)
+    ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+    m = _module(sd, hp, "tcgen05")
+    m.set_fuse_level(level)
+    m(_cuda(data))
+    _check_against(m.last_batched, ref, f"fuse level {level}")
+
+
 def test_repeat_calls_are_deterministic():
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
