@@ -656,7 +656,7 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (!q || !m0 || !m1 || !s0 || !s1 || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward: bad argument (B=%d, N=%d)", B, N);
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 4;
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 16;
   if (chunk > B) chunk = B;
   if (int rc = ensure_workspace(m, chunk, N)) return rc;
   m->launches = 0;

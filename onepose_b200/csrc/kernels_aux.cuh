@@ -146,14 +146,24 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = include_self ? (p_self * inv) * h3[j] : 0.f;
-  for (int c = 0; c < n_leaf; ++c) {
-    float a = __shfl_sync(0xffffffffu, p, c) * inv;
-    const float4* lr = reinterpret_cast<const float4*>(leaves + ((long long)i * n_leaf + c) * kD);
-    float4 u = lr[lane], v = lr[32 + lane];
-    acc[0] = fmaf(a, u.x, acc[0]); acc[1] = fmaf(a, u.y, acc[1]);
-    acc[2] = fmaf(a, u.z, acc[2]); acc[3] = fmaf(a, u.w, acc[3]);
-    acc[4] = fmaf(a, v.x, acc[4]); acc[5] = fmaf(a, v.y, acc[5]);
-    acc[6] = fmaf(a, v.z, acc[6]); acc[7] = fmaf(a, v.w, acc[7]);
+  // leaves in batches of 4 rows: 8 independent 16-byte loads per lane in flight before the first use
+  for (int c0 = 0; c0 < n_leaf; c0 += 4) {
+    float4 u[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = min(c0 + k, n_leaf - 1);
+      const float4* lr = reinterpret_cast<const float4*>(leaves + ((long long)i * n_leaf + c) * kD);
+      u[k] = lr[lane];
+      v[k] = lr[32 + lane];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = (c0 + k < n_leaf) ? __shfl_sync(0xffffffffu, p, (c0 + k) & 31) * inv : 0.f;
+      acc[0] = fmaf(a, u[k].x, acc[0]); acc[1] = fmaf(a, u[k].y, acc[1]);
+      acc[2] = fmaf(a, u[k].z, acc[2]); acc[3] = fmaf(a, u[k].w, acc[3]);
+      acc[4] = fmaf(a, v[k].x, acc[4]); acc[5] = fmaf(a, v[k].y, acc[5]);
+      acc[6] = fmaf(a, v[k].z, acc[6]); acc[7] = fmaf(a, v[k].w, acc[7]);
+    }
   }
   uint2 oh[2], ol[2];
 #pragma unroll
@@ -258,7 +268,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 constexpr int kKvLd = 264;   // smem row stride (floats): 8 mod 32 -> conflict-free fragment loads
-__global__ void __launch_bounds__(256) kv_state_partial_mma(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated,
+__global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated,
                                                             Layout L, float* __restrict__ partial) {
   __shared__ __align__(16) uint32_t sKh[8][kKvLd], sKl[8][kKvLd], sVh[8][kKvLd], sVl[8][kKvLd];
   const int tile = blockIdx.x;
@@ -270,19 +280,30 @@ __global__ void __launch_bounds__(256) kv_state_partial_mma(const float* __restr
   const int h = warp >> 1, mh = (warp & 1) * 32;
   float acc[2][8][4] = {};
   float ksum = 0.f;                               // thread tid owns K column tid
-  for (int r0 = 0; r0 < n_valid; r0 += 8) {
-    // stage 8 rows: 8 x 512 floats, split into tf32 hi / lo once
+  // software pipeline: the global loads of the NEXT 8 rows are in flight while the current 8 rows go through the MMAs
+  float4 pre[4];
+  auto prefetch = [&](int r0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;              // 0..1023 float4 slots: row = idx / 128, 128 float4 per row (K 64 | V 64)
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool is_k = c4 < 256;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + rr < n_valid) {
         const float* rowp = kv + (long long)(row0 + r0 + rr) * ld;
-        x = *reinterpret_cast<const float4*>(rowp + (is_k ? k_off + c4 : v_off + c4 - 256));
-        if (is_k && !k_activated) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+        pre[i] = *reinterpret_cast<const float4*>(rowp + (c4 < 256 ? k_off + c4 : v_off + c4 - 256));
       }
+    }
+  };
+  if (n_valid > 0) prefetch(0);
+  for (int r0 = 0; r0 < n_valid; r0 += 8) {
+    // stage 8 rows: 8 x 512 floats, split into tf32 hi / lo once
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int rr = idx >> 7, c4 = (idx & 127) * 4;
+      float4 x = pre[i];
+      const bool is_k = c4 < 256;
+      if (is_k && !k_activated && r0 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
       const float xs[4] = {x.x, x.y, x.z, x.w};
       uint32_t hi[4], lo[4];
 #pragma unroll
@@ -296,6 +317,7 @@ __global__ void __launch_bounds__(256) kv_state_partial_mma(const float* __restr
       *reinterpret_cast<uint4*>(dl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     __syncthreads();
+    if (r0 + 8 < n_valid) prefetch(r0 + 8);
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) ksum += __uint_as_float(sKh[rr][tid]) + __uint_as_float(sKl[rr][tid]);
     // A = K^T (m = K channel, k = row), B = V (k = row, n = V channel)
