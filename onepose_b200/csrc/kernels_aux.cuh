@@ -254,23 +254,24 @@ __global__ void __launch_bounds__(256) kv_state_partial(const float* __restrict_
   }
 }
 
-// Same partial sums on the (legacy) warp-level tensor-core path: mma.sync m16n8k8 TF32 with the 3-pass hi/lo split
-// (3xTF32), reading the fp32 [K | V] rows the QKV GEMM wrote.  One block = one 128-row tile, all 4 heads; warp w owns
-// head w/2 and 32 of its 64 K-channels (2 m16 tiles) x all 64 V-channels (8 n8 tiles).
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+// Same partial sums on the warp-level tensor-core path (mma.sync m16n8k16, fp16 operands, fp32 accumulate) with
+// the fp16 hi/lo split of common.cuh (3 passes), reading the fp32 [K | V] rows the QKV GEMM wrote.  One block = one
+// 128-row tile, all 4 heads; warp w owns head w/2 and 32 of its 64 K-channels (2 m16 tiles) x all 64 V-channels.
+// K^T and V fragments come straight from row-major smem tiles through ldmatrix.trans.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
 }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-constexpr int kKvLd = 264;   // smem row stride (floats): 8 mod 32 -> conflict-free fragment loads
+constexpr int kKvLd = 264;   // smem row stride in halves (528 B): 16-byte aligned rows, conflict-free ldmatrix
 __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated,
-                                                            Layout L, float* __restrict__ partial) {
-  __shared__ __align__(16) uint32_t sKh[8][kKvLd], sKl[8][kKvLd], sVh[8][kKvLd], sVl[8][kKvLd];
+                                                               Layout L, float* __restrict__ partial) {
+  __shared__ __align__(16) __half sKh[16][kKvLd], sKl[16][kKvLd], sVh[16][kKvLd], sVl[16][kKvLd];
   const int tile = blockIdx.x;
   const int row0 = tile * kTileRows;
   const int seg = L.seg_of_row(row0);
@@ -280,12 +281,12 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
   const int h = warp >> 1, mh = (warp & 1) * 32;
   float acc[2][8][4] = {};
   float ksum = 0.f;                               // thread tid owns K column tid
-  // software pipeline: the global loads of the NEXT 8 rows are in flight while the current 8 rows go through the MMAs
-  float4 pre[4];
+  // software pipeline: the global loads of the NEXT 16 rows are in flight while the current 16 rows go through the MMAs
+  float4 pre[8];
   auto prefetch = [&](int r0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * 256;              // 0..1023 float4 slots: row = idx / 128, 128 float4 per row (K 64 | V 64)
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;              // 0..2047 float4 slots: row = idx / 128, 128 float4 per row (K 64 | V 64)
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
       pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + rr < n_valid) {
@@ -295,51 +296,53 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
     }
   };
   if (n_valid > 0) prefetch(0);
-  for (int r0 = 0; r0 < n_valid; r0 += 8) {
-    // stage 8 rows: 8 x 512 floats, split into tf32 hi / lo once
+  for (int r0 = 0; r0 < n_valid; r0 += 16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
       float4 x = pre[i];
       const bool is_k = c4 < 256;
       if (is_k && !k_activated && r0 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
       const float xs[4] = {x.x, x.y, x.z, x.w};
-      uint32_t hi[4], lo[4];
+      __half hi[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        hi[e] = to_tf32(xs[e]);
-        lo[e] = to_tf32(xs[e] - __uint_as_float(hi[e]));
-      }
-      uint32_t* dh = is_k ? &sKh[rr][c4] : &sVh[rr][c4 - 256];
-      uint32_t* dl = is_k ? &sKl[rr][c4] : &sVl[rr][c4 - 256];
-      *reinterpret_cast<uint4*>(dh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(dl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      for (int e = 0; e < 4; ++e) split_f32(xs[e], hi[e], lo[e]);
+      __half* dh = is_k ? &sKh[rr][c4] : &sVh[rr][c4 - 256];
+      __half* dl = is_k ? &sKl[rr][c4] : &sVl[rr][c4 - 256];
+      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(hi);
+      *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(lo);
     }
     __syncthreads();
-    if (r0 + 8 < n_valid) prefetch(r0 + 8);
+    if (r0 + 16 < n_valid) prefetch(r0 + 16);
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) ksum += __uint_as_float(sKh[rr][tid]) + __uint_as_float(sKl[rr][tid]);
-    // A = K^T (m = K channel, k = row), B = V (k = row, n = V channel)
+    for (int rr = 0; rr < 16; ++rr) ksum += join_f32(sKh[rr][tid], sKl[rr][tid]);
+    // A = K^T (m = K channel, k = row): 16x16 blocks of the row-major K tile, transposed on load
     uint32_t ah[2][4], al[2][4];
+    const int a_row = (lane & 7) + 8 * (lane >> 4), a_col = 8 * ((lane >> 3) & 1);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       const int d0 = h * kDh + mh + mt * 16;
-      ah[mt][0] = sKh[t][d0 + g];     ah[mt][1] = sKh[t][d0 + g + 8];
-      ah[mt][2] = sKh[t + 4][d0 + g]; ah[mt][3] = sKh[t + 4][d0 + g + 8];
-      al[mt][0] = sKl[t][d0 + g];     al[mt][1] = sKl[t][d0 + g + 8];
-      al[mt][2] = sKl[t + 4][d0 + g]; al[mt][3] = sKl[t + 4][d0 + g + 8];
+      ldmatrix_x4_trans(ah[mt], &sKh[a_row][d0 + a_col]);
+      ldmatrix_x4_trans(al[mt], &sKl[a_row][d0 + a_col]);
     }
+    // B = V (k = row, n = V channel): two n8 tiles per ldmatrix.x4.trans
+    const int b_row = (lane & 7) + 8 * ((lane >> 3) & 1), b_col = 8 * (lane >> 4);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int q0 = h * kDh + nt * 8;
-      const uint32_t bh[2] = {sVh[t][q0 + g], sVh[t + 4][q0 + g]};
-      const uint32_t bl[2] = {sVl[t][q0 + g], sVl[t + 4][q0 + g]};
+    for (int np = 0; np < 4; ++np) {
+      const int q0 = h * kDh + np * 16;
+      uint32_t bh[4], bl[4];
+      ldmatrix_x4_trans(bh, &sVh[b_row][q0 + b_col]);
+      ldmatrix_x4_trans(bl, &sVl[b_row][q0 + b_col]);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        mma_tf32(acc[mt][nt], ah[mt], bh);
-        mma_tf32(acc[mt][nt], ah[mt], bl);
-        mma_tf32(acc[mt][nt], al[mt], bh);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          float (&d)[4] = acc[mt][np * 2 + s2];
+          mma_f16(d, ah[mt], bh[2 * s2], bh[2 * s2 + 1]);
+          mma_f16(d, ah[mt], bl[2 * s2], bl[2 * s2 + 1]);
+          mma_f16(d, al[mt], bh[2 * s2], bh[2 * s2 + 1]);
+        }
       }
     }
     __syncthreads();
@@ -350,8 +353,8 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int d = mh + mt * 16 + g, q = nt * 8 + 2 * t;
-      *reinterpret_cast<float2*>(out + d * kDh + q) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-      *reinterpret_cast<float2*>(out + (d + 8) * kDh + q) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      *reinterpret_cast<float2*>(out + d * kDh + q) = make_float2(acc[mt][nt][0] * kProdInv, acc[mt][nt][1] * kProdInv);
+      *reinterpret_cast<float2*>(out + (d + 8) * kDh + q) = make_float2(acc[mt][nt][2] * kProdInv, acc[mt][nt][3] * kProdInv);
     }
   // K column sums: column tid -> head tid/64, channel tid%64
   partial[((long long)tile * kHeads + (tid >> 6)) * kKVPartial + kDh * kDh + (tid & 63)] = ksum;
