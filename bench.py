@@ -168,8 +168,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "GATsSPG forward, N2D=1024 N3D=7000 L=8 D=256, 1 frame per step (B=1, reference calling convention)",
-                   "frames_per_step": 1},
+        "config": {"workload": f"synthetic frames of one object, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2] shape)",
+                   "frames_per_step": 1,
+                   "note": "reference calling convention B=1 (inference.py:85-92); each step = one frame = a bounded sample of the workload"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                          "sample": f"{args.steps} single-frame forwards of the oracle port (torch CPU fp32, {cpu_threads()} threads of {os.cpu_count()} logical CPUs), cpu={cpu_model()}"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -288,12 +289,9 @@ def main():
 
     # ---------------- per-rank records over NCCL (the path's only collective) ----------------
     rec = torch.tensor([float(B * args.steps), my_ms, float(n_match)], dtype=torch.float64, device=dev)
-    if world > 1:
-        allrec = [torch.zeros_like(rec) for _ in range(world)]
-        dist.all_gather(allrec, rec)
-    else:
-        allrec = [rec]
-    frames_total = sum(float(r[0]) for r in allrec)
+    from onepose_b200 import sharding
+    allrec = sharding.gather_records(rec)           # the path's only collective: one all_gather of a 3-double record
+    frames_total = float(allrec[:, 0].sum())
 
     if rank == 0:
         fps = frames_total / (total_ms * 1e-3)
@@ -303,7 +301,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 semantics via fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate" if args.backend != "simt" else "f32 (SIMT cross-check core)",
             "data": "synthetic",
-            "config": {"workload": f"synthetic batch={B} frames of one object per GPU, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2])",
+            "config": {"workload": f"synthetic frames of one object, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2] shape)",
                        "frames_per_step": B, "gemm_backend": args.backend,
                        "l2": "256 MB buffer written between timed iterations (outside the event pair); query batches rotated",
                        "sharding": "one object per rank, no data-path collective"},
