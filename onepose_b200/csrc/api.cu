@@ -311,7 +311,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   if (m->cfg.gemm_backend == 1)   // SIMT cross-check path keeps the plain FFMA kernel
     kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
   else
-    kv_state_partial_mma<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+    kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
   launched("kv_state_partial");
   kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
   launched("kv_state_reduce");
@@ -494,6 +494,8 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   if (prop.major != 10) return fail(nullptr, OPB_E_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  e = cudaFuncSetAttribute(kv_state_partial_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBytes);
+  if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaFuncSetAttribute(kv_state_partial_mma): %s", cudaGetErrorString(e));
   auto* m = new opb_matcher();
   m->cfg = *cfg;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));

@@ -269,9 +269,26 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 constexpr int kKvLd = 264;   // smem row stride in halves (528 B): 16-byte aligned rows, conflict-free ldmatrix
+constexpr int kKvRawStages = 2;   // 2 x 32 KB raw + 33 KB planes = 98 KB per block -> 2 blocks per SM
+constexpr int kKvRawBytes = 16 * 512 * 4;                                  // one raw stage: 16 rows x [K 256 | V 256] fp32
+constexpr int kKvSmemBytes = kKvRawStages * kKvRawBytes + 4 * 16 * kKvLd * 2;   // raw ring + 4 fp16 planes
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Stage flow (16 rows per stage): cp.async ring of raw fp32 rows (global latency hidden 2 stages ahead)
+//   -> convert raw -> fp16 hi/lo planes in smem (elu+1 on K, pad rows already zero) -> ldmatrix.trans + 48 MMAs per warp.
 __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated,
                                                                Layout L, float* __restrict__ partial) {
-  __shared__ __align__(16) __half sKh[16][kKvLd], sKl[16][kKvLd], sVh[16][kKvLd], sVl[16][kKvLd];
+  extern __shared__ __align__(16) uint8_t kv_smem[];
+  float* raw = reinterpret_cast<float*>(kv_smem);                                            // [stages][16][512]
+  __half (*sKh)[kKvLd] = reinterpret_cast<__half (*)[kKvLd]>(kv_smem + kKvRawStages * kKvRawBytes);
+  __half (*sKl)[kKvLd] = sKh + 16;
+  __half (*sVh)[kKvLd] = sKh + 32;
+  __half (*sVl)[kKvLd] = sKh + 48;
   const int tile = blockIdx.x;
   const int row0 = tile * kTileRows;
   const int seg = L.seg_of_row(row0);
@@ -281,29 +298,36 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
   const int h = warp >> 1, mh = (warp & 1) * 32;
   float acc[2][8][4] = {};
   float ksum = 0.f;                               // thread tid owns K column tid
-  // software pipeline: the global loads of the NEXT 16 rows are in flight while the current 16 rows go through the MMAs
-  float4 pre[8];
-  auto prefetch = [&](int r0) {
+  const int n_stages = n_valid > 0 ? (n_valid + 15) / 16 : 0;
+  auto issue = [&](int s) {                       // raw rows of stage s -> ring slot s % kKvRawStages (rows past n_valid: zero-filled)
+    float* dst = raw + (s % kKvRawStages) * (16 * 512);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;              // 0..2047 float4 slots: row = idx / 128, 128 float4 per row (K 64 | V 64)
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
-      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + rr < n_valid) {
-        const float* rowp = kv + (long long)(row0 + r0 + rr) * ld;
-        pre[i] = *reinterpret_cast<const float4*>(rowp + (c4 < 256 ? k_off + c4 : v_off + c4 - 256));
+      const int r = s * 16 + rr;
+      if (r < n_valid) {
+        const float* rowp = kv + (long long)(row0 + r) * ld;
+        cp_async16(dst + rr * 512 + c4, rowp + (c4 < 256 ? k_off + c4 : v_off + c4 - 256));
+      } else {
+        *reinterpret_cast<float4*>(dst + rr * 512 + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    cp_async_commit();
   };
-  if (n_valid > 0) prefetch(0);
-  for (int r0 = 0; r0 < n_valid; r0 += 16) {
+  if (n_stages > 0) issue(0);
+  if (n_stages > 1) issue(1); else cp_async_commit();
+  for (int s = 0; s < n_stages; ++s) {
+    cp_async_wait<1>();                           // stage s has landed (one younger group may still be in flight)
+    __syncthreads();                              // ... for every thread; also: previous stage's MMAs are done with the planes
+    const float* src = raw + (s % kKvRawStages) * (16 * 512);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
-      float4 x = pre[i];
+      float4 x = *reinterpret_cast<const float4*>(src + rr * 512 + c4);
       const bool is_k = c4 < 256;
-      if (is_k && !k_activated && r0 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+      if (is_k && !k_activated && s * 16 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
       const float xs[4] = {x.x, x.y, x.z, x.w};
       __half hi[4], lo[4];
 #pragma unroll
@@ -313,8 +337,8 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
       *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(hi);
       *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(lo);
     }
-    __syncthreads();
-    if (r0 + 16 < n_valid) prefetch(r0 + 16);
+    __syncthreads();                              // planes complete; raw slot s is free again
+    if (s + 2 < n_stages) issue(s + 2); else cp_async_commit();
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) ksum += join_f32(sKh[rr][tid], sKl[rr][tid]);
     // A = K^T (m = K channel, k = row): 16x16 blocks of the row-major K tile, transposed on load
@@ -345,7 +369,6 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
         }
       }
     }
-    __syncthreads();
   }
   float* out = partial + ((long long)tile * kHeads + h) * kKVPartial;
 #pragma unroll
