@@ -234,9 +234,14 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
 static int run_gats(opb_matcher* m, const Layout& L, PlaneBuf& x, int gi, cudaStream_t st) {
   const long long warps = (long long)L.M * L.B;
   if (warps == 0) return 0;
-  gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-      x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
-      m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
+  if (m->Lf == 8 && L.B > 1)   // leaves loaded once per point and reused across the frames of the chunk
+    gats_aggregate_frames8<<<(unsigned)(((long long)L.M * 32 + 255) / 256), 256, 0, st>>>(
+        x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+        m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
+  else
+    gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+        x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+        m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
   m->launches++;
   prof_mark(m, st, "gats_aggregate", 0.0);
   return 0;

@@ -183,6 +183,89 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
   ql[lane] = ol[0]; ql[32 + lane] = ol[1];
 }
 
+// Same layer, warp per POINT looping over the frames of the chunk: the point's 8 leaf rows and leaf logits are read once
+// into registers and reused for every frame (the leaves are per-object constants; reference GATs.py:46 reshapes the same
+// tensor for every batch element).  Fast path for num_leaf == 8 (the released configuration, test_GATsSPG.yaml:5).
+__global__ void __launch_bounds__(256) gats_aggregate_frames8(__half* __restrict__ x_hi, __half* __restrict__ x_lo, Layout L,
+                                                              const float* __restrict__ leaves, const float* __restrict__ s2,
+                                                              const float* __restrict__ wa3, int include_self, int additional, float alpha) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= L.M) return;
+  float4 lu[8], lv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4* lr = reinterpret_cast<const float4*>(leaves + ((long long)i * 8 + c) * kD);
+    lu[c] = lr[lane];
+    lv[c] = lr[32 + lane];
+  }
+  const float s2l = lane < 8 ? s2[(long long)i * 8 + lane] : 0.f;
+  float w3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w3[j] = wa3[(j >> 2) * 128 + lane * 4 + (j & 3)];
+  auto lrelu = [alpha](float v) { return v > 0.f ? v : alpha * v; };
+#pragma unroll 2
+  for (int b = 0; b < L.B; ++b) {
+    const long long row = (long long)b * L.R + L.n_pad + i;
+    float h3[8];
+    {
+      const uint2* ph = reinterpret_cast<const uint2*>(x_hi + row * kD);
+      const uint2* pl = reinterpret_cast<const uint2*>(x_lo + row * kD);
+#pragma unroll
+      for (int half_i = 0; half_i < 2; ++half_i) {
+        uint2 uh = ph[half_i * 32 + lane], ul = pl[half_i * 32 + lane];
+        const __half* hh = reinterpret_cast<const __half*>(&uh);
+        const __half* hl = reinterpret_cast<const __half*>(&ul);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h3[half_i * 4 + j] = join_f32(hh[j], hl[j]);
+      }
+    }
+    float s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s3 = fmaf(h3[j], w3[j], s3);
+    s3 = warp_sum(s3);
+    float e = lane < 8 ? lrelu(s3 + s2l) : -INFINITY;
+    const float e_self = include_self ? lrelu(2.f * s3) : -INFINITY;
+    float mx = e;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // lanes 0..7 hold the leaf logits
+    mx = fmaxf(__shfl_sync(0xffffffffu, mx, 0), e_self);
+    const float p = lane < 8 ? expf(e - mx) : 0.f;
+    const float p_self = include_self ? expf(e_self - mx) : 0.f;
+    float ps = p;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    const float inv = 1.f / (__shfl_sync(0xffffffffu, ps, 0) + p_self);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = include_self ? (p_self * inv) * h3[j] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float a = __shfl_sync(0xffffffffu, p, c) * inv;
+      acc[0] = fmaf(a, lu[c].x, acc[0]); acc[1] = fmaf(a, lu[c].y, acc[1]);
+      acc[2] = fmaf(a, lu[c].z, acc[2]); acc[3] = fmaf(a, lu[c].w, acc[3]);
+      acc[4] = fmaf(a, lv[c].x, acc[4]); acc[5] = fmaf(a, lv[c].y, acc[5]);
+      acc[6] = fmaf(a, lv[c].z, acc[6]); acc[7] = fmaf(a, lv[c].w, acc[7]);
+    }
+    uint2 oh[2], ol[2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[j];
+      if (!include_self) v = v * 0.5f + h3[j];
+      else if (additional) v += h3[j];
+      v = v > 0.f ? v : expm1f(v);  // ELU (GATs.py:69-70)
+      __half hh, ll;
+      split_f32(v, hh, ll);
+      reinterpret_cast<__half*>(&oh[j >> 2])[j & 3] = hh;
+      reinterpret_cast<__half*>(&ol[j >> 2])[j & 3] = ll;
+    }
+    uint2* qh = reinterpret_cast<uint2*>(x_hi + row * kD);
+    uint2* ql = reinterpret_cast<uint2*>(x_lo + row * kD);
+    qh[lane] = oh[0]; qh[32 + lane] = oh[1];
+    ql[lane] = ol[0]; ql[32 + lane] = ol[1];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Linear-attention state (reference GATs_SuperGlue.py:71-78), per segment s and head h:
 //   Kmean[s][h][d]     = (1/m) sum_rows elu1(K[r,h,d])
@@ -297,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
   const int g = lane >> 2, t = lane & 3;
   const int h = warp >> 1, mh = (warp & 1) * 32;
   float acc[2][8][4] = {};
-  float ksum = 0.f;                               // thread tid owns K column tid
+  float ks4[4] = {0.f, 0.f, 0.f, 0.f};            // K column sums of this thread's 4 columns (rows tid/128, +2, +4, ...)
   const int n_stages = n_valid > 0 ? (n_valid + 15) / 16 : 0;
   auto issue = [&](int s) {                       // raw rows of stage s -> ring slot s % kKvRawStages (rows past n_valid: zero-filled)
     float* dst = raw + (s % kKvRawStages) * (16 * 512);
@@ -327,20 +410,23 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
       const int rr = idx >> 7, c4 = (idx & 127) * 4;
       float4 x = *reinterpret_cast<const float4*>(src + rr * 512 + c4);
       const bool is_k = c4 < 256;
-      if (is_k && !k_activated && s * 16 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
-      const float xs[4] = {x.x, x.y, x.z, x.w};
-      __half hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) split_f32(xs[e], hi[e], lo[e]);
+      if (is_k) {
+        if (!k_activated && s * 16 + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+        ks4[0] += x.x; ks4[1] += x.y; ks4[2] += x.z; ks4[3] += x.w;
+      }
+      // packed split: hi = fp16x2(64 x), lo = fp16x2(64 x - hi)
+      const float2 a = make_float2(x.x * kPre, x.y * kPre), b = make_float2(x.z * kPre, x.w * kPre);
+      const __half2 ha = __float22half2_rn(a), hb = __float22half2_rn(b);
+      const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+      const __half2 la = __float22half2_rn(make_float2(a.x - fa.x, a.y - fa.y)), lb = __float22half2_rn(make_float2(b.x - fb.x, b.y - fb.y));
       __half* dh = is_k ? &sKh[rr][c4] : &sVh[rr][c4 - 256];
       __half* dl = is_k ? &sKl[rr][c4] : &sVl[rr][c4 - 256];
-      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(hi);
-      *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(lo);
+      __half2 hv[2] = {ha, hb}, lv[2] = {la, lb};
+      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(hv);
+      *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(lv);
     }
     __syncthreads();                              // planes complete; raw slot s is free again
     if (s + 2 < n_stages) issue(s + 2); else cp_async_commit();
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) ksum += join_f32(sKh[rr][tid], sKl[rr][tid]);
     // A = K^T (m = K channel, k = row): 16x16 blocks of the row-major K tile, transposed on load
     uint32_t ah[2][4], al[2][4];
     const int a_row = (lane & 7) + 8 * (lane >> 4), a_col = 8 * ((lane >> 3) & 1);
@@ -379,8 +465,15 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
       *reinterpret_cast<float2*>(out + d * kDh + q) = make_float2(acc[mt][nt][0] * kProdInv, acc[mt][nt][1] * kProdInv);
       *reinterpret_cast<float2*>(out + (d + 8) * kDh + q) = make_float2(acc[mt][nt][2] * kProdInv, acc[mt][nt][3] * kProdInv);
     }
-  // K column sums: column tid -> head tid/64, channel tid%64
-  partial[((long long)tile * kHeads + (tid >> 6)) * kKVPartial + kDh * kDh + (tid & 63)] = ksum;
+  // K column sums: threads t and t+128 hold the even / odd rows of the same 4 columns (K columns: (tid & 127) < 64)
+  __syncthreads();
+  float* red = raw;                               // raw ring is idle now
+  if ((tid & 127) < 64) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[(tid >> 7) * 256 + (tid & 127) * 4 + e] = ks4[e];
+  }
+  __syncthreads();
+  partial[((long long)tile * kHeads + (tid >> 6)) * kKVPartial + kDh * kDh + (tid & 63)] = red[tid] + red[256 + tid];
 }
 
 // grid (S*H, 17), block 256: fixed-order sum over the segment's tiles, scaled by 1/m
@@ -735,13 +828,11 @@ __global__ void conf_argmax_simt(const float* __restrict__ s, Layout L, float in
       unsigned long long pk = pack_arg(c, n);
       cbest = pk > cbest ? pk : cbest;
     }
-    unsigned long long rb = mv ? pack_arg(c, m) : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long other = __shfl_xor_sync(0xffffffffu, rb, o);
-      rb = other > rb ? other : rb;
-    }
-    if (lane == 0 && rb) atomicMax(&rowbest[(long long)b * L.N + n], rb);
+    // row arg-max over this warp's 32 columns: conf >= 0 so its bit pattern orders like an unsigned integer
+    const unsigned bits = mv ? __float_as_uint(c) : 0u;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned who = __ballot_sync(0xffffffffu, mv && bits == wmax);
+    if (who && lane == __ffs(who) - 1) atomicMax(&rowbest[(long long)b * L.N + n], pack_arg(c, m));   // lowest column wins ties
   }
   if (mv && cbest) atomicMax(&colbest[(long long)b * L.M + m], cbest);
 }
