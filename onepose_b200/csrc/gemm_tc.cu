@@ -565,6 +565,67 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         } else if (row_ok && rbest) {
           atomicMax(p.rowbest + (long long)z * N + row, rbest);
         }
+      } else if (EPI == EPI_RESID) {
+        // ---- x += delta (reference GATs_SuperGlue.py:59,64), in place on the fp16-split planes, 32 columns per chunk.
+        // The old x values of the NEXT chunk are prefetched while the current chunk is staged and stored.
+        const __half* xh_row = p.x_hi + (long long)(out_row0 + r_in_tile) * kD + n_tile * BN;
+        const __half* xl_row = p.x_lo + (long long)(out_row0 + r_in_tile) * kD + n_tile * BN;
+        uint4 xh[4], xl[4];
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          xh[j8] = *reinterpret_cast<const uint4*>(xh_row + j8 * 8);
+          xl[j8] = *reinterpret_cast<const uint4*>(xl_row + j8 * 8);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          float x[32];
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const __half* hh = reinterpret_cast<const __half*>(&xh[j8]);
+            const __half* hl = reinterpret_cast<const __half*>(&xl[j8]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              x[j8 * 8 + e] = fmaf(__uint_as_float(v[j8 * 8 + e]), kProdInv, bb[e]) + join_f32(hh[e], hl[e]);
+          }
+          if (c0 + 32 < BN) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              xh[j8] = *reinterpret_cast<const uint4*>(xh_row + c0 + 32 + j8 * 8);
+              xl[j8] = *reinterpret_cast<const uint4*>(xl_row + c0 + 32 + j8 * 8);
+            }
+          }
+          uint8_t* sh = staging + (chunk_ctr & 1) * 8192;
+          uint8_t* sl = staging + kStagingBytes + (chunk_ctr & 1) * 8192;
+          if (leader) tma_store_wait_read<1>();
+          epi_bar();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 oh, ol;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __half h, l;
+              split_f32(x[j8 * 8 + e], h, l);
+              reinterpret_cast<__half*>(&oh)[e] = h;
+              reinterpret_cast<__half*>(&ol)[e] = l;
+            }
+            *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
+            *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, sh, col0, out_row0);
+            tma_store_2d(&maps.out_lo, sl, col0, out_row0);
+            tma_store_commit();
+          }
+        }
       } else if (EPI == EPI_KVT) {
         // ---- [K | V] projection -> transposed fp16-split planes out[channel][row] (operands of the KV-state GEMM)
         __half* st_hi = reinterpret_cast<__half*>(staging);
