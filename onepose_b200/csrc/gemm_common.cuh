@@ -19,7 +19,6 @@ enum GemmEpilogue {
   EPI_F32_STATS = 1,  // EPI_F32 + InstanceNorm partial sums (sum, sum^2 per 32-row quarter and column) -> statpart
   EPI_QSCALE = 2,     // Q' = elu1(acc+bias) / (elu1(.) . Kmean_src + 1e-6/m_src) per head -> out planes   (n_out = 256)
   EPI_RESID = 3,      // out planes = resid planes + acc + bias  (x += delta, in place)                     (n_out = 256)
-  EPI_KVT = 4,        // [K | V] projection -> TRANSPOSED planes out[n_out channels][total rows]; elu+1 on K; pad rows zeroed
   EPI_L2NORM = 5,     // F.normalize(acc + bias) over the 256 columns -> out planes                          (n_out = 256)
   // dual-softmax tail on the batched score GEMM (one batch = one frame; rows = queries, columns = 3D points):
   EPI_SCORE_SUMS = 6, // e = exp((cos-1)/scale): per-tile row sums and per-32-row column sums -> rowsum_part / colsum_part
@@ -42,7 +41,7 @@ struct GemmProblem {
   int ldc;
   // ---- tcgen05 core only ----
   int epi;               // GemmEpilogue
-  Planes out;            // planes output (EPI_QSCALE / EPI_RESID / EPI_L2NORM: [rows, out.ld]; EPI_KVT: [n_out, out.ld = total rows])
+  Planes out;            // planes output [rows, out.ld] (EPI_QSCALE / EPI_RESID / EPI_L2NORM / EPI_KV)
   CPlanes resid;         // EPI_RESID input planes [rows, 256]
   const float* kmean;    // EPI_QSCALE: [S][256]
   int cross;             // EPI_QSCALE: source segment selection

@@ -257,7 +257,7 @@ struct TcParams {
 struct Maps {
   CUtensorMap a1h, a1l, a2h, a2l, b1h, b1l, b2h, b2l;   // loads
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128 (SWIZZLE_128B)
-  CUtensorMap out_hi, out_lo;                             // store: planes, box 32 x 128 (SWIZZLE_64B); EPI_KVT: transposed, box 128 x 64 (no swizzle)
+  CUtensorMap out_hi, out_lo;                             // store: fp16-split planes, box 32 x 128 (SWIZZLE_64B)
 };
 
 // CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
@@ -626,38 +626,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             tma_store_commit();
           }
         }
-      } else if (EPI == EPI_KVT) {
-        // ---- [K | V] projection -> transposed fp16-split planes out[channel][row] (operands of the KV-state GEMM)
-        __half* st_hi = reinterpret_cast<__half*>(staging);
-        __half* st_lo = reinterpret_cast<__half*>(staging + kStagingBytes);
-        const bool row_ok = r_in_tile < n_valid;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(lane_base + c0, v0);
-          tmem_ld32(lane_base + c0 + 32, v1);
-          tmem_ld_wait();
-          const int col0 = n_tile * BN + c0;
-          if (leader) tma_store_wait_read<0>();
-          epi_bar();
-#pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            float x = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) * kProdInv + __ldg(p.bias + col0 + j);
-            if (col0 < p.elu_cols) x = elu1(x);
-            if (!row_ok) x = 0.f;                   // pad rows must not reach the K^T V reduction
-            __half h, l;
-            split_f32(x, h, l);
-            st_hi[j * BM + r_in_tile] = h;
-            st_lo[j * BM + r_in_tile] = l;
-          }
-          fence_async_smem();
-          epi_bar();
-          if (leader) {
-            tma_store_2d(&maps.out_hi, st_hi, out_row0, col0);
-            tma_store_2d(&maps.out_lo, st_lo, out_row0, col0);
-            tma_store_commit();
-          }
-        }
       } else {
         // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM / EPI_KV
         float inv_norm = 1.f;
@@ -916,10 +884,6 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     if (p.epi == EPI_SCORE_CONF && p.conf && p.L.M % 4 == 0) {
       conf_tma = make_map3(&mp.out_f32, p.conf, p.L.M, p.L.N, p.batch) ? 1 : 0;
     }
-  } else if (p.epi == EPI_KVT) {
-    // transposed planes [n_out channels][out.ld = total rows]; box = 128 rows (inner) x 64 channels
-    ok = ok && make_map(&mp.out_hi, p.out.hi, p.n_out, out_rows, p.out.ld, BM, 64, false) && make_map(&mp.out_lo, p.out.lo, p.n_out, out_rows, p.out.ld, BM, 64, false);
-    mp.out_f32 = mp.out_hi;
   } else {
     ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, p.n_out, p.out.ld, 32, BM, false) && make_map(&mp.out_lo, p.out.lo, out_rows, p.n_out, p.out.ld, 32, BM, false);
     mp.out_f32 = mp.out_hi;
@@ -952,7 +916,6 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
       case EPI_F32_STATS: le = launch_variant<2, true, EPI_F32_STATS>(cfg, mp, tp); break;
       case EPI_QSCALE: le = launch_variant<2, true, EPI_QSCALE>(cfg, mp, tp); break;
       case EPI_RESID: le = launch_variant<2, true, EPI_RESID>(cfg, mp, tp); break;
-      case EPI_KVT: le = launch_variant<2, true, EPI_KVT>(cfg, mp, tp); break;
       case EPI_L2NORM: le = launch_variant<2, true, EPI_L2NORM>(cfg, mp, tp); break;
       case EPI_SCORE_SUMS: le = launch_variant<2, true, EPI_SCORE_SUMS>(cfg, mp, tp); break;
       case EPI_SCORE_CONF: le = launch_variant<2, true, EPI_SCORE_CONF>(cfg, mp, tp); break;

@@ -492,9 +492,9 @@ __global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
   else kmean[(long long)sh * kDh + (i - kDh * kDh)] = s;
 }
 
-// Tensor-core path of the linear-attention state.  The [K | V] projection epilogue (EPI_KVT) leaves
-// K^T (elu+1 applied) and V^T as fp16-split planes kvt[512][rows] with pad rows zeroed; one batched-K GEMM
-// then yields, per 256-row piece, part[piece][256 (K channel)][256 (V channel)] = K_piece^T V_piece.
+// tcgen05 path of the linear-attention state (fuse level 2).  The [K | V] projection epilogue (EPI_KV) leaves elu1(K) and V
+// as row-major fp16-split planes kv[rows, 512] with pad rows zeroed; one batched GEMM whose reduction index is the tensor
+// ROW (MN-major UMMA operands) then yields, per 256-row piece, part[piece][256 (K channel)][256 (V channel)] = K_piece^T V_piece.
 // kv_reduce_pieces: fixed-order sum over the pieces of a segment, diagonal head blocks only, 1/m scale; the last
 // y-block of each (segment, head) combines the per-32-row K column sums (EPI_KV epilogue) into Kmean.
 // grid (S*H, 17), block 256
