@@ -14,6 +14,7 @@
 #include "gemm_common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_aux.cuh"
+#include "kv_state_tc.cuh"
 
 namespace opb {
 
@@ -88,6 +89,7 @@ struct opb_matcher {
   int ws_frames = 0, ws_N = 0;
   PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
   DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
+  int kv_mode = 0;       // 0 = tcgen05 KV-state kernel, 1 = mma.sync variant (env OPB_KV_MODE)
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
                          // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
@@ -313,12 +315,18 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLaye
   p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
   if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)
-  if (m->cfg.gemm_backend == 1)   // SIMT cross-check path keeps the plain FFMA kernel
+  int rows_per_partial = kTileRows;
+  if (m->cfg.gemm_backend == 1) {                 // SIMT cross-check path: plain FFMA kernel
     kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
-  else
+  } else if (m->kv_mode == 1) {                   // warp-level mma.sync variant (kept for comparison)
     kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+  } else {                                        // tcgen05: conversion + UMMA in one kernel, one partial per 256-row slab
+    if (launch_kv_state_tc(m->c768.as<float>(), 768, 256, 512, L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_tc launch failed");
+    rows_per_partial = 256;
+  }
   launched("kv_state_partial");
-  kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, m->kvmean.as<float>(), m->kmean.as<float>());
+  kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, rows_per_partial, m->kvmean.as<float>(),
+                                                                             m->kmean.as<float>());
   launched("kv_state_reduce");
   // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
   q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
@@ -503,6 +511,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaFuncSetAttribute(kv_state_partial_mma): %s", cudaGetErrorString(e));
   auto* m = new opb_matcher();
   m->cfg = *cfg;
+  if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
   *out = m;
   return OPB_OK;

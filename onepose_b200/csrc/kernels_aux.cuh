@@ -477,14 +477,14 @@ __global__ void __launch_bounds__(256, 2) kv_state_partial_mma(const float* __re
 }
 
 // grid (S*H, 17), block 256: fixed-order sum over the segment's tiles, scaled by 1/m
-__global__ void kv_state_reduce(const float* __restrict__ partial, Layout L,
+__global__ void kv_state_reduce(const float* __restrict__ partial, Layout L, int rows_per_partial,
                                 float* __restrict__ kvmean /*[S][H][64][64]*/, float* __restrict__ kmean /*[S][H][64]*/) {
   const int sh = blockIdx.x;
   const int seg = sh / kHeads, h = sh % kHeads;
   const int i = blockIdx.y * 256 + threadIdx.x;
   if (i >= kKVPartial) return;
-  const int t0 = L.seg_start(seg) / kTileRows;
-  const int nt = (L.seg_valid(seg) + kTileRows - 1) / kTileRows;
+  const int t0 = L.seg_start(seg) / rows_per_partial;
+  const int nt = (L.seg_valid(seg) + rows_per_partial - 1) / rows_per_partial;
   float s = 0.f;
   for (int t = 0; t < nt; ++t) s += partial[((long long)(t0 + t) * kHeads + h) * kKVPartial + i];
   s = L.seg_valid(seg) > 0 ? s * (1.f / (float)L.seg_valid(seg)) : 0.f;   // empty segment (object prologue / query-only pass)

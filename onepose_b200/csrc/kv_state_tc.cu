@@ -1,0 +1,238 @@
+// Linear-attention state on the 5th-gen tensor cores, straight from the fp32 [K | V] rows of the QKV GEMM.
+//
+//   per segment s, head h:   KV[h][d][q] = sum_rows elu1(K[r,h,d]) * V[r,h,q],   Ksum[h][d] = sum_rows elu1(K[r,h,d])
+//   (reference GATs_SuperGlue.py:71-78; the 1/m of :75 is applied by kv_state_reduce)
+//
+// One CTA per 256-row slab (slabs never straddle a segment: segments are padded to 256 rows).  256 threads:
+//   all threads : stream 32-row stages of fp32 K,V from global (register prefetch one stage ahead), apply elu+1 to K, zero
+//                 the pad rows, split to fp16 hi/lo and write them into shared memory in the UMMA MN-major SWIZZLE_128B
+//                 layout (what a TMA load of a row-major [rows, channels] box would produce);
+//   thread 0    : per stage 12 tcgen05.mma (2 head pairs x 2 k-steps of 16 rows x 3 split passes, M = N = 128, both operands
+//                 MN-major: A = K^T, B = V, reduction index = row) accumulating in TMEM across the whole slab;
+//   warps 0-3   : epilogue -- the two diagonal 64x64 head blocks of each 128x128 accumulator -> partial[slab][h][64*64 + 64].
+// The conversion (SIMT) is the bound; the MMAs of stage i run under the conversion of stage i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kv_state_tc.cuh"
+
+namespace opb {
+namespace {
+
+constexpr int kRowsPerStage = 32;
+constexpr int kStagesInFlight = 2;
+constexpr int kPlaneBytes = kRowsPerStage * 256 * 2;          // one fp16 plane of one operand: 32 rows x 256 channels = 16 KB
+constexpr int kStageBytes = 4 * kPlaneBytes;                   // K_hi, K_lo, V_hi, V_lo = 64 KB
+constexpr int kSmemBytes = kStagesInFlight * kStageBytes + 1024 + 64;
+constexpr int kChanBlockBytes = kRowsPerStage * 128;           // LBO: 64-channel blocks are 32 rows x 128 B = 4 KB apart
+constexpr uint32_t kSpin = 1u << 22;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > kSpin) __trap();
+  }
+}
+// MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 rows per atom; LBO between 64-channel blocks, SBO = 1024 B between 8-row groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(kChanBlockBytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, D = f32, A = B = f16, A and B MN-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a), "l"(b), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// byte offset of channel c (0..255), row r (0..31) inside one MN-major SWIZZLE_128B plane of a stage
+__device__ __forceinline__ uint32_t plane_off(int r, int c) {
+  return (uint32_t)((c >> 6) * kChanBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+}
+
+__global__ void __launch_bounds__(256, 1) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
+                                                             float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* free_bar = reinterpret_cast<uint64_t*>(smem + kStagesInFlight * kStageBytes);   // [2] stage buffer free (its MMAs retired)
+  uint64_t* done_bar = free_bar + kStagesInFlight;                                          // accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slab = blockIdx.x;
+  const int row0 = slab * 256;
+  const int seg = L.seg_of_row(row0);
+  const int n_valid = min(256, L.seg_valid(seg) - (row0 - L.seg_start(seg)));   // <= 0: slab entirely in the padding
+  float* out = partial + (long long)slab * kHeads * (kDh * kDh + kDh);
+
+  if (n_valid <= 0) {                              // nothing to reduce: define the partial and leave
+    for (int i = tid; i < kHeads * (kDh * kDh + kDh); i += 256) out[i] = 0.f;
+    return;
+  }
+  if (tid == 0) {
+    mbar_init(&free_bar[0], 1); mbar_init(&free_bar[1], 1); mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // thread -> data: 4 consecutive channels (c4) of 16 rows (rsel, rsel+2, ...) of every stage
+  const int c4 = (tid & 127) * 4;                  // 0..508: < 256 -> K channel, else V channel c4-256
+  const int rsel = tid >> 7;
+  const bool is_k = c4 < 256;
+  const float* col_ptr = kv + (is_k ? k_off + c4 : v_off + c4 - 256);
+  float ks4[4] = {0.f, 0.f, 0.f, 0.f};
+  const int n_stages = (n_valid + kRowsPerStage - 1) / kRowsPerStage;
+
+  float4 pre[16];
+  auto prefetch = [&](int s) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = s * kRowsPerStage + rsel + 2 * i;
+      pre[i] = r < n_valid ? *reinterpret_cast<const float4*>(col_ptr + (long long)(row0 + r) * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  prefetch(0);
+  for (int s = 0; s < n_stages; ++s) {
+    const int buf = s & 1;
+    uint8_t* st = smem + buf * kStageBytes;
+    if (s >= kStagesInFlight) mbar_wait(&free_bar[buf], ((s >> 1) - 1) & 1);   // MMAs of stage s-2 have retired
+    uint8_t* p_hi = st + (is_k ? 0 : 2 * kPlaneBytes);
+    uint8_t* p_lo = p_hi + kPlaneBytes;
+    const int cc = c4 & 255;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int rr = rsel + 2 * i;
+      float4 x = pre[i];
+      if (is_k) {
+        if (s * kRowsPerStage + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+        ks4[0] += x.x; ks4[1] += x.y; ks4[2] += x.z; ks4[3] += x.w;
+      }
+      const float2 a = make_float2(x.x * kPre, x.y * kPre), b = make_float2(x.z * kPre, x.w * kPre);
+      const __half2 ha = __float22half2_rn(a), hb = __float22half2_rn(b);
+      const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+      const __half2 la = __float22half2_rn(make_float2(a.x - fa.x, a.y - fa.y)), lb = __float22half2_rn(make_float2(b.x - fb.x, b.y - fb.y));
+      __half2 hv[2] = {ha, hb}, lv[2] = {la, lb};
+      const uint32_t off = plane_off(rr, cc);
+      *reinterpret_cast<uint2*>(p_hi + off) = *reinterpret_cast<uint2*>(hv);
+      *reinterpret_cast<uint2*>(p_lo + off) = *reinterpret_cast<uint2*>(lv);
+    }
+    if (s + 1 < n_stages) prefetch(s + 1);         // next stage's global loads fly during the barrier + MMA issue
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t kh = smem_u32(st), kl = kh + kPlaneBytes, vh = kh + 2 * kPlaneBytes, vl = kh + 3 * kPlaneBytes;
+#pragma unroll
+      for (int pair = 0; pair < 2; ++pair) {       // head pair (2 x 64 channels = one M=128 / N=128 operand)
+        const uint32_t d = tmem_base + pair * 128;
+        const uint32_t po = pair * 2 * kChanBlockBytes;
+#pragma unroll
+        for (int k = 0; k < kRowsPerStage / 16; ++k) {
+          const uint32_t ko = k * 2048;            // 16 rows = two 8-row atoms
+          const uint64_t ah = make_desc_mn(kh + po + ko), al = make_desc_mn(kl + po + ko);
+          const uint64_t bh = make_desc_mn(vh + po + ko), bl = make_desc_mn(vl + po + ko);
+          mma(d, ah, bh, (uint32_t)((s | k) != 0));
+          mma(d, ah, bl, 1u);
+          mma(d, al, bh, 1u);
+        }
+      }
+      commit(&free_bar[buf]);
+      if (s == n_stages - 1) commit(done_bar);
+    }
+  }
+  // ---- epilogue: diagonal head blocks of the two accumulators
+  mbar_wait(done_bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 4) {
+    const int lane_row = warp * 32 + lane;         // accumulator row = K channel within the head pair
+    const int hl = lane_row >> 6, d = lane_row & 63;
+#pragma unroll 1
+    for (int pair = 0; pair < 2; ++pair) {
+      const int h = pair * 2 + hl;
+      float* o = out + (long long)h * (kDh * kDh + kDh) + d * kDh;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + pair * 128 + hl * 64 + half * 32 + ((uint32_t)(warp * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + half * 32 + j) = make_float4(__uint_as_float(v[j]) * kProdInv, __uint_as_float(v[j + 1]) * kProdInv,
+                                                                      __uint_as_float(v[j + 2]) * kProdInv, __uint_as_float(v[j + 3]) * kProdInv);
+      }
+    }
+  }
+  // K column sums: threads t and t+128 hold the even / odd rows of the same 4 K channels
+  float* red = reinterpret_cast<float*>(smem);     // stage buffers are idle now (all MMAs retired: done_bar)
+  __syncthreads();
+  if (is_k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[rsel * 256 + c4 + e] = ks4[e];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  out[(long long)(tid >> 6) * (kDh * kDh + kDh) + kDh * kDh + (tid & 63)] = red[tid] + red[256 + tid];
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+  }
+}
+
+}  // namespace
+
+int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, const Layout& L, float* partial, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kv_state_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -2;
+    attr_done = true;
+  }
+  const int slabs = L.rows() / 256;
+  kv_state_tc_kernel<<<slabs, 256, kSmemBytes, stream>>>(kv, ld, k_off, v_off, L, partial);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace opb
