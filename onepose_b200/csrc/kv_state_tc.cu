@@ -4,10 +4,10 @@
 //   (reference GATs_SuperGlue.py:71-78; the 1/m of :75 is applied by kv_state_reduce)
 //
 // One CTA per 256-row slab (slabs never straddle a segment: segments are padded to 256 rows).  256 threads:
-//   all threads : stream 32-row stages of fp32 K,V from global (register prefetch one stage ahead), apply elu+1 to K, zero
+//   all threads : stream 16-row stages of fp32 K,V from global (register prefetch one stage ahead), apply elu+1 to K, zero
 //                 the pad rows, split to fp16 hi/lo and write them into shared memory in the UMMA MN-major SWIZZLE_128B
 //                 layout (what a TMA load of a row-major [rows, channels] box would produce);
-//   thread 0    : per stage 12 tcgen05.mma (2 head pairs x 2 k-steps of 16 rows x 3 split passes, M = N = 128, both operands
+//   thread 0    : per stage 6 tcgen05.mma (2 head pairs x one k-step of 16 rows x 3 split passes, M = N = 128, both operands
 //                 MN-major: A = K^T, B = V, reduction index = row) accumulating in TMEM across the whole slab;
 //   warps 0-3   : epilogue -- the two diagonal 64x64 head blocks of each 128x128 accumulator -> partial[slab][h][64*64 + 64].
 // The conversion (SIMT) is the bound; the MMAs of stage i run under the conversion of stage i+1.
@@ -19,12 +19,12 @@
 namespace opb {
 namespace {
 
-constexpr int kRowsPerStage = 32;
+constexpr int kRowsPerStage = 16;
 constexpr int kStagesInFlight = 2;
-constexpr int kPlaneBytes = kRowsPerStage * 256 * 2;          // one fp16 plane of one operand: 32 rows x 256 channels = 16 KB
-constexpr int kStageBytes = 4 * kPlaneBytes;                   // K_hi, K_lo, V_hi, V_lo = 64 KB
+constexpr int kPlaneBytes = kRowsPerStage * 256 * 2;          // one fp16 plane of one operand: 16 rows x 256 channels = 8 KB
+constexpr int kStageBytes = 4 * kPlaneBytes;                   // K_hi, K_lo, V_hi, V_lo = 32 KB (2 stages + slack = 66 KB: 2 CTAs per SM)
 constexpr int kSmemBytes = kStagesInFlight * kStageBytes + 1024 + 64;
-constexpr int kChanBlockBytes = kRowsPerStage * 128;           // LBO: 64-channel blocks are 32 rows x 128 B = 4 KB apart
+constexpr int kChanBlockBytes = kRowsPerStage * 128;           // LBO: 64-channel blocks are 16 rows x 128 B = 2 KB apart
 constexpr uint32_t kSpin = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t plane_off(int r, int c) {
   return (uint32_t)((c >> 6) * kChanBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
 }
 
-__global__ void __launch_bounds__(256, 1) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
+__global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
                                                              float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) kv_state_tc_kernel(const float* __rest
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // thread -> data: 4 consecutive channels (c4) of 16 rows (rsel, rsel+2, ...) of every stage
+  // thread -> data: 4 consecutive channels (c4) of 8 rows (rsel, rsel+2, ...) of every stage
   const int c4 = (tid & 127) * 4;                  // 0..508: < 256 -> K channel, else V channel c4-256
   const int rsel = tid >> 7;
   const bool is_k = c4 < 256;
@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(256, 1) kv_state_tc_kernel(const float* __rest
   float ks4[4] = {0.f, 0.f, 0.f, 0.f};
   const int n_stages = (n_valid + kRowsPerStage - 1) / kRowsPerStage;
 
-  float4 pre[16];
+  float4 pre[kRowsPerStage / 2];
   auto prefetch = [&](int s) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < kRowsPerStage / 2; ++i) {
       const int r = s * kRowsPerStage + rsel + 2 * i;
       pre[i] = r < n_valid ? *reinterpret_cast<const float4*>(col_ptr + (long long)(row0 + r) * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) kv_state_tc_kernel(const float* __rest
     uint8_t* p_lo = p_hi + kPlaneBytes;
     const int cc = c4 & 255;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < kRowsPerStage / 2; ++i) {
       const int rr = rsel + 2 * i;
       float4 x = pre[i];
       if (is_k) {
