@@ -82,6 +82,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// elu(x)+1 with the hardware exponential (ex2.approx, ~2^-22 relative -- the same order as the fp16 split that follows)
+__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+
 // byte offset of channel c (0..255), row r (0..31) inside one MN-major SWIZZLE_128B plane of a stage
 __device__ __forceinline__ uint32_t plane_off(int r, int c) {
   return (uint32_t)((c >> 6) * kChanBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __rest
       const int rr = rsel + 2 * i;
       float4 x = pre[i];
       if (is_k) {
-        if (s * kRowsPerStage + rr < n_valid) { x.x = elu1(x.x); x.y = elu1(x.y); x.z = elu1(x.z); x.w = elu1(x.w); }
+        if (s * kRowsPerStage + rr < n_valid) { x.x = elu1_fast(x.x); x.y = elu1_fast(x.y); x.z = elu1_fast(x.z); x.w = elu1_fast(x.w); }
         ks4[0] += x.x; ks4[1] += x.y; ks4[2] += x.z; ks4[3] += x.w;
       }
       const float2 a = make_float2(x.x * kPre, x.y * kPre), b = make_float2(x.z * kPre, x.w * kPre);
