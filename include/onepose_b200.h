@@ -95,6 +95,8 @@ int opb_last_launch_count(const opb_matcher* m);
  * whole forward (first to last kernel).  Profiling perturbs timing slightly: never on in timed runs. */
 int opb_set_profiling(opb_matcher* m, int32_t enable);
 int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms);
+/* Same for the launches whose profile name starts with `prefix` ("gemm epi1" = the mlp.0 GEMM, "kv_state", ...). */
+int opb_get_profile_entry(opb_matcher* m, const char* prefix, double* ms, double* flops, int32_t* launches);
 
 /* Which element-wise consumers ride in the GEMM epilogues (gemm_backend 0 only): 0 = none, 1 = those that measured
  * faster in-stream on B200 (InstanceNorm partial sums, residual add, L2 normalise; default), 2 = all (K/V planes +

@@ -40,6 +40,7 @@ SYMBOLS = {
     "opb_set_hoist": (C.c_int, [_P, C.c_int32]),
     "opb_set_fuse_level": (C.c_int, [_P, C.c_int32]),
     "opb_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "opb_get_profile_entry": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "opb_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "opb_segmented_mean_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "opb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -734,6 +734,24 @@ int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t
   return OPB_OK;
 }
 
+int opb_get_profile_entry(opb_matcher* m, const char* prefix, double* ms_out, double* flops_out, int32_t* launches_out) {
+  if (!m || !prefix || !m->ev_fwd1) return OPB_E_STATE;
+  CK(m, cudaEventSynchronize(m->ev_fwd1));
+  double ms = 0, fl = 0;
+  int n = 0;
+  const size_t pl = strlen(prefix);
+  for (size_t i = 0; i < m->ev_flops.size(); ++i) {
+    if (m->ev_name[i].compare(0, pl, prefix) != 0) continue;
+    float t = 0;
+    CK(m, cudaEventElapsedTime(&t, i == 0 ? m->ev_fwd0 : m->ev_pool[i - 1], m->ev_pool[i]));
+    ms += t; fl += m->ev_flops[i]; ++n;
+  }
+  if (ms_out) *ms_out = ms;
+  if (flops_out) *flops_out = fl;
+  if (launches_out) *launches_out = n;
+  return OPB_OK;
+}
+
 int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int64_t* m0h, int64_t* m1h, float* s0h, float* s1h, float* confh,
                      void* stream) {
   if (!m) return OPB_E_INVALID;

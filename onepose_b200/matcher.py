@@ -222,6 +222,12 @@ class GATsSuperGlue(nn.Module):
         _lib.check(self._lib.opb_get_profile(self._handle, C.byref(g), C.byref(f), C.byref(n), C.byref(t)), self._handle)
         return {"gemm_ms": g.value, "gemm_flops": f.value, "gemm_launches": n.value, "total_ms": t.value}
 
+    def get_profile_entry(self, prefix: str):
+        g, f = C.c_double(), C.c_double()
+        n = C.c_int32()
+        _lib.check(self._lib.opb_get_profile_entry(self._handle, prefix.encode(), C.byref(g), C.byref(f), C.byref(n)), self._handle)
+        return {"ms": g.value, "flops": f.value, "launches": n.value}
+
     def launch_count(self) -> int:
         return int(self._lib.opb_last_launch_count(self._handle)) if self._handle is not None else 0
 
