@@ -97,6 +97,9 @@ struct opb_matcher {
   DevBuf range_flag;
   // host-call staging
   DevBuf st_q, st_m0, st_m1, st_s0, st_s1, st_conf;
+  cudaStream_t copy_stream = nullptr;          // opb_forward_host: H2D of chunk i+1 overlaps the compute of chunk i
+  std::vector<cudaEvent_t> h2d_ev;              // one per chunk; consumed by the chunk loop of opb_forward
+  int h2d_pending = 0;
   Layout last_layout{};
   // profiling (bench.py roofline leg)
   bool profiling = false;
@@ -529,6 +532,8 @@ void opb_destroy(opb_matcher* m) {
   m->kvpieces.release(); m->rowsum_part.release(); m->colsum_part.release(); m->ksum_part.release();
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
+  for (auto e : m->h2d_ev) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }
   delete m;
 }
@@ -686,8 +691,9 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (m->hoist) {
     if (int rc = object_prologue(m, st)) return rc;
   }
-  for (int f0 = 0; f0 < B; f0 += chunk) {
+  for (int f0 = 0, ci = 0; f0 < B; f0 += chunk, ++ci) {
     const int fb = std::min(chunk, B - f0);
+    if (ci < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[ci], 0));   // this chunk's queries have landed
     int rc = forward_chunk(m, q + (size_t)f0 * kD * N, N, fb, m0 + (size_t)f0 * N, m1 + (size_t)f0 * m->M, s0 + (size_t)f0 * N,
                            s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st);
     if (rc) return rc;
@@ -766,10 +772,29 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   CK(m, m->st_s0.ensure((size_t)B * N * sizeof(float)));
   CK(m, m->st_s1.ensure((size_t)B * M * sizeof(float)));
   CK(m, m->st_conf.ensure((size_t)B * N * M * sizeof(float)));  // conf is always materialised (reference returns it)
-  CK(m, cudaMemcpyAsync(m->st_q.p, qh, (size_t)B * kD * N * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (int rc = opb_forward(m, m->st_q.as<float>(), B, N, m->st_m0.as<int64_t>(), m->st_m1.as<int64_t>(), m->st_s0.as<float>(),
-                           m->st_s1.as<float>(), m->st_conf.as<float>(), stream))
-    return rc;
+  // H2D per chunk on a side stream: the copy of chunk i+1 runs under the compute of chunk i
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 16;
+  if (chunk > B) chunk = B;
+  if (!m->copy_stream) CK(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  const int n_chunks = (B + chunk - 1) / chunk;
+  while ((int)m->h2d_ev.size() < n_chunks + 1) {
+    cudaEvent_t e;
+    CK(m, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->h2d_ev.push_back(e);
+  }
+  CK(m, cudaEventRecord(m->h2d_ev[n_chunks], st));                       // staging buffer reuse: wait for earlier work on `st`
+  CK(m, cudaStreamWaitEvent(m->copy_stream, m->h2d_ev[n_chunks], 0));
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int f0 = ci * chunk, fb = std::min(chunk, B - f0);
+    const size_t off = (size_t)f0 * kD * N;
+    CK(m, cudaMemcpyAsync(m->st_q.as<float>() + off, qh + off, (size_t)fb * kD * N * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+    CK(m, cudaEventRecord(m->h2d_ev[ci], m->copy_stream));
+  }
+  m->h2d_pending = n_chunks;
+  const int frc = opb_forward(m, m->st_q.as<float>(), B, N, m->st_m0.as<int64_t>(), m->st_m1.as<int64_t>(), m->st_s0.as<float>(),
+                              m->st_s1.as<float>(), m->st_conf.as<float>(), stream);
+  m->h2d_pending = 0;
+  if (frc) return frc;
   CK(m, cudaMemcpyAsync(m0h, m->st_m0.p, (size_t)B * N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CK(m, cudaMemcpyAsync(m1h, m->st_m1.p, (size_t)B * M * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CK(m, cudaMemcpyAsync(s0h, m->st_s0.p, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToHost, st));

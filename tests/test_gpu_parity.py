@@ -238,6 +238,24 @@ def test_fuse_levels_agree(level):
     _check_against(m.last_batched, ref, f"fuse level {level}")
 
 
+def test_host_buffer_call_equals_device_call():
+    """opb_forward_host (pinned host in / host out, chunked H2D on a side stream) == opb_forward on device tensors."""
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    data = synthetic.make_batch(8, list(range(5)), 260, 600, 8)
+    m = _module(sd, hp, "tcgen05")
+    m.set_chunk_frames(2)                       # 3 chunks: 2 + 2 + 1
+    m.set_object(torch.from_numpy(data["descriptors3d_db"][0]).cuda(), torch.from_numpy(data["descriptors2d_db"][0]).cuda())
+    q = torch.from_numpy(data["descriptors2d_query"])
+    dev = m.match_frames(q.cuda())
+    for _ in range(2):                          # second call reuses the staging buffers / events
+        host = m.match_frames_host(q.pin_memory())
+    for k in ("matches0", "matches1", "matching_scores0", "matching_scores1"):
+        assert torch.equal(host[k], dev[k].cpu()), k
+    ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+    np.testing.assert_array_equal(host["matches0"].numpy(), ref["matches0"].numpy())
+
+
 def test_repeat_calls_are_deterministic():
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
