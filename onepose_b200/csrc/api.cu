@@ -18,6 +18,8 @@
 
 namespace opb {
 
+constexpr int kDefaultChunk = 32;   // frames pushed through the GNN together (measured: 4 -> 1340, 8 -> 1650, 16 -> 2390, 32 -> 2550 frames/s)
+
 static thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -677,7 +679,7 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (!q || !m0 || !m1 || !s0 || !s1 || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward: bad argument (B=%d, N=%d)", B, N);
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 16;
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
   if (chunk > B) chunk = B;
   if (int rc = ensure_workspace(m, chunk, N)) return rc;
   m->launches = 0;
@@ -773,7 +775,7 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   CK(m, m->st_s1.ensure((size_t)B * M * sizeof(float)));
   CK(m, m->st_conf.ensure((size_t)B * N * M * sizeof(float)));  // conf is always materialised (reference returns it)
   // H2D per chunk on a side stream: the copy of chunk i+1 runs under the compute of chunk i
-  int chunk = m->chunk_frames > 0 ? m->chunk_frames : 16;
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
   if (chunk > B) chunk = B;
   if (!m->copy_stream) CK(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   const int n_chunks = (B + chunk - 1) / chunk;
