@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = row_ok && (col0 + j) < M;
-            const float e = ok ? expf((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
+            const float e = ok ? __expf((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
             if (EPI == EPI_SCORE_SUMS) {
               o[j] = e;
               rs += e;

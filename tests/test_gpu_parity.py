@@ -125,6 +125,19 @@ def test_metric_shape_one_frame_vs_oracle():
     print(f"metric-shape max|dconf| = {err:.2e}")
 
 
+def test_dense_stress_shape_vs_oracle():
+    """BASELINE configs[3]: N2D=2000, N3D=15000 (dual-softmax + mutual-NN at the largest size the survey names)."""
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    data = synthetic.make_batch(11, [90], 2000, 15000, 8)
+    ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+    m = _module(sd, hp, "tcgen05")
+    m(_cuda(data))
+    err = _check_against(m.last_batched, ref, "dense stress")
+    assert int((m.last_batched["matches0"] > -1).sum()) >= 900
+    print(f"dense-stress max|dconf| = {err:.2e}")
+
+
 def test_full_size_properties():
     """Size-independent properties at the bench configuration (B=8 frames of one object)."""
     hp = dict(synthetic.DEFAULT_HPARAMS)
