@@ -134,7 +134,7 @@ def test_dense_stress_shape_vs_oracle():
     m = _module(sd, hp, "tcgen05")
     m(_cuda(data))
     err = _check_against(m.last_batched, ref, "dense stress")
-    assert int((m.last_batched["matches0"] > -1).sum()) >= 900
+    assert int((m.last_batched["matches0"] > -1).sum()) == int((ref["matches0"] > -1).sum()) > 500
     print(f"dense-stress max|dconf| = {err:.2e}")
 
 
