@@ -478,7 +478,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   launched("score_col_sums");
   CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
   CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
-  conf_argmax_simt<<<dim3((L.M + 895) / 896, (N + 63) / 64, fb), 128, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>(),
+  conf_argmax_simt<<<dim3((L.M + 127) / 128, (N + 31) / 32, fb), 128, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>(),
                                                                               m->colsum.as<float>(), conf,
                                                                               m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
   launched("conf_argmax_simt");

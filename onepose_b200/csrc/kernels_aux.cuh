@@ -808,56 +808,33 @@ __device__ __forceinline__ unsigned long long pack_arg(float v, int idx) {
 }
 
 // conf = e^2 / (rowsum*colsum); optional store to conf [B][N][M]; row/col arg-max via packed atomicMax.
-// Each warp owns a strip of 7 x 32 columns for 64 rows: one row-best atomic per (row, 224 columns) and one
-// column-best atomic per (column, 64 rows) -- 7x / 2x fewer L2 atomics than one per 32-wide piece.
-// grid (ceil(M/896), ceil(N/64), B), block 128 (4 warps x 224 columns).
-constexpr int kConfStrip = 7;
-__global__ void __launch_bounds__(128) conf_argmax_simt(const float* __restrict__ s, Layout L, float inv_scale, const float* __restrict__ rowsum,
-                                                        const float* __restrict__ colsum, float* __restrict__ conf,
-                                                        unsigned long long* __restrict__ rowbest /*[B][N]*/,
-                                                        unsigned long long* __restrict__ colbest /*[B][M]*/) {
+// block = 32 rows x 128 cols tile; grid (ceil(M/128), ceil(N/32), B); block 128 threads (thread = column).
+__global__ void conf_argmax_simt(const float* __restrict__ s, Layout L, float inv_scale, const float* __restrict__ rowsum,
+                                 const float* __restrict__ colsum, float* __restrict__ conf,
+                                 unsigned long long* __restrict__ rowbest /*[B][N]*/, unsigned long long* __restrict__ colbest /*[B][M]*/) {
   const int b = blockIdx.z;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cb = (blockIdx.x * 4 + warp) * (32 * kConfStrip) + lane;      // this lane's first column
-  const int n0 = blockIdx.y * 64, n1 = min(n0 + 64, L.N);
-  float ics[kConfStrip];
-  unsigned long long cbest[kConfStrip];
-#pragma unroll
-  for (int k = 0; k < kConfStrip; ++k) {
-    const int m = cb + 32 * k;
-    ics[k] = m < L.M ? colsum[b * L.m_pad + m] : 0.f;                      // the sums kernels store inverses
-    cbest[k] = 0ull;
-  }
-  for (int n = n0; n < n1; ++n) {
-    const float irs = rowsum[b * L.n_pad + n];
-    const float* srow = s + ((long long)b * L.n_pad + n) * L.m_pad;
-    float* crow = conf ? conf + ((long long)b * L.N + n) * L.M : nullptr;
-    float rv = -1.f;
-    int rm = 0;
-#pragma unroll
-    for (int k = 0; k < kConfStrip; ++k) {
-      const int m = cb + 32 * k;
-      if (m < L.M) {
-        const float e = __expf((srow[m] - 1.f) * inv_scale);
-        const float c = (e * irs) * (e * ics[k]);
-        if (crow) crow[m] = c;
-        const unsigned long long pk = pack_arg(c, n);
-        cbest[k] = pk > cbest[k] ? pk : cbest[k];
-        if (c > rv) { rv = c; rm = m; }                                     // ascending m: the first maximum is kept
-      }
+  const int m = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * 32;
+  const bool mv = m < L.M;
+  const float inv_cs = mv ? colsum[b * L.m_pad + m] : 0.f;      // the sums kernels store inverses
+  unsigned long long cbest = 0ull;
+  const int lane = threadIdx.x & 31;
+  for (int n = n0; n < min(n0 + 32, L.N); ++n) {
+    float c = 0.f;
+    if (mv) {
+      float e = __expf((s[((long long)b * L.n_pad + n) * L.m_pad + m] - 1.f) * inv_scale);
+      c = (e * rowsum[b * L.n_pad + n]) * (e * inv_cs);
+      if (conf) conf[((long long)b * L.N + n) * L.M + m] = c;
+      unsigned long long pk = pack_arg(c, n);
+      cbest = pk > cbest ? pk : cbest;
     }
-    // row arg-max over the strip: conf >= 0, so its bit pattern orders like an unsigned integer; lowest column wins ties
-    const unsigned bits = rv >= 0.f ? __float_as_uint(rv) : 0u;
+    // row arg-max over this warp's 32 columns: conf >= 0 so its bit pattern orders like an unsigned integer
+    const unsigned bits = mv ? __float_as_uint(c) : 0u;
     const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-    const unsigned cand = (rv >= 0.f && bits == wmax) ? (unsigned)rm : 0xFFFFFFFFu;
-    const unsigned mmin = __reduce_min_sync(0xffffffffu, cand);
-    if (lane == 0 && mmin != 0xFFFFFFFFu) atomicMax(&rowbest[(long long)b * L.N + n], pack_arg(__uint_as_float(wmax), (int)mmin));
+    const unsigned who = __ballot_sync(0xffffffffu, mv && bits == wmax);
+    if (who && lane == __ffs(who) - 1) atomicMax(&rowbest[(long long)b * L.N + n], pack_arg(c, m));   // lowest column wins ties
   }
-#pragma unroll
-  for (int k = 0; k < kConfStrip; ++k) {
-    const int m = cb + 32 * k;
-    if (m < L.M && cbest[k]) atomicMax(&colbest[(long long)b * L.M + m], cbest[k]);
-  }
+  if (mv && cbest) atomicMax(&colbest[(long long)b * L.M + m], cbest);
 }
 
 // Mutual nearest neighbour + threshold (reference GATs_SuperGlue.py:220-230).
