@@ -85,6 +85,10 @@ int opb_forward_host(opb_matcher* m, const float* desc2d_query_host, int32_t B, 
                      int64_t* matches0_host, int64_t* matches1_host, float* mscores0_host,
                      float* mscores1_host, float* conf_host, void* stream);
 
+/* Range guard of the fp16-split operand format: synchronises `stream` and returns OPB_E_RANGE if any opb_forward since the
+ * last check produced an activation outside |x| < 1023 (or a NaN); OPB_OK otherwise.  opb_forward_host calls it itself. */
+int opb_check_range(opb_matcher* m, void* stream);
+
 /* Number of kernels opb_forward launched in its last call (bench.py "gpu_launches"). */
 int opb_last_launch_count(const opb_matcher* m);
 

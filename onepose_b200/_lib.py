@@ -35,6 +35,7 @@ SYMBOLS = {
     "opb_set_object": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "opb_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "opb_forward_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "opb_check_range": (C.c_int, [_P, _P]),
     "opb_last_launch_count": (C.c_int, [_P]),
     "opb_set_chunk_frames": (C.c_int, [_P, C.c_int32]),
     "opb_set_hoist": (C.c_int, [_P, C.c_int32]),

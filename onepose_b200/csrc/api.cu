@@ -432,6 +432,9 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     }
   }
 
+  range_check<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, (long long)rows * kD / 8, m->range_flag.as<int>());
+  launched("range_check");
+
   // ---- tail (GATs_SuperGlue.py:209-237) ----
   GemmProblem pf{};
   pf.L = L; pf.batch = 1; pf.rows = rows;
@@ -803,6 +806,18 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   CK(m, cudaMemcpyAsync(s1h, m->st_s1.p, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (confh) CK(m, cudaMemcpyAsync(confh, m->st_conf.p, (size_t)B * N * M * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(m, cudaStreamSynchronize(st));
+  return opb_check_range(m, stream);
+}
+
+int opb_check_range(opb_matcher* m, void* stream) {
+  if (!m || !m->range_flag.p) return OPB_OK;
+  int flag = 0;
+  CK(m, cudaMemcpyAsync(&flag, m->range_flag.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(m, cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) {
+    CK(m, cudaMemsetAsync(m->range_flag.p, 0, sizeof(int), (cudaStream_t)stream));
+    return fail(m, OPB_E_RANGE, "an activation left the fp16-split operand range (|x| >= 1023) or became NaN: results of this call are invalid");
+  }
   return OPB_OK;
 }
 

@@ -708,6 +708,19 @@ __global__ void residual_update(__half* __restrict__ x_hi, __half* __restrict__ 
   reinterpret_cast<uint4*>(x_lo)[i] = ul;
 }
 
+// Range guard of the fp16-split operand format (|x| < 1023): an overflow anywhere in the GNN turns into inf/NaN and
+// stays in the residual stream, so scanning the final X hi-plane once per chunk detects it.  Sets *flag = 1.
+__global__ void range_check(const __half* __restrict__ x_hi, long long n_vec /* elements / 8 */, int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const uint4 u = reinterpret_cast<const uint4*>(x_hi)[i];
+  const unsigned w[4] = {u.x, u.y, u.z, u.w};
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) bad |= ((w[k] & 0x7C00u) == 0x7C00u) || ((w[k] & 0x7C000000u) == 0x7C000000u);   // exponent all ones: inf / NaN
+  if (bad) atomicOr(flag, 1);
+}
+
 // planes -> fp32 (debug / tests)
 __global__ void join_planes(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

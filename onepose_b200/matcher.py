@@ -277,6 +277,8 @@ class GATsSuperGlue(nn.Module):
                 self.set_object(desc3d_db[g[0]], desc2d_db[g[0]])
                 self._object_key = key
             outs.append(self.match_frames(desc2d_query[g[0]:g[-1] + 1]))
+        # range guard of the fp16-split operand format (one 4-byte read-back; the reference caller syncs right after anyway)
+        _lib.check(self._lib.opb_check_range(self._handle, torch.cuda.current_stream(desc2d_query.device).cuda_stream), self._handle)
         out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
         self.last_batched = out
         pred = {

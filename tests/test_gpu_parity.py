@@ -269,6 +269,21 @@ def test_host_buffer_call_equals_device_call():
     np.testing.assert_array_equal(host["matches0"].numpy(), ref["matches0"].numpy())
 
 
+def test_operand_range_guard_fires():
+    """Activations beyond the fp16-split operand range (|x| >= 1023) must be reported, not silently wrong."""
+    from onepose_b200 import _lib
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0)
+    sd = {k: (v * 3e4 if k.endswith("mlp.3.weight") else v) for k, v in sd.items()}     # residual stream explodes
+    m = _module(sd, hp, "tcgen05")
+    with pytest.raises(_lib.OpbError, match="OPB_E_RANGE"):
+        m(_cuda(synthetic.make_batch(1, [1], 128, 256, 8)))
+    # the guard is cleared by the check: a sane model on the same process still works
+    ok = _module(synthetic.make_state_dict(0), hp, "tcgen05")
+    pred, _ = ok(_cuda(synthetic.make_batch(1, [1], 128, 256, 8)))
+    assert int((pred["matches0"] > -1).sum()) > 0
+
+
 def test_repeat_calls_are_deterministic():
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
