@@ -44,6 +44,14 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// A window of rows of a [rows, 256] plane pair (the residual stream of a chunk, the query-only buffer, ...).
+struct XView {
+  __half* hi;
+  __half* lo;
+  CPlanes c(int ld) const { return CPlanes{hi, lo, ld}; }
+  Planes m(int ld) const { return Planes{hi, lo, ld}; }
+};
+
 struct PlaneBuf {
   DevBuf hi, lo;
   cudaError_t ensure(size_t elems, bool zero = false) {
@@ -54,6 +62,7 @@ struct PlaneBuf {
   void release() { hi.release(); lo.release(); }
   CPlanes c(int ld, size_t off_elems = 0) const { return CPlanes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
   Planes m(int ld, size_t off_elems = 0) const { return Planes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
+  XView view(size_t row_off = 0) const { return XView{hi.as<__half>() + row_off * kD, lo.as<__half>() + row_off * kD}; }
 };
 
 struct AttnLayerW {       // one AttentionPropagation (reference GATs_SuperGlue.py:104-113)
@@ -238,16 +247,16 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
 }
 
 // One GATs layer on the 3D-point segments of `x` (layout L).
-static int run_gats(opb_matcher* m, const Layout& L, PlaneBuf& x, int gi, cudaStream_t st) {
+static int run_gats(opb_matcher* m, const Layout& L, XView x, int gi, cudaStream_t st) {
   const long long warps = (long long)L.M * L.B;
   if (warps == 0) return 0;
   if (m->Lf == 8 && L.B > 1)   // leaves loaded once per point and reused across the frames of the chunk
     gats_aggregate_frames8<<<(unsigned)(((long long)L.M * 32 + 255) / 256), 256, 0, st>>>(
-        x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+        x.hi, x.lo, L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
         m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
   else
     gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-        x.hi.as<__half>(), x.lo.as<__half>(), L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
+        x.hi, x.lo, L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
         m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
   m->launches++;
   prof_mark(m, st, "gats_aggregate", 0.0);
@@ -256,12 +265,12 @@ static int run_gats(opb_matcher* m, const Layout& L, PlaneBuf& x, int gi, cudaSt
 
 // One AttentionPropagation layer (reference GATs_SuperGlue.py:55-64, :104-113) on every segment of `x`:
 // both sides of all frames in ONE set of launches (the layer's weights are shared by the two sides).
-static int run_attn_layer(opb_matcher* m, const Layout& L, PlaneBuf& x, AttnLayerW& W, int cross, cudaStream_t st) {
+static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& W, int cross, cudaStream_t st) {
   const int rows = L.rows();
   const int S = L.segs();
   const int tiles = rows / kTileRows;
   const double valid_rows = (double)L.B * (L.N + L.M);
-  __half *xh = x.hi.as<__half>(), *xl = x.lo.as<__half>();
+  __half *xh = x.hi, *xl = x.lo;
   auto launched = [&](const char* name = "aux") { m->launches++; prof_mark(m, st, name, 0.0); };
   if (m->cfg.gemm_backend == 0 && m->fuse >= 2) {
     // ---------------- fully fused tcgen05 pipeline ----------------
@@ -383,13 +392,15 @@ static int object_prologue(opb_matcher* m, cudaStream_t st) {
   Lo.B = 1; Lo.N = 0; Lo.M = m->M; Lo.n_pad = 0; Lo.m_pad = m->m_pad; Lo.R = m->m_pad;
   CK(m, cudaMemcpyAsync(m->xo.hi.p, m->db.hi.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
   CK(m, cudaMemcpyAsync(m->xo.lo.p, m->db.lo.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
-  if (int rc = run_gats(m, Lo, m->xo, 0, st)) return rc;
-  return run_attn_layer(m, Lo, m->xo, m->attn[0], /*cross=*/0, st);
+  if (int rc = run_gats(m, Lo, m->xo.view(), 0, st)) return rc;
+  return run_attn_layer(m, Lo, m->xo.view(), m->attn[0], /*cross=*/0, st);
 }
 
 // GNN + tail for `fb` frames starting at frame f0 of the call.
+constexpr int kQPassFrames = 16;
+
 static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
-                         float* conf, cudaStream_t st) {
+                         float* conf, cudaStream_t st, int piece, int h2d_first) {
   Layout L;
   L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kSegPad); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
   m->last_layout = L;
@@ -401,12 +412,19 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
   int first_layer = 0;
   if (m->hoist) {
     // layer 1 (self) for the query side only, on a compact [fb*n_pad, 256] buffer; layer 0 does not touch queries
-    Layout Lq;
-    Lq.B = fb; Lq.N = N; Lq.M = 0; Lq.n_pad = L.n_pad; Lq.m_pad = 0; Lq.R = L.n_pad;
-    transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, m->xq.hi.as<__half>(), m->xq.lo.as<__half>(),
-                                                                             nullptr, Lq.R, 0);
-    launched("transpose_cf_to_rows");
-    if (int rc = run_attn_layer(m, Lq, m->xq, m->attn[0], 0, st)) return rc;
+    // in sub-batches of `piece` frames: with host input (opb_forward_host) each sub-batch starts as soon as ITS descriptors
+    // have landed, so the H2D copy of the rest runs under this pass
+    for (int s0 = 0, si = 0; s0 < fb; s0 += piece, ++si) {
+      const int sb = std::min(piece, fb - s0);
+      if (h2d_first + si < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[h2d_first + si], 0));
+      Layout Lq;
+      Lq.B = sb; Lq.N = N; Lq.M = 0; Lq.n_pad = L.n_pad; Lq.m_pad = 0; Lq.R = L.n_pad;
+      XView xq = m->xq.view((size_t)s0 * L.n_pad);
+      transpose_cf_to_rows<0><<<dim3((N + 31) / 32, sb), dim3(32, 8), 0, st>>>(q_cf + (size_t)s0 * kD * N, N, (long long)kD * N, xq.hi, xq.lo, nullptr,
+                                                                               Lq.R, 0);
+      launched("transpose_cf_to_rows");
+      if (int rc = run_attn_layer(m, Lq, xq, m->attn[0], 0, st)) return rc;
+    }
     // assemble the full layout: query rows from xq, 3D rows from the object prologue
     CK(m, cudaMemcpy2DAsync(xh, (size_t)L.R * kD * sizeof(__half), m->xq.hi.p, (size_t)L.n_pad * kD * sizeof(__half),
                             (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
@@ -425,10 +443,10 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
 
   for (int layer = first_layer; layer < 12; ++layer) {
     if (layer % 3 == 0) {
-      if (int rc = run_gats(m, L, m->x, layer / 3, st)) return rc;
+      if (int rc = run_gats(m, L, m->x.view(), layer / 3, st)) return rc;
     } else {
       const int attn_idx = (layer / 3) * 2 + (layer % 3) - 1;
-      if (int rc = run_attn_layer(m, L, m->x, m->attn[attn_idx], (layer % 3 == 2) ? 1 : 0, st)) return rc;
+      if (int rc = run_attn_layer(m, L, m->x.view(), m->attn[attn_idx], (layer % 3 == 2) ? 1 : 0, st)) return rc;
     }
   }
 
@@ -696,11 +714,15 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (m->hoist) {
     if (int rc = object_prologue(m, st)) return rc;
   }
+  const int piece = std::min(chunk, kQPassFrames);          // granularity of the query-side layer-1 pass and of the host copies
+  const int ppc = (chunk + piece - 1) / piece;              // pieces per chunk
   for (int f0 = 0, ci = 0; f0 < B; f0 += chunk, ++ci) {
     const int fb = std::min(chunk, B - f0);
-    if (ci < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[ci], 0));   // this chunk's queries have landed
+    if (!m->hoist)                                          // per-frame evaluation consumes the whole chunk at once
+      for (int si = 0; si * piece < fb; ++si)
+        if (ci * ppc + si < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[ci * ppc + si], 0));
     int rc = forward_chunk(m, q + (size_t)f0 * kD * N, N, fb, m0 + (size_t)f0 * N, m1 + (size_t)f0 * m->M, s0 + (size_t)f0 * N,
-                           s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st);
+                           s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st, piece, ci * ppc);
     if (rc) return rc;
   }
   if (m->profiling) cudaEventRecord(m->ev_fwd1, st);
@@ -781,21 +803,29 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
   if (chunk > B) chunk = B;
   if (!m->copy_stream) CK(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  const int piece = std::min(chunk, kQPassFrames);
+  const int ppc = (chunk + piece - 1) / piece;
   const int n_chunks = (B + chunk - 1) / chunk;
-  while ((int)m->h2d_ev.size() < n_chunks + 1) {
+  const int n_ev = n_chunks * ppc;
+  while ((int)m->h2d_ev.size() < n_ev + 1) {
     cudaEvent_t e;
     CK(m, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     m->h2d_ev.push_back(e);
   }
-  CK(m, cudaEventRecord(m->h2d_ev[n_chunks], st));                       // staging buffer reuse: wait for earlier work on `st`
-  CK(m, cudaStreamWaitEvent(m->copy_stream, m->h2d_ev[n_chunks], 0));
+  CK(m, cudaEventRecord(m->h2d_ev[n_ev], st));                           // staging buffer reuse: wait for earlier work on `st`
+  CK(m, cudaStreamWaitEvent(m->copy_stream, m->h2d_ev[n_ev], 0));
   for (int ci = 0; ci < n_chunks; ++ci) {
-    const int f0 = ci * chunk, fb = std::min(chunk, B - f0);
-    const size_t off = (size_t)f0 * kD * N;
-    CK(m, cudaMemcpyAsync(m->st_q.as<float>() + off, qh + off, (size_t)fb * kD * N * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
-    CK(m, cudaEventRecord(m->h2d_ev[ci], m->copy_stream));
+    const int c0 = ci * chunk, cb = std::min(chunk, B - c0);
+    for (int si = 0; si < ppc; ++si) {
+      const int f0 = c0 + si * piece, fb = std::min(piece, c0 + cb - f0);
+      if (fb > 0) {
+        const size_t off = (size_t)f0 * kD * N;
+        CK(m, cudaMemcpyAsync(m->st_q.as<float>() + off, qh + off, (size_t)fb * kD * N * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+      }
+      CK(m, cudaEventRecord(m->h2d_ev[ci * ppc + si], m->copy_stream));
+    }
   }
-  m->h2d_pending = n_chunks;
+  m->h2d_pending = n_ev;
   const int frc = opb_forward(m, m->st_q.as<float>(), B, N, m->st_m0.as<int64_t>(), m->st_m1.as<int64_t>(), m->st_s0.as<float>(),
                               m->st_s1.as<float>(), m->st_conf.as<float>(), stream);
   m->h2d_pending = 0;
