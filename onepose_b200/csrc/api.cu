@@ -714,7 +714,8 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
   if (m->hoist) {
     if (int rc = object_prologue(m, st)) return rc;
   }
-  const int piece = std::min(chunk, kQPassFrames);          // granularity of the query-side layer-1 pass and of the host copies
+  // granularity of the query-side layer-1 pass: the host-copy pieces when the queries stream in from the host, else the chunk
+  const int piece = m->h2d_pending > 0 ? std::min(chunk, kQPassFrames) : chunk;
   const int ppc = (chunk + piece - 1) / piece;              // pieces per chunk
   for (int f0 = 0, ci = 0; f0 < B; f0 += chunk, ++ci) {
     const int fb = std::min(chunk, B - f0);
