@@ -251,7 +251,7 @@ static int run_gats(opb_matcher* m, const Layout& L, XView x, int gi, cudaStream
   const long long warps = (long long)L.M * L.B;
   if (warps == 0) return 0;
   if (m->Lf == 8 && L.B > 1)   // leaves loaded once per point and reused across the frames of the chunk
-    gats_aggregate_frames8<<<(unsigned)(((long long)L.M * 32 + 255) / 256), 256, 0, st>>>(
+    gats_aggregate_frames8<<<(unsigned)(((long long)L.M * ((L.B + kGatsFramesPerWarp - 1) / kGatsFramesPerWarp) * 32 + 255) / 256), 256, 0, st>>>(
         x.hi, x.lo, L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
         m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
   else
@@ -327,15 +327,17 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p.L = L; p.batch = 1; p.rows = rows;
   p.a1 = x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
   p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
+  const int pre_act = m->cfg.gemm_backend != 1 ? 1 : 0;    // tcgen05 core: elu+1 on the Q and K columns already in the GEMM epilogue
+  if (pre_act) p.elu_cols = 512;
   if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)
   int rows_per_partial = kTileRows;
   if (m->cfg.gemm_backend == 1) {                 // SIMT cross-check path: plain FFMA kernel
     kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
   } else if (m->kv_mode == 1) {                   // warp-level mma.sync variant (kept for comparison)
-    kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
+    kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, pre_act, L, m->kvpart.as<float>());
   } else {                                        // tcgen05: conversion + UMMA in one kernel, one partial per 256-row slab
-    if (launch_kv_state_tc(m->c768.as<float>(), 768, 256, 512, L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_tc launch failed");
+    if (launch_kv_state_tc(m->c768.as<float>(), 768, 256, 512, pre_act, L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_tc launch failed");
     rows_per_partial = 256;
   }
   launched("kv_state_partial");
@@ -343,7 +345,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
                                                                              m->kmean.as<float>());
   launched("kv_state_reduce");
   // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
-  q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, L, cross, m->kmean.as<float>(),
+  q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, pre_act, L, cross, m->kmean.as<float>(),
                                                                                 m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
   launched("q_scale_split");
   // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight

@@ -218,6 +218,9 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
 constexpr uint32_t kIdesc2MN = kIdesc2 | (1u << 15) | (1u << 16);                                           // A and B MN-major
 
+// elu(x)+1 on the hardware exponential (ex2.approx, ~2^-22 relative: the order of the fp16 split every consumer applies next)
+__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 // same for a 128-row x 64-B SWIZZLE_64B buffer (16-byte chunk j in 0..3): Swizzle<2,4,3> = address bits [4,6) ^= bits [7,9)
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             }
-            if (col0 < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
+            if (col0 < p.elu_cols) { o.x = elu1_fast(o.x); o.y = elu1_fast(o.y); o.z = elu1_fast(o.z); o.w = elu1_fast(o.w); }
             *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = o;
           }
           fence_async_smem();

@@ -186,12 +186,16 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
 // Same layer, warp per POINT looping over the frames of the chunk: the point's 8 leaf rows and leaf logits are read once
 // into registers and reused for every frame (the leaves are per-object constants; reference GATs.py:46 reshapes the same
 // tensor for every batch element).  Fast path for num_leaf == 8 (the released configuration, test_GATsSPG.yaml:5).
+constexpr int kGatsFramesPerWarp = 8;
 __global__ void __launch_bounds__(256) gats_aggregate_frames8(__half* __restrict__ x_hi, __half* __restrict__ x_lo, Layout L,
                                                               const float* __restrict__ leaves, const float* __restrict__ s2,
                                                               const float* __restrict__ wa3, int include_self, int additional, float alpha) {
   const int lane = threadIdx.x & 31;
-  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_groups = (L.B + kGatsFramesPerWarp - 1) / kGatsFramesPerWarp;   // frame groups: more warps in flight than points alone
+  const int i = (int)(wid / n_groups), fg = (int)(wid % n_groups);
   if (i >= L.M) return;
+  const int b_begin = fg * kGatsFramesPerWarp, b_end = min(L.B, b_begin + kGatsFramesPerWarp);
   float4 lu[8], lv[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(256) gats_aggregate_frames8(__half* __restrict
   for (int j = 0; j < 8; ++j) w3[j] = wa3[(j >> 2) * 128 + lane * 4 + (j & 3)];
   auto lrelu = [alpha](float v) { return v > 0.f ? v : alpha * v; };
 #pragma unroll 2
-  for (int b = 0; b < L.B; ++b) {
+  for (int b = b_begin; b < b_end; ++b) {
     const long long row = (long long)b * L.R + L.n_pad + i;
     float h3[8];
     {
@@ -528,7 +532,7 @@ __global__ void kv_reduce_pieces(const float* __restrict__ part, const float* __
 // with the /m, *m of :75,:79 folded into the means).  q: fp32 [rows, ldq] (cols 0..255,
 // head-contiguous, bias added).  Output fp16-split planes [rows, 256].  Warp per row.
 // ---------------------------------------------------------------------------------------
-__global__ void q_scale_split(const float* __restrict__ q, int ldq, Layout L, int cross,
+__global__ void q_scale_split(const float* __restrict__ q, int ldq, int activated, Layout L, int cross,
                               const float* __restrict__ kmean, __half* __restrict__ o_hi, __half* __restrict__ o_lo) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -539,7 +543,11 @@ __global__ void q_scale_split(const float* __restrict__ q, int ldq, Layout L, in
   const float4* qp = reinterpret_cast<const float4*>(q + row * ldq) + lane * 2;   // channels lane*8 .. +7
   const float4* kp = reinterpret_cast<const float4*>(kmean + (long long)src * kD) + lane * 2;
   float4 a = qp[0], b = qp[1], ka = kp[0], kb = kp[1];
-  float v[8] = {elu1(a.x), elu1(a.y), elu1(a.z), elu1(a.w), elu1(b.x), elu1(b.y), elu1(b.z), elu1(b.w)};
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (!activated) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = elu1(v[j]);
+  }
   float kk[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
   float dot = 0.f;
 #pragma unroll

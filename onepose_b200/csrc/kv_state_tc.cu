@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t plane_off(int r, int c) {
   return (uint32_t)((c >> 6) * kChanBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
 }
 
-__global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, Layout L,
+__global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated, Layout L,
                                                              float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __rest
       const int rr = rsel + 2 * i;
       float4 x = pre[i];
       if (is_k) {
-        if (s * kRowsPerStage + rr < n_valid) { x.x = elu1_fast(x.x); x.y = elu1_fast(x.y); x.z = elu1_fast(x.z); x.w = elu1_fast(x.w); }
+        if (!k_activated && s * kRowsPerStage + rr < n_valid) { x.x = elu1_fast(x.x); x.y = elu1_fast(x.y); x.z = elu1_fast(x.z); x.w = elu1_fast(x.w); }
         ks4[0] += x.x; ks4[1] += x.y; ks4[2] += x.z; ks4[3] += x.w;
       }
       const float2 a = make_float2(x.x * kPre, x.y * kPre), b = make_float2(x.z * kPre, x.w * kPre);
@@ -227,14 +227,14 @@ __global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __rest
 
 }  // namespace
 
-int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, const Layout& L, float* partial, cudaStream_t stream) {
+int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, int k_activated, const Layout& L, float* partial, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kv_state_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -2;
     attr_done = true;
   }
   const int slabs = L.rows() / 256;
-  kv_state_tc_kernel<<<slabs, 256, kSmemBytes, stream>>>(kv, ld, k_off, v_off, L, partial);
+  kv_state_tc_kernel<<<slabs, 256, kSmemBytes, stream>>>(kv, ld, k_off, v_off, k_activated, L, partial);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
