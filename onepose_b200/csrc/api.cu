@@ -327,7 +327,8 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p.L = L; p.batch = 1; p.rows = rows;
   p.a1 = x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
   p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
-  const int pre_act = m->cfg.gemm_backend != 1 ? 1 : 0;    // tcgen05 core: elu+1 on the Q and K columns already in the GEMM epilogue
+  const int pre_act = 0;   // 1: elu+1 on the Q and K columns in the GEMM epilogue -- measured slower (the 4-lane MUFU per SMSP stretches the
+                          // epilogue by more than the consumers save), kept as a switch
   if (pre_act) p.elu_cols = 512;
   if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)

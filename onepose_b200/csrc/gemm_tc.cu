@@ -8,12 +8,13 @@
 // computes in fp32 (GATs_SuperGlue.py:191-193) and the contract is 1e-4 abs on conf.
 //
 // Persistent grid (one CTA per SM), static round-robin tile schedule (n-tile fastest so CTAs that
-// share an A row-tile run together).  256 threads:
+// share an A row-tile run together).  384 threads:
 //   warp 0    TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B boxes -> 2-stage smem ring
 //   warp 1    MMA issuer     one lane: tcgen05.mma kind::f16, tcgen05.commit -> mbarriers
 //   warp 2    TMEM owner     512 columns = 2 accumulator buffers x 256 (epilogue of tile i overlaps
 //                            the main loop of tile i+1)
-//   warps 4-7 epilogue       tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
+//   warps 4-11 epilogue      two groups of 4 warps (each group = the 4 TMEM lane quarters) splitting the tile's columns:
+//                            tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
 #include <cuda.h>
 
 #include <cstdlib>
@@ -49,6 +50,7 @@ struct Cfg {
   static constexpr uint32_t kSBO = 8 * BK_ * 2;                   // bytes between 8-row groups
 };
 constexpr int kTmemCols = 512;
+constexpr int kThreads = 384;                    // warps 0-3: TMA / MMA / TMEM / spare; warps 4-11: two epilogue groups of 4 warps
 constexpr uint32_t kSpinLimit = 1u << 22;        // bounded waits: trap instead of hanging the GPU
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -188,7 +190,7 @@ __device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[1
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_id(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // the 4 warps of one epilogue group
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = bytes between 8-row groups | swizzle mode
@@ -267,7 +269,7 @@ struct Maps {
 // cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
 // B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
 template <int BK_, int CL, bool TWO, int EPI>
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
   using C = Cfg<BK_, TWO>;
   constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
@@ -280,6 +282,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+  // Epilogue groups: the TMEM -> registers -> staging -> TMA-store chain of one 32-column chunk is a serial latency chain
+  // (tcgen05.ld, two named barriers, proxy fence), so ONE group of 4 warps drains a 128 x 256 tile in ~8.5k cycles no matter
+  // how little it computes.  Two groups (each: 4 warps = the 4 TMEM lane quarters) split the tile's columns and overlap
+  // their chains.  The score epilogues keep one group (their row accumulators span the whole tile).
+  constexpr int kEpiGroups = (TWO && EPI != EPI_SCORE_SUMS && EPI != EPI_SCORE_CONF) ? 2 : 1;
+  constexpr int kColsPerGroup = BN / kEpiGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb1 = p.K1 / BK, nkb = (p.K1 + p.K2) / BK;
   // work unit = CL adjacent row tiles x one n-tile; this CTA takes row tile (CL*mgroup + crank)
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], TWO ? 8 : 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], (TWO ? 8 : 4) * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -422,18 +430,30 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         else tc_commit(&tmem_full_bar[buf]);                          // accumulator complete
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
     // ===================== epilogue: TMEM -> registers -> staging smem -> TMA store =====================
-    const int q = warp - 4;                         // TMEM lane quarter == warp_id % 4
+    const int grp = (warp - 4) >> 2;                // epilogue group: columns [grp*kColsPerGroup, +kColsPerGroup) of every tile
+    const int q = (warp - 4) & 3;                   // TMEM lane quarter == warp_id % 4
     const int r_in_tile = q * 32 + lane;
-    const bool leader = threadIdx.x == 128;
+    const int t_in_grp = threadIdx.x - 128 - grp * 128;
+    const bool leader = t_in_grp == 0;
+    const int c_begin = grp * kColsPerGroup, c_end = c_begin + kColsPerGroup;
+    auto epi_bar = [grp]() { epi_bar_id(1 + grp); };
+    // staging: one group -> two buffers used alternately; two groups -> one buffer each (the other group's chain overlaps)
+    auto stage_sel = [grp](uint32_t ctr) { return kEpiGroups == 2 ? (uint32_t)grp : (ctr & 1u); };
+    auto stage_wait = [leader]() {
+      if (leader) {
+        if (kEpiGroups == 2) tma_store_wait_read<0>();
+        else tma_store_wait_read<1>();
+      }
+    };
     uint32_t tc = 0, chunk_ctr = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++tc) {
       const int z = u / units_per_batch, rem = u - z * units_per_batch;
       const int m_tile = (rem / p.n_tiles) * CL + crank, n_tile = rem % p.n_tiles;
       const uint32_t buf = tc & 1;
       mbar_wait(&tmem_full_bar[buf], (tc >> 1) & 1);
-      if (tl && leader && tc < 8) tl[40 + 2 * tc] = clock64();
+      if (tl && threadIdx.x == 128 && tc < 8) tl[40 + 2 * tc] = clock64();
       tc_fence_after();
       const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       const int out_row0 = z * p.c_batch_rows + m_tile * BM;
@@ -447,13 +467,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       if (EPI == EPI_F32 || EPI == EPI_F32_STATS) {
         // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk, double-buffered staging
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
           tmem_ld32(lane_base + c0, v);
           tmem_ld_wait();
           const int col0 = n_tile * BN + c0;
-          uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
-          if (leader) tma_store_wait_read<1>();     // the store that last read this buffer (2 chunks ago) is done with it
+          uint8_t* sb = staging + stage_sel(chunk_ctr) * kStagingBytes;
+          stage_wait();                             // the store that last read this buffer is done with it
           epi_bar();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -477,7 +497,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           }
           if (EPI == EPI_F32_STATS) {
             // InstanceNorm partial sums straight from the staged tile: thread = (32-row quarter, column)
-            const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;
+            const int t = t_in_grp, qq = t >> 5, cc = t & 31;
             float sum = 0.f, sq = 0.f;
             const int r_end = min(32, n_valid - qq * 32);
             for (int i = 0; i < r_end; ++i) {
@@ -496,7 +516,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         const int N = p.L.N, M = p.L.M;
         const int row = row0 + r_in_tile;                          // query index inside frame z
         const bool row_ok = row < N;
-        const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31; // column-pass role: (32-row quarter, column)
+        const int t = t_in_grp, qq = t >> 5, cc = t & 31;          // column-pass role: (32-row quarter, column)
         float rs = 0.f;                                            // SUMS: row sum over this tile's columns
         float irs = 0.f;
         unsigned long long rbest = 0ull;
@@ -576,11 +596,11 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         uint4 xh[4], xl[4];
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          xh[j8] = *reinterpret_cast<const uint4*>(xh_row + j8 * 8);
-          xl[j8] = *reinterpret_cast<const uint4*>(xl_row + j8 * 8);
+          xh[j8] = *reinterpret_cast<const uint4*>(xh_row + c_begin + j8 * 8);
+          xl[j8] = *reinterpret_cast<const uint4*>(xl_row + c_begin + j8 * 8);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
           tmem_ld32(lane_base + c0, v);
           tmem_ld_wait();
@@ -597,16 +617,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             for (int e = 0; e < 8; ++e)
               x[j8 * 8 + e] = fmaf(__uint_as_float(v[j8 * 8 + e]), kProdInv, bb[e]) + join_f32(hh[e], hl[e]);
           }
-          if (c0 + 32 < BN) {
+          if (c0 + 32 < c_end) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               xh[j8] = *reinterpret_cast<const uint4*>(xh_row + c0 + 32 + j8 * 8);
               xl[j8] = *reinterpret_cast<const uint4*>(xl_row + c0 + 32 + j8 * 8);
             }
           }
-          uint8_t* sh = staging + (chunk_ctr & 1) * 8192;
-          uint8_t* sl = staging + kStagingBytes + (chunk_ctr & 1) * 8192;
-          if (leader) tma_store_wait_read<1>();
+          uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
+          uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
+          stage_wait();
           epi_bar();
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
@@ -654,7 +674,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           eps_m = 1e-6f / (float)max(p.L.seg_valid(src), 1);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 64) {
           uint32_t v0[32], v1[32];
           tmem_ld32(lane_base + c0, v0);
           tmem_ld32(lane_base + c0 + 32, v1);
@@ -698,9 +718,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           // store of one sub-chunk drains while the next is being written (same 32 KB of staging as the fp32 path)
 #pragma unroll
           for (int sc = 0; sc < 2; ++sc, ++chunk_ctr) {
-            uint8_t* sh = staging + (chunk_ctr & 1) * 8192;
-            uint8_t* sl = staging + kStagingBytes + (chunk_ctr & 1) * 8192;
-            if (leader) tma_store_wait_read<1>();
+            uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
+            uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
+            stage_wait();
             epi_bar();
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -724,7 +744,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             }
             if (EPI == EPI_KV && col0 < p.elu_cols) {
               // K mean of the linear attention: per-32-row column sums of elu1(K) from the staged planes
-              const int t = threadIdx.x - 128, qq = t >> 5, cc = t & 31;       // thread = (quarter, column)
+              const int t = t_in_grp, qq = t >> 5, cc = t & 31;                // thread = (quarter, column)
               float s0 = 0.f;
 #pragma unroll 8
               for (int i = 0; i < 32; ++i) {
@@ -743,7 +763,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         if (TWO && crank != 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tmem_empty_bar[buf]);
       }
-      if (tl && leader && tc < 8) tl[41 + 2 * tc] = clock64();
+      if (tl && threadIdx.x == 128 && tc < 8) tl[41 + 2 * tc] = clock64();
     }
     if (leader) tma_store_wait_all();
   }
@@ -906,7 +926,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kThreads);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
