@@ -101,6 +101,7 @@ struct opb_matcher {
   PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
   DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
   int kv_mode = 0;       // 0 = tcgen05 KV-state kernel, 1 = mma.sync variant (env OPB_KV_MODE)
+  int aconv = 1;         // 1 = A-operand converters inside the GEMM core replace q_scale_split / norm_relu_split (env OPB_ACONV)
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
                          // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
@@ -345,21 +346,25 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, rows_per_partial, m->kvmean.as<float>(),
                                                                              m->kmean.as<float>());
   launched("kv_state_reduce");
-  // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79)
-  q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, pre_act, L, cross, m->kmean.as<float>(),
-                                                                                m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
-  launched("q_scale_split");
+  // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79): a separate pass, or converted on the fly inside (5)
+  const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
+  const bool aconv = fuse1 && m->aconv && !pre_act;
+  if (!aconv) {
+    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, pre_act, L, cross, m->kmean.as<float>(),
+                                                                                  m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
+    launched("q_scale_split");
+  }
   // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
   g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
   launched("g_fold");
   // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
-  const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
   GemmProblem p2{};
   p2.L = L; p2.batch = 1; p2.rows = rows;
   p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
   p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
   p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
   if (fuse1) { p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>(); }   // InstanceNorm partial sums in the epilogue
+  if (aconv) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = 768; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
   if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
   // (6) InstanceNorm statistics per segment (:126)
   if (!fuse1) {
@@ -368,16 +373,19 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   }
   in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
   launched("in_stats_final");
-  norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
-                                                                                  m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-  launched("norm_relu_split");
-  // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64)
+  if (!aconv) {
+    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
+                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
+    launched("norm_relu_split");
+  }
+  // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64); with converters hn = ReLU(InstanceNorm(hid)) is formed inside the GEMM
   GemmProblem p3{};
   p3.L = L; p3.batch = 1; p3.rows = rows;
   p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
   p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
   if (fuse1) {                                       // residual add + re-split in the epilogue, in place
     p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
+    if (aconv) { p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>(); }
     return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
   }
   if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
@@ -541,6 +549,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   auto* m = new opb_matcher();
   m->cfg = *cfg;
   if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
+  if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
   *out = m;
   return OPB_OK;

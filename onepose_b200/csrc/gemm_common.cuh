@@ -49,6 +49,13 @@ struct GemmProblem {
   long long a_batch_k, b_batch_k;   // batched along the reduction dimension: batch z starts at column z*a_batch_k (KV state)
   int mn_major;                     // operands are [K, rows]-shaped row-major tensors (reduction index = tensor ROW): the KV-state
                                     // GEMM  C[256,256] = K_piece^T . V_piece  reads the row-major K/V planes directly (UMMA MN-major)
+  // A-operand conversion inside the tcgen05 core (gemm_tc.cu ACV_*): 1 = A1 = ReLU((a_raw - mu_seg) * rstd_seg)  (K1 columns),
+  // 2 = A2 = elu1(a_raw) / (elu1(a_raw) . kmean_src + eps/m) per head (K2 = 256 columns); a_raw is fp32 [rows, a_raw_ld]
+  int a_conv;
+  const float* a_raw;
+  int a_raw_ld;
+  const float* mu;                  // [S][512]
+  const float* rstd;
   // EPI_SCORE_*: L gives N, M, n_pad, m_pad
   float inv_scale;
   float* rowsum_part;               // [B][n_out/256][n_pad]

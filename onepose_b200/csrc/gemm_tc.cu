@@ -129,6 +129,28 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_r
       "r"(cta_rank)
       : "memory");
 }
+// cluster-scope release/acquire pair for operand tiles written by SIMT warps of EITHER CTA of a pair (A-operand converters)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta_rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -247,6 +269,9 @@ struct TcParams {
   const __half* x_lo;
   float* statpart;       // EPI_F32_STATS / EPI_KV
   int mn_major;
+  // A-operand converters (ACV)
+  const float* mu;       // ACV_NORM_RELU: [S][512]
+  const float* rstd;
   // EPI_SCORE_*
   float inv_scale;
   float* rowsum_part;
@@ -263,14 +288,24 @@ struct Maps {
   CUtensorMap a1h, a1l, a2h, a2l, b1h, b1l, b2h, b2l;   // loads
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128 (SWIZZLE_128B)
   CUtensorMap out_hi, out_lo;                             // store: fp16-split planes, box 32 x 128 (SWIZZLE_64B)
+  CUtensorMap a_raw;                                      // load: fp32 source of a converted A operand, box 32 x 128 (SWIZZLE_128B)
 };
+
+// A-operand conversion: instead of fp16-split planes prepared by a separate kernel, the TMA producer lands the RAW fp32
+// tile (128 rows x 64 columns = exactly the 32 KB of the stage's A_hi + A_lo planes) and four converter warps rewrite it
+// IN PLACE as the (hi, lo) planes the UMMA descriptors expect -- the pointwise op between two GEMMs runs on data that is
+// already on the SM, and its 4 KB/row HBM round trip disappears:
+//   ACV_NORM_RELU  A  = ReLU((hid - mu_seg) * rstd_seg)          mlp.3 reads mlp.0's fp32 output (GATs_SuperGlue.py:126-127)
+//   ACV_QSCALE     A2 = elu1(q) / (elu1(q) . Kmean_src + eps/m)  mlp.0 reads the raw Q projection   (:71,:78-79)
+enum { ACV_NONE = 0, ACV_NORM_RELU = 1, ACV_QSCALE = 2 };
 
 // CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
 // cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
 // B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
-template <int BK_, int CL, bool TWO, int EPI>
+template <int BK_, int CL, bool TWO, int EPI, int ACV = ACV_NONE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
+  static_assert(ACV == ACV_NONE || (TWO && BK_ == 64), "A-operand converters exist for the 2-CTA BK=64 form only");
   using C = Cfg<BK_, TWO>;
   constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -280,13 +315,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* raw_bar = tmem_empty_bar + 2;            // [kStages] raw fp32 A tile has landed (ACV)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(raw_bar + kMaxStages);
 
   // Epilogue groups: the TMEM -> registers -> staging -> TMA-store chain of one 32-column chunk is a serial latency chain
   // (tcgen05.ld, two named barriers, proxy fence), so ONE group of 4 warps drains a 128 x 256 tile in ~8.5k cycles no matter
   // how little it computes.  Two groups (each: 4 warps = the 4 TMEM lane quarters) split the tile's columns and overlap
   // their chains.  The score epilogues keep one group (their row accumulators span the whole tile).
-  constexpr int kEpiGroups = (TWO && EPI != EPI_SCORE_SUMS && EPI != EPI_SCORE_CONF) ? 2 : 1;
+  // With A-operand converters, warps 8-11 convert and one group drains the accumulator.
+  constexpr int kEpiGroups = (TWO && ACV == ACV_NONE && EPI != EPI_SCORE_SUMS && EPI != EPI_SCORE_CONF) ? 2 : 1;
   constexpr int kColsPerGroup = BN / kEpiGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb1 = p.K1 / BK, nkb = (p.K1 + p.K2) / BK;
@@ -299,13 +336,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (tl && threadIdx.x == 0) tl[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); }
+    // full: the TMA transaction arrive (+ with converters: one arrive per converter warp of BOTH CTAs, on the leader)
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 9 : 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); mbar_init(&raw_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], (TWO ? 8 : 4) * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a1h); prefetch_tmap(&maps.a1l); prefetch_tmap(&maps.b1h); prefetch_tmap(&maps.b1l);
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
+    if (ACV) prefetch_tmap(&maps.a_raw);
     if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF) prefetch_tmap(&maps.out_f32);
     else if (EPI != EPI_SCORE_SUMS) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
@@ -343,9 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
-          if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
-          else if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);     // leader arms for both CTAs' loads
           const bool first = kb < nkb1;
+          const bool conv = ACV == ACV_NORM_RELU || (ACV == ACV_QSCALE && !first);   // this k-block's A tile comes in raw
+          if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
+          else if (crank == 0) mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);   // leader arms for both CTAs' loads
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
           const int kca = kc + (int)(z * p.a_batch_k), kcb = kc + (int)(z * p.b_batch_k);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
@@ -366,8 +406,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             continue;
           }
           if (TWO) {
-            tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
-            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
+            if (conv) {
+              // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
+              mbar_expect_tx(&raw_bar[s], 2 * kABytes);
+              tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
+              tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
+            } else {
+              tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
+              tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
+            }
             tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kcb, brow);
             tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kcb, brow);
             continue;
@@ -395,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
-          mbar_wait(&full_bar[s], (it / kStages) & 1);
+          if (ACV) mbar_wait_acquire_cluster(&full_bar[s], (it / kStages) & 1);   // converter warps of the peer CTA wrote smem the pair's MMA reads
+          else mbar_wait(&full_bar[s], (it / kStages) & 1);
           if (tl && tc == 0 && kb < 16) tl[20 + kb] = clock64();
           tc_fence_after();
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
@@ -428,6 +476,97 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         if (TWO) tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);   // accumulator halves complete in both CTAs
         else tc_commit(&tmem_full_bar[buf]);                          // accumulator complete
+      }
+    }
+  } else if (ACV != ACV_NONE && warp >= 8) {
+    // ===================== A-operand converters (warps 8-11): raw fp32 tile -> (hi, lo) planes, in place =====================
+    // Warp cw owns rows [32 cw, 32 cw + 32) of the tile: it reads exactly the smem bytes it later overwrites (row r of the raw
+    // boxes and row r of the planes are the same two 128-byte slots), so a __syncwarp between the read and the write phase is
+    // the only ordering needed.  Lane = (row 4i + lane/8, 8-column group c = lane%8): reads raw chunks 2c', 2c'+1 of box c/4,
+    // writes chunk c of both planes -- every shared-memory instruction touches each bank group exactly once per wavefront.
+    const int cw = warp - 8;
+    const int c = lane & 7, rsub = lane >> 3;
+    uint32_t it = 0, raw_phase = 0;
+    for (int u = unit0; u < total_units; u += unit_step) {
+      const int z = u / units_per_batch, rem = u - z * units_per_batch;
+      const int m_tile = (rem / p.n_tiles) * CL + crank;
+      const int row0 = m_tile * BM;
+      const int seg = p.L.seg_of_row(row0);
+      int src = 0;
+      float eps_m = 0.f;
+      if (ACV == ACV_QSCALE) {
+        src = p.L.src_seg(seg, p.cross);
+        eps_m = 1e-6f / (float)max(p.L.seg_valid(src), 1);
+      }
+      (void)z;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        const bool conv = ACV == ACV_NORM_RELU || kb >= nkb1;
+        if (!conv) {
+          // plain TMA k-block: nothing to convert, but the barrier's arrival count is fixed -- arrive once the stage's
+          // previous use has been consumed (so the arrival lands in the right phase)
+          mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_release_cluster(&full_bar[s], 0);
+          continue;
+        }
+        mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
+        raw_phase ^= 1u << s;
+        uint8_t* st = smem + s * kStageBytes;
+        const uint8_t* rawbox = st + (c >> 2) * kABytes;
+        const int kcol = (ACV == ACV_NORM_RELU ? kb : kb - nkb1) * BK + 8 * c;     // first of this lane's 8 source columns
+        float4 ra[8], rb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = cw * 32 + 4 * i + rsub;
+          ra[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3)) ^ (r & 7)) << 4));
+          rb[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3) + 1) ^ (r & 7)) << 4));
+        }
+        float pa[8], pb[8];                // per-column parameters: (mu, rstd) or (Kmean, -)
+        {
+          const float* base_a = ACV == ACV_NORM_RELU ? p.mu + (long long)seg * 512 + kcol : p.kmean + (long long)src * kD + kcol;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(base_a)), a1 = __ldg(reinterpret_cast<const float4*>(base_a) + 1);
+          pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
+          if (ACV == ACV_NORM_RELU) {
+            const float* base_b = p.rstd + (long long)seg * 512 + kcol;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(base_b)), b1 = __ldg(reinterpret_cast<const float4*>(base_b) + 1);
+            pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+          }
+        }
+        __syncwarp();                      // every lane holds its raw values before any lane overwrites them
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = cw * 32 + 4 * i + rsub;
+          float v[8] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w, rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+          if (ACV == ACV_NORM_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf((v[j] - pa[j]) * pb[j], 0.f);
+          } else {
+            // one k-block = one head: the row's normaliser is a dot product over the 8 lanes that share the row
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = elu1(v[j]); dot = fmaf(v[j], pa[j], dot); }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            const float zf = 1.f / (dot + eps_m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= zf;
+          }
+          uint4 oh, ol;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __half h, l;
+            split_f32(v[j], h, l);
+            reinterpret_cast<__half*>(&oh)[j] = h;
+            reinterpret_cast<__half*>(&ol)[j] = l;
+          }
+          *reinterpret_cast<uint4*>(st + stg_off(r, c)) = oh;
+          *reinterpret_cast<uint4*>(st + kABytes + stg_off(r, c)) = ol;
+        }
+        fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_release_cluster(&full_bar[s], 0);
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
@@ -842,10 +981,10 @@ int num_sms() {
   return n;
 }
 
-template <int CL, bool TWO, int EPI>
+template <int CL, bool TWO, int EPI, int ACV = ACV_NONE>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg0, const Maps& mp, const TcParams& tp) {
   static bool attr_done = false;
-  auto* kern = gemm_tc_kernel<64, CL, TWO, EPI>;
+  auto* kern = gemm_tc_kernel<64, CL, TWO, EPI, ACV>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, TWO>::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -874,6 +1013,9 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.epi != EPI_F32 && !TWO) return -1;                       // fused epilogues exist for the 2-CTA form only
   if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM) && p.n_out != BN) return -1;
   if (p.mn_major && (!TWO || p.K2)) return -1;
+  if (p.a_conv && (!TWO || p.mn_major || p.batch != 1 || !p.a_raw)) return -1;
+  if (p.a_conv == ACV_NORM_RELU && (p.epi != EPI_RESID || p.K2 || !p.mu || !p.rstd)) return -1;
+  if (p.a_conv == ACV_QSCALE && (p.epi != EPI_F32_STATS || p.K2 != kD || !p.kmean)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
   const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
   int conf_tma = 0;
@@ -889,12 +1031,17 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     const long long k_rows = (long long)(p.batch - 1) * p.a_batch_k + p.K1;
     ok = make_map(&mp.a1h, p.a1.hi, k_rows, p.rows, p.a1.ld, 64, 64, false) && make_map(&mp.a1l, p.a1.lo, k_rows, p.rows, p.a1.ld, 64, 64, false) &&
          make_map(&mp.b1h, p.b1.hi, k_rows, p.n_out, p.b1.ld, 64, 64, false) && make_map(&mp.b1l, p.b1.lo, k_rows, p.n_out, p.b1.ld, 64, 64, false);
-  } else
-  ok = make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false) &&
-            make_map(&mp.b1h, p.b1.hi, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false);
+  } else {
+    ok = make_map(&mp.b1h, p.b1.hi, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false);
+    if (p.a_conv == ACV_NORM_RELU) { mp.a1h = mp.b1h; mp.a1l = mp.b1l; }     // every A tile comes in raw: the plane maps are never used
+    else ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false);
+  }
+  if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.a_conv == ACV_NORM_RELU ? p.K1 : p.K2, p.a_raw_ld, 32, BM, true);
+  else mp.a_raw = mp.b1h;
   if (ok && p.K2) {
-    ok = make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false) &&
-         make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false);
+    ok = make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false);
+    if (p.a_conv == ACV_QSCALE) { mp.a2h = mp.b2h; mp.a2l = mp.b2l; }
+    else ok = ok && make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false);
   } else if (ok) {
     mp.a2h = mp.a1h; mp.a2l = mp.a1l; mp.b2h = mp.b1h; mp.b2l = mp.b1l;
   }
@@ -921,6 +1068,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   tp.inv_scale = p.inv_scale; tp.rowsum_part = p.rowsum_part; tp.colsum_part = p.colsum_part; tp.inv_rowsum = p.inv_rowsum;
   tp.inv_colsum = p.inv_colsum; tp.conf = p.conf; tp.conf_tma = conf_tma; tp.rowbest = p.rowbest; tp.colbest = p.colbest;
   tp.mn_major = p.mn_major;
+  tp.mu = p.mu; tp.rstd = p.rstd;
   tp.kmean = p.kmean; tp.cross = p.cross; tp.x_hi = p.resid.hi; tp.x_lo = p.resid.lo; tp.statpart = p.statpart;
   const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
   const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
@@ -933,7 +1081,11 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le;
-  if (TWO) {
+  if (TWO && p.a_conv == ACV_NORM_RELU) {
+    le = launch_variant<2, true, EPI_RESID, ACV_NORM_RELU>(cfg, mp, tp);
+  } else if (TWO && p.a_conv == ACV_QSCALE) {
+    le = launch_variant<2, true, EPI_F32_STATS, ACV_QSCALE>(cfg, mp, tp);
+  } else if (TWO) {
     switch (p.epi) {
       case EPI_F32: le = launch_variant<2, true, EPI_F32>(cfg, mp, tp); break;
       case EPI_F32_STATS: le = launch_variant<2, true, EPI_F32_STATS>(cfg, mp, tp); break;
