@@ -50,7 +50,12 @@ struct Cfg {
   static constexpr uint32_t kSBO = 8 * BK_ * 2;                   // bytes between 8-row groups
 };
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 384;                    // warps 0-3: TMA / MMA / TMEM / spare; warps 4-11: two epilogue groups of 4 warps
+// warps 0-3: TMA / MMA / TMEM / spare.  Plain variants: warps 4-11 = two epilogue groups of 4 warps (384 threads).
+// Converter variants (ACV): warps 4-7 = one epilogue group, warps 8-15 = eight A-operand converter warps (512 threads,
+// 128 registers per thread at launch; the converters hand 24 registers each to the epilogue group via setmaxnreg).
+constexpr int threads_of(int acv) { return acv ? 512 : 384; }
+constexpr int kConvWarps = 8;
+constexpr int kConvRegs = 104, kEpiRegsAcv = 176;   // 128 + 176 + 2 x 104 = 512 = 4 warpgroups x 128
 constexpr uint32_t kSpinLimit = 1u << 22;        // bounded waits: trap instead of hanging the GPU
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -211,6 +216,10 @@ __device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[1
       : "r"(taddr)
       : "memory");
 }
+template <uint32_t R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <uint32_t R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_id(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // the 4 warps of one epilogue group
 
@@ -303,7 +312,7 @@ enum { ACV_NONE = 0, ACV_NORM_RELU = 1, ACV_QSCALE = 2 };
 // cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
 // B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
 template <int BK_, int CL, bool TWO, int EPI, int ACV = ACV_NONE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
+__global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
   static_assert(ACV == ACV_NONE || (TWO && BK_ == 64), "A-operand converters exist for the 2-CTA BK=64 form only");
   using C = Cfg<BK_, TWO>;
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     // full: the TMA transaction arrive (+ with converters: one arrive per converter warp of BOTH CTAs, on the leader)
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 9 : 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); mbar_init(&raw_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 1 + 2 * kConvWarps : 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); mbar_init(&raw_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], (TWO ? 8 : 4) * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -479,11 +488,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else if (ACV != ACV_NONE && warp >= 8) {
-    // ===================== A-operand converters (warps 8-11): raw fp32 tile -> (hi, lo) planes, in place =====================
-    // Warp cw owns rows [32 cw, 32 cw + 32) of the tile: it reads exactly the smem bytes it later overwrites (row r of the raw
+    // ===================== A-operand converters (warps 8-15): raw fp32 tile -> (hi, lo) planes, in place =====================
+    // Warp cw owns rows [16 cw, 16 cw + 16) of the tile: it reads exactly the smem bytes it later overwrites (row r of the raw
     // boxes and row r of the planes are the same two 128-byte slots), so a __syncwarp between the read and the write phase is
     // the only ordering needed.  Lane = (row 4i + lane/8, 8-column group c = lane%8): reads raw chunks 2c', 2c'+1 of box c/4,
     // writes chunk c of both planes -- every shared-memory instruction touches each bank group exactly once per wavefront.
+    reg_dec<kConvRegs>();
+    constexpr int kRowIters = BM / kConvWarps / 4;   // 4 rows per shared-memory instruction
     const int cw = warp - 8;
     const int c = lane & 7, rsub = lane >> 3;
     uint32_t it = 0, raw_phase = 0;
@@ -515,10 +526,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         uint8_t* st = smem + s * kStageBytes;
         const uint8_t* rawbox = st + (c >> 2) * kABytes;
         const int kcol = (ACV == ACV_NORM_RELU ? kb : kb - nkb1) * BK + 8 * c;     // first of this lane's 8 source columns
-        float4 ra[8], rb[8];
+        float4 ra[kRowIters], rb[kRowIters];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = cw * 32 + 4 * i + rsub;
+        for (int i = 0; i < kRowIters; ++i) {
+          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
           ra[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3)) ^ (r & 7)) << 4));
           rb[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3) + 1) ^ (r & 7)) << 4));
         }
@@ -535,8 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         __syncwarp();                      // every lane holds its raw values before any lane overwrites them
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = cw * 32 + 4 * i + rsub;
+        for (int i = 0; i < kRowIters; ++i) {
+          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
           float v[8] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w, rb[i].x, rb[i].y, rb[i].z, rb[i].w};
           if (ACV == ACV_NORM_RELU) {
 #pragma unroll
@@ -545,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             // one k-block = one head: the row's normaliser is a dot product over the 8 lanes that share the row
             float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] = elu1(v[j]); dot = fmaf(v[j], pa[j], dot); }
+            for (int j = 0; j < 8; ++j) { v[j] = elu1_fast(v[j]); dot = fmaf(v[j], pa[j], dot); }
             dot += __shfl_xor_sync(0xffffffffu, dot, 1);
             dot += __shfl_xor_sync(0xffffffffu, dot, 2);
             dot += __shfl_xor_sync(0xffffffffu, dot, 4);
@@ -555,11 +566,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           uint4 oh, ol;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __half h, l;
-            split_f32(v[j], h, l);
-            reinterpret_cast<__half*>(&oh)[j] = h;
-            reinterpret_cast<__half*>(&ol)[j] = l;
+          for (int j = 0; j < 4; ++j) {    // same rounding as split_f32, two elements per conversion instruction
+            const float2 sc = make_float2(v[2 * j] * kPre, v[2 * j + 1] * kPre);
+            const __half2 h2 = __float22half2_rn(sc);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
+            reinterpret_cast<__half2*>(&oh)[j] = h2;
+            reinterpret_cast<__half2*>(&ol)[j] = l2;
           }
           *reinterpret_cast<uint4*>(st + stg_off(r, c)) = oh;
           *reinterpret_cast<uint4*>(st + kABytes + stg_off(r, c)) = ol;
@@ -571,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
     // ===================== epilogue: TMEM -> registers -> staging smem -> TMA store =====================
+    if (ACV != ACV_NONE) reg_inc<kEpiRegsAcv>();
     const int grp = (warp - 4) >> 2;                // epilogue group: columns [grp*kColsPerGroup, +kColsPerGroup) of every tile
     const int q = (warp - 4) & 3;                   // TMEM lane quarter == warp_id % 4
     const int r_in_tile = q * 32 + lane;
@@ -1074,7 +1088,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads_of(p.a_conv));
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
