@@ -134,28 +134,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_r
       "r"(cta_rank)
       : "memory");
 }
-// cluster-scope release/acquire pair for operand tiles written by SIMT warps of EITHER CTA of a pair (A-operand converters)
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta_rank) {
-  asm volatile(
-      "{\n\t.reg .b32 remAddr32;\n\t"
-      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(cta_rank)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > kSpinLimit) __trap();
-  }
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -215,6 +193,14 @@ __device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 template <uint32_t R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -451,9 +437,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
-          if (ACV) mbar_wait_acquire_cluster(&full_bar[s], (it / kStages) & 1);   // converter warps of the peer CTA wrote smem the pair's MMA reads
-          else mbar_wait(&full_bar[s], (it / kStages) & 1);
-          if (tl && tc == 0 && kb < 16) tl[20 + kb] = clock64();
+          mbar_wait(&full_bar[s], (it / kStages) & 1);
+          if (tl && tc == 1 && kb < 16) tl[20 + kb] = clock64();
           tc_fence_after();
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
           const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + 2 * kABytes, sb_l = sb_h + kBBytes;
@@ -497,8 +482,14 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     constexpr int kRowIters = BM / kConvWarps / 4;   // 4 rows per shared-memory instruction
     const int cw = warp - 8;
     const int c = lane & 7, rsub = lane >> 3;
-    uint32_t it = 0, raw_phase = 0;
-    for (int u = unit0; u < total_units; u += unit_step) {
+    // proxy fence + plain (remote) arrive on the leader's barrier -- the pattern CUTLASS's 2-SM transform warps use.  A
+    // .release.cluster arrive compiles to MEMBAR.ALL.GPU and costs ~4k cycles per k-block (measured).
+    auto conv_arrive = [crank](uint64_t* bar) {
+      if (TWO && crank != 0) mbar_arrive_remote(bar, 0);
+      else mbar_arrive(bar);
+    };
+    uint32_t it = 0, raw_phase = 0, tidx = 0;
+    for (int u = unit0; u < total_units; u += unit_step, ++tidx) {
       const int z = u / units_per_batch, rem = u - z * units_per_batch;
       const int m_tile = (rem / p.n_tiles) * CL + crank;
       const int row0 = m_tile * BM;
@@ -518,21 +509,12 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           // previous use has been consumed (so the arrival lands in the right phase)
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           __syncwarp();
-          if (lane == 0) mbar_arrive_release_cluster(&full_bar[s], 0);
+          if (lane == 0) conv_arrive(&full_bar[s]);
           continue;
         }
-        mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
-        raw_phase ^= 1u << s;
-        uint8_t* st = smem + s * kStageBytes;
-        const uint8_t* rawbox = st + (c >> 2) * kABytes;
+        const uint32_t st = smem_u32(smem) + s * kStageBytes;
+        const uint32_t rawbox = st + (c >> 2) * kABytes;
         const int kcol = (ACV == ACV_NORM_RELU ? kb : kb - nkb1) * BK + 8 * c;     // first of this lane's 8 source columns
-        float4 ra[kRowIters], rb[kRowIters];
-#pragma unroll
-        for (int i = 0; i < kRowIters; ++i) {
-          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
-          ra[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3)) ^ (r & 7)) << 4));
-          rb[i] = *reinterpret_cast<const float4*>(rawbox + r * 128 + (((2 * (c & 3) + 1) ^ (r & 7)) << 4));
-        }
         float pa[8], pb[8];                // per-column parameters: (mu, rstd) or (Kmean, -)
         {
           const float* base_a = ACV == ACV_NORM_RELU ? p.mu + (long long)seg * 512 + kcol : p.kmean + (long long)src * kD + kcol;
@@ -543,6 +525,16 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(base_b)), b1 = __ldg(reinterpret_cast<const float4*>(base_b) + 1);
             pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
           }
+        }
+        mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
+        raw_phase ^= 1u << s;
+        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb < 8) tl[3 + 2 * kb] = clock64();
+        float4 ra[kRowIters], rb[kRowIters];
+#pragma unroll
+        for (int i = 0; i < kRowIters; ++i) {
+          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
+          ra[i] = lds128(rawbox + r * 128 + (((2 * (c & 3)) ^ (r & 7)) << 4));
+          rb[i] = lds128(rawbox + r * 128 + (((2 * (c & 3) + 1) ^ (r & 7)) << 4));
         }
         __syncwarp();                      // every lane holds its raw values before any lane overwrites them
 #pragma unroll
@@ -574,12 +566,13 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             reinterpret_cast<__half2*>(&oh)[j] = h2;
             reinterpret_cast<__half2*>(&ol)[j] = l2;
           }
-          *reinterpret_cast<uint4*>(st + stg_off(r, c)) = oh;
-          *reinterpret_cast<uint4*>(st + kABytes + stg_off(r, c)) = ol;
+          sts128(st + stg_off(r, c), oh);
+          sts128(st + kABytes + stg_off(r, c), ol);
         }
         fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive_release_cluster(&full_bar[s], 0);
+        if (lane == 0) conv_arrive(&full_bar[s]);
+        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb < 8) tl[4 + 2 * kb] = clock64();
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
