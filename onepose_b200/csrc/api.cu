@@ -101,6 +101,7 @@ struct opb_matcher {
   PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
   DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
   int kv_mode = 0;       // 0 = tcgen05 KV-state kernel, 1 = mma.sync variant (env OPB_KV_MODE)
+  int kv_half = 1;       // 1 = [K | V] leave the QKV GEMM as one fp16 plane and the state is a single tensor-core pass (env OPB_KV_HALF)
   int aconv = 1;         // 1 = A-operand converters inside the GEMM core replace q_scale_split / norm_relu_split (env OPB_ACONV)
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
                          // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
@@ -328,13 +329,20 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p.L = L; p.batch = 1; p.rows = rows;
   p.a1 = x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
   p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
+  // fp16 [K | V] plane + single-pass state (tcgen05 core with its fused epilogues only); Q then lives compactly in c768[rows, 256]
+  const bool kv_half = m->cfg.gemm_backend == 0 && m->fuse >= 1 && m->kv_half && m->kv_mode == 0;
+  const int q_ld = kv_half ? 256 : 768;
+  if (kv_half) { p.epi = EPI_QKV; p.ldc = 256; p.out = Planes{m->kvt.hi.as<__half>(), m->kvt.hi.as<__half>(), 512}; }
   const int pre_act = 0;   // 1: elu+1 on the Q and K columns in the GEMM epilogue -- measured slower (the 4-lane MUFU per SMSP stretches the
                           // epilogue by more than the consumers save), kept as a switch
   if (pre_act) p.elu_cols = 512;
   if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)
   int rows_per_partial = kTileRows;
-  if (m->cfg.gemm_backend == 1) {                 // SIMT cross-check path: plain FFMA kernel
+  if (kv_half) {
+    if (launch_kv_state_h(m->kvt.hi.as<__half>(), L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_h launch failed");
+    rows_per_partial = 256;
+  } else if (m->cfg.gemm_backend == 1) {          // SIMT cross-check path: plain FFMA kernel
     kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
   } else if (m->kv_mode == 1) {                   // warp-level mma.sync variant (kept for comparison)
     kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, pre_act, L, m->kvpart.as<float>());
@@ -350,7 +358,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
   const bool aconv = fuse1 && m->aconv && !pre_act;
   if (!aconv) {
-    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), 768, pre_act, L, cross, m->kmean.as<float>(),
+    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), q_ld, pre_act, L, cross, m->kmean.as<float>(),
                                                                                   m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
     launched("q_scale_split");
   }
@@ -364,7 +372,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
   p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
   if (fuse1) { p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>(); }   // InstanceNorm partial sums in the epilogue
-  if (aconv) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = 768; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
+  if (aconv) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = q_ld; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
   if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
   // (6) InstanceNorm statistics per segment (:126)
   if (!fuse1) {
@@ -550,6 +558,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   m->cfg = *cfg;
   if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
   if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) != 0 ? 1 : 0;
+  if (const char* f = getenv("OPB_KV_HALF")) m->kv_half = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
   *out = m;
   return OPB_OK;

@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     prefetch_tmap(&maps.a1h); prefetch_tmap(&maps.a1l); prefetch_tmap(&maps.b1h); prefetch_tmap(&maps.b1l);
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
     if (ACV) prefetch_tmap(&maps.a_raw);
-    if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF) prefetch_tmap(&maps.out_f32);
-    else if (EPI != EPI_SCORE_SUMS) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
+    if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF || EPI == EPI_QKV) prefetch_tmap(&maps.out_f32);
+    if (EPI != EPI_F32 && EPI != EPI_F32_STATS && EPI != EPI_SCORE_CONF && EPI != EPI_SCORE_SUMS) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
   if (warp == 2) {
     if (TWO) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         seg = p.L.seg_of_row(row0);
         n_valid = p.L.seg_valid(seg) - (row0 - p.L.seg_start(seg));
       }
-      if (EPI == EPI_F32 || EPI == EPI_F32_STATS) {
+      if (EPI == EPI_F32 || EPI == EPI_F32_STATS || (EPI == EPI_QKV && n_tile == 0)) {
         // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk, double-buffered staging
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
@@ -654,6 +654,46 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             }
             float2* dst = reinterpret_cast<float2*>(p.statpart) + ((long long)(out_row0 / 32 + qq) * p.n_out + col0 + cc);
             *dst = make_float2(sum, sq);
+          }
+        }
+      } else if (EPI == EPI_QKV) {
+        // ---- [K | V] tiles of the q,k,v projection -> one fp16 plane (x 2^6), 64 columns per chunk (128-byte staging rows).
+        // elu+1 on K (GATs_SuperGlue.py:71-72); pad rows are zeroed so the state kernel needs no row masks.
+        const bool is_k = n_tile == 1;
+        const bool row_ok = r_in_tile < n_valid;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 64, ++chunk_ctr) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_base + c0, v0);
+          tmem_ld32(lane_base + c0 + 32, v1);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sb = staging + stage_sel(chunk_ctr) * kStagingBytes;
+          stage_wait();
+          epi_bar();
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int jj = j8 * 8 + e;
+              x[e] = fmaf(__uint_as_float(jj < 32 ? v0[jj & 31] : v1[jj & 31]), kProdInv, bb[e]);
+              if (is_k) x[e] = elu1_fast(x[e]);
+              x[e] = row_ok ? x[e] * kPre : 0.f;
+            }
+            uint4 o;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) reinterpret_cast<__half2*>(&o)[e] = __float22half2_rn(make_float2(x[2 * e], x[2 * e + 1]));
+            *reinterpret_cast<uint4*>(sb + stg_off(r_in_tile, j8)) = o;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, sb, col0 - BN, out_row0);
+            tma_store_commit();
           }
         }
       } else if (EPI == EPI_SCORE_SUMS || EPI == EPI_SCORE_CONF) {
@@ -1004,6 +1044,10 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg0, const Maps& mp, const
 
 }  // namespace
 
+bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32) {
+  return make_map(out, ptr, rows, cols, ld, box_cols, box_rows, f32);
+}
+
 static int g_cluster = 0;   // 0 = undecided; 1 = no cluster, 2 = multicast B (1-CTA MMA), 3 = 2-CTA MMA (default)
 
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
@@ -1024,6 +1068,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.a_conv == ACV_NORM_RELU && (p.epi != EPI_RESID || p.K2 || !p.mu || !p.rstd)) return -1;
   if (p.a_conv == ACV_QSCALE && (p.epi != EPI_F32_STATS || p.K2 != kD || !p.kmean)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
+  if (p.epi == EPI_QKV && (p.n_out != 3 * BN || p.batch != 1 || p.ldc % 4 || !p.c || !p.out.hi || !p.bias)) return -1;
   const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
   int conf_tma = 0;
   if (f32_out && (p.ldc % 4 || (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc))) return -1;
@@ -1056,6 +1101,9 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (f32_out) {
     ok = ok && make_map(&mp.out_f32, p.c, out_rows, p.n_out, p.ldc, 32, BM, true);
     mp.out_hi = mp.out_f32; mp.out_lo = mp.out_f32;
+  } else if (p.epi == EPI_QKV) {
+    ok = ok && make_map(&mp.out_f32, p.c, out_rows, BN, p.ldc, 32, BM, true) && make_map(&mp.out_hi, p.out.hi, out_rows, 2 * BN, p.out.ld, 64, BM, false);
+    mp.out_lo = mp.out_hi;
   } else if (score) {
     mp.out_f32 = mp.a1h; mp.out_hi = mp.a1h; mp.out_lo = mp.a1h;
     if (p.epi == EPI_SCORE_CONF && p.conf && p.L.M % 4 == 0) {
@@ -1102,6 +1150,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
       case EPI_SCORE_SUMS: le = launch_variant<2, true, EPI_SCORE_SUMS>(cfg, mp, tp); break;
       case EPI_SCORE_CONF: le = launch_variant<2, true, EPI_SCORE_CONF>(cfg, mp, tp); break;
       case EPI_KV: le = launch_variant<2, true, EPI_KV>(cfg, mp, tp); break;
+      case EPI_QKV: le = launch_variant<2, true, EPI_QKV>(cfg, mp, tp); break;
       default: return -1;
     }
   } else if (CL == 2) {

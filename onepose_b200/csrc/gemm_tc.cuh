@@ -1,5 +1,7 @@
 // tcgen05 / TMA GEMM core (sm_100a) -- declarations.  See gemm_tc.cu.
 #pragma once
+#include <cuda.h>
+
 #include "gemm_common.cuh"
 
 namespace opb {
@@ -7,4 +9,7 @@ namespace opb {
 // scheme.  Returns 0, -1 (bad shape / unsupported combination) or -2 (CUDA error).
 // `timeline` (optional, debug): device buffer [n_ctas][64] of clock64 stamps per CTA.
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline = nullptr);
+// 2-D row-major tensor map [rows, ld] (columns used: `cols`), box = box_cols x box_rows; swizzle follows the box row width
+// (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B).  Cached per (pointer, shape, box, dtype).
+bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32);
 }  // namespace opb

@@ -14,6 +14,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "kv_state_tc.cuh"
 
 namespace opb {
@@ -225,6 +226,174 @@ __global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp16 variant: the QKV GEMM epilogue (EPI_QKV) already wrote  kvh[rows, 512] = fp16(64 * [elu1(K) | V])  (pad rows zero), so
+// the state is ONE tensor-core pass over operands that TMA lands directly in the UMMA MN-major SWIZZLE_128B layout -- no SIMT
+// conversion, half the bytes.  Rounding K and V to fp16 perturbs each product by <= 2^-11 relative with zero mean; the state is
+// a MEAN over the segment's rows, so the perturbation of the mean is ~2^-12/sqrt(rows) -- measured end to end in
+// tools/kv_precision.py (cosine error unchanged at 7e-7 down to 16-row segments).
+//
+// One CTA per 256-row slab, 192 threads, 2 CTAs per SM:
+//   warp 0     TMA producer: 32-row stages = 8 boxes of 64 channels x 32 rows (4 K blocks, 4 V blocks), 3-stage ring
+//   warp 1     TMEM owner + MMA issuer: per stage 2 head pairs x 2 k-steps of 16 rows, M = N = 128, accumulating over the slab
+//   warps 2-5  K column sums from the staged tile (the K mean of the attention normaliser), then the epilogue
+constexpr int kHRows = 32;                                 // rows per stage
+constexpr int kHStages = 3;
+constexpr int kHBlockBytes = kHRows * 128;                 // one 64-channel x 32-row box = 4 KB (LBO between channel blocks)
+constexpr int kHStageBytes = 8 * kHBlockBytes;             // 32 KB
+constexpr int kHSmemBytes = kHStages * kHStageBytes + 1024 + 128;
+
+__device__ __forceinline__ uint64_t make_desc_mn_h(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(kHBlockBytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constant__ CUtensorMap kv_map, Layout L, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kHStages * kHStageBytes);   // [3] stage landed
+  uint64_t* empty_bar = full_bar + kHStages;                                          // [3] stage consumed (MMAs retired + sums read)
+  uint64_t* done_bar = empty_bar + kHStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slab = blockIdx.x;
+  const int row0 = slab * 256;
+  const int seg = L.seg_of_row(row0);
+  const int n_valid = min(256, L.seg_valid(seg) - (row0 - L.seg_start(seg)));
+  float* out = partial + (long long)slab * kHeads * (kDh * kDh + kDh);
+  if (n_valid <= 0) {
+    for (int i = tid; i < kHeads * (kDh * kDh + kDh); i += 192) out[i] = 0.f;
+    return;
+  }
+  const int n_stages = (n_valid + kHRows - 1) / kHRows;    // rows past n_valid inside the last stage are zero (EPI_QKV zeroes pad rows)
+  if (tid == 0) {
+    for (int s = 0; s < kHStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < n_stages; ++s) {
+        const int buf = s % kHStages;
+        if (s >= kHStages) mbar_wait(&empty_bar[buf], ((s / kHStages) - 1) & 1);
+        mbar_expect_tx(&full_bar[buf], kHStageBytes);
+        const uint32_t st = smem_u32(smem) + buf * kHStageBytes;
+#pragma unroll
+        for (int blk = 0; blk < 8; ++blk) tma_load_2d(st + blk * kHBlockBytes, &kv_map, &full_bar[buf], blk * 64, row0 + s * kHRows);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < n_stages; ++s) {
+        const int buf = s % kHStages;
+        mbar_wait(&full_bar[buf], (s / kHStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t kb = smem_u32(smem) + buf * kHStageBytes, vb = kb + 4 * kHBlockBytes;
+#pragma unroll
+        for (int pair = 0; pair < 2; ++pair) {
+          const uint32_t d = tmem_base + pair * 128;
+          const uint32_t po = pair * 2 * kHBlockBytes;
+#pragma unroll
+          for (int k = 0; k < kHRows / 16; ++k)
+            mma(d, make_desc_mn_h(kb + po + k * 2048), make_desc_mn_h(vb + po + k * 2048), (uint32_t)((s | k) != 0));
+        }
+        commit(&empty_bar[buf]);
+        if (s == n_stages - 1) commit(done_bar);
+      }
+    }
+  } else {
+    // ---- K column sums: thread = (8-channel chunk j of the 256 K channels, row group g of 4)
+    const int t = tid - 64;
+    const int j = t & 31, g = t >> 5;
+    float ks[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < n_stages; ++s) {
+      const int buf = s % kHStages;
+      mbar_wait(&full_bar[buf], (s / kHStages) & 1);
+      const uint32_t base = smem_u32(smem) + buf * kHStageBytes + (j >> 3) * kHBlockBytes;
+#pragma unroll
+      for (int i = 0; i < kHRows / 4; ++i) {
+        const int r = g + 4 * i;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + r * 128 + (((j & 7) ^ (r & 7)) << 4)));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          ks[2 * e] += f.x;
+          ks[2 * e + 1] += f.y;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[buf]);
+    }
+    // ---- epilogue: diagonal head blocks of the two accumulators (this warp's TMEM lane quarter = warp % 4)
+    mbar_wait(done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    const int lane_row = quarter * 32 + lane;      // accumulator row = K channel within the head pair
+    const int hl = lane_row >> 6, d = lane_row & 63;
+#pragma unroll 1
+    for (int pair = 0; pair < 2; ++pair) {
+      const int h = pair * 2 + hl;
+      float* o = out + (long long)h * (kDh * kDh + kDh) + d * kDh;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + pair * 128 + hl * 64 + half * 32 + ((uint32_t)(quarter * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(o + half * 32 + q) = make_float4(__uint_as_float(v[q]) * kProdInv, __uint_as_float(v[q + 1]) * kProdInv,
+                                                                      __uint_as_float(v[q + 2]) * kProdInv, __uint_as_float(v[q + 3]) * kProdInv);
+      }
+    }
+    // K sums: combine the 4 row groups through the (now idle) stage memory
+    float* red = reinterpret_cast<float*>(smem);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[g * 256 + j * 8 + e] = ks[e];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+    for (int c = t; c < 256; c += 128)
+      out[(long long)(c >> 6) * (kDh * kDh + kDh) + kDh * kDh + (c & 63)] = (red[c] + red[256 + c] + red[512 + c] + red[768 + c]) * kPreInv;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+  }
+}
+
 }  // namespace
 
 int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, int k_activated, const Layout& L, float* partial, cudaStream_t stream) {
@@ -238,4 +407,19 @@ int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, int k_acti
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+}  // namespace opb
+
+namespace opb {
+int launch_kv_state_h(const __half* kvh, const Layout& L, float* partial, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kv_state_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBytes) != cudaSuccess) return -2;
+    attr_done = true;
+  }
+  CUtensorMap map;
+  if (!make_tensor_map_2d(&map, kvh, L.rows(), 512, 512, 64, kHRows, false)) return -2;
+  const int slabs = L.rows() / 256;
+  kv_state_h_kernel<<<slabs, 192, kHSmemBytes, stream>>>(map, L, partial);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
 }  // namespace opb
