@@ -102,7 +102,11 @@ struct opb_matcher {
   DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
   int kv_mode = 0;       // 0 = tcgen05 KV-state kernel, 1 = mma.sync variant (env OPB_KV_MODE)
   int kv_half = 1;       // 1 = [K | V] leave the QKV GEMM as one fp16 plane and the state is a single tensor-core pass (env OPB_KV_HALF)
-  int aconv = 1;         // 1 = A-operand converters inside the GEMM core replace q_scale_split / norm_relu_split (env OPB_ACONV)
+  int aconv = 1;         // A-operand converters inside the GEMM core (env OPB_ACONV, bit mask): 1 = ReLU(InstanceNorm(.)) inside mlp.3
+                         // (replaces norm_relu_split; default), 2 = Q' scaling inside mlp.0 (replaces q_scale_split; measured no gain:
+                         // mlp.0 has two n-tiles, so every A tile is converted twice)
+  int resid_k = 1;       // 1 = residual as an identity K-block of the mlp.3 GEMM (EPI_BIAS_PLANES), 0 = x re-read in the epilogue (EPI_RESID)
+  PlaneBuf eye;          // [256,256] identity, fp16-split
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
                          // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
   bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
@@ -356,8 +360,8 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   launched("kv_state_reduce");
   // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79): a separate pass, or converted on the fly inside (5)
   const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
-  const bool aconv = fuse1 && m->aconv && !pre_act;
-  if (!aconv) {
+  const bool aconv_q = fuse1 && (m->aconv & 2) && !pre_act, aconv_n = fuse1 && (m->aconv & 1);
+  if (!aconv_q) {
     q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), q_ld, pre_act, L, cross, m->kmean.as<float>(),
                                                                                   m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
     launched("q_scale_split");
@@ -372,7 +376,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
   p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
   if (fuse1) { p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>(); }   // InstanceNorm partial sums in the epilogue
-  if (aconv) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = q_ld; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
+  if (aconv_q) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = q_ld; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
   if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
   // (6) InstanceNorm statistics per segment (:126)
   if (!fuse1) {
@@ -381,7 +385,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   }
   in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
   launched("in_stats_final");
-  if (!aconv) {
+  if (!aconv_n) {
     norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
                                                                                     m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
     launched("norm_relu_split");
@@ -393,7 +397,8 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
   if (fuse1) {                                       // residual add + re-split in the epilogue, in place
     p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
-    if (aconv) { p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>(); }
+    if (m->resid_k) { p3.epi = EPI_BIAS_PLANES; p3.a2 = x.c(kD); p3.K2 = kD; p3.b2 = m->eye.c(kD); }   // x_new = [hn | x].[W1 | I]^T + b
+    if (aconv_n) { p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>(); }
     return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
   }
   if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
@@ -557,7 +562,8 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   auto* m = new opb_matcher();
   m->cfg = *cfg;
   if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
-  if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) != 0 ? 1 : 0;
+  if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) & 3;
+  if (const char* f = getenv("OPB_RESID_K")) m->resid_k = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_KV_HALF")) m->kv_half = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
   *out = m;
@@ -572,7 +578,7 @@ void opb_destroy(opb_matcher* m) {
                     &m->mu, &m->rstd, &m->score, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
                     &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
   for (auto* b : bufs) b->release();
-  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq, &m->kvt};
+  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq, &m->kvt, &m->eye};
   m->kvpieces.release(); m->rowsum_part.release(); m->colsum_part.release(); m->ksum_part.release();
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
@@ -663,6 +669,11 @@ int opb_finalize_weights(opb_matcher* m) {
   auto* bfv = find_w(m, "final_proj.bias", kD);
   if (!Wf || !bfv) return OPB_E_STATE;
   if (int rc = upload_planes(m, m->wf, std::vector<double>(Wf->begin(), Wf->end()))) return rc;
+  {
+    std::vector<double> eye((size_t)kD * kD, 0.0);
+    for (int i = 0; i < kD; ++i) eye[(size_t)i * kD + i] = 1.0;
+    if (int rc = upload_planes(m, m->eye, eye)) return rc;
+  }
   if (int rc = upload_f32(m, m->bf, std::vector<double>(bfv->begin(), bfv->end()))) return rc;
   if (int rc = upload_f32(m, m->wa2, wa2)) return rc;
   if (int rc = upload_f32(m, m->wa3, wa3)) return rc;

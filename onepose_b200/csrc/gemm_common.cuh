@@ -25,6 +25,10 @@ enum GemmEpilogue {
   EPI_SCORE_CONF = 7, // conf = e^2 / (rowsum*colsum) -> conf [B,N,M] (optional) + packed row / column arg-max (atomicMax)
   EPI_KV = 8,         // [K | V] projection -> row-major planes out[rows, 512]; elu+1 on K; pad rows zeroed; per-32-row column
                       // sums of K -> statpart [rows/32][256] (K mean of the linear attention)
+  EPI_BIAS_PLANES = 10,  // out planes = acc + bias.  The residual GEMM of a layer uses it with the residual INSIDE the reduction:
+                      // x_new = [hn | x] . [W1 | I]^T + b  (K2 = 256 identity block; x_hi*64 + x_lo*64 is exact in the fp32 accumulator),
+                      // so the epilogue has no global loads -- every chunk of an epilogue ends in a proxy fence that waits for the
+                      // thread's outstanding loads, which made the load-x-in-the-epilogue form (EPI_RESID) latency-bound
   EPI_QKV = 9,        // q,k,v projection (n_out = 768): columns [0,256) = Q -> fp32 c[rows, ldc]; columns [256,768) = [K | V] ->
                       // out.hi[rows, 512] = fp16(64 * [elu1(K) | V]), pad rows zero -- the single-pass operands of kv_state_h
 };

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           const bool first = kb < nkb1;
-          const bool conv = ACV == ACV_NORM_RELU || (ACV == ACV_QSCALE && !first);   // this k-block's A tile comes in raw
+          const bool conv = ACV == ACV_NORM_RELU ? first : (ACV == ACV_QSCALE && !first);   // this k-block's A tile comes in raw
           if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
           else if (crank == 0) mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);   // leader arms for both CTAs' loads
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       (void)z;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % kStages;
-        const bool conv = ACV == ACV_NORM_RELU || kb >= nkb1;
+        const bool conv = ACV == ACV_NORM_RELU ? kb < nkb1 : kb >= nkb1;
         if (!conv) {
           // plain TMA k-block: nothing to convert, but the barrier's arrival count is fixed -- arrive once the stage's
           // previous use has been consumed (so the arrival lands in the right phase)
@@ -569,7 +569,9 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           sts128(st + stg_off(r, c), oh);
           sts128(st + kABytes + stg_off(r, c), ol);
         }
+        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb == 3) tl[56] = clock64();
         fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb == 3) tl[57] = clock64();
         __syncwarp();
         if (lane == 0) conv_arrive(&full_bar[s]);
         if (tl && cw == 0 && lane == 0 && tidx == 1 && kb < 8) tl[4 + 2 * kb] = clock64();
@@ -774,60 +776,126 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         } else if (row_ok && rbest) {
           atomicMax(p.rowbest + (long long)z * N + row, rbest);
         }
-      } else if (EPI == EPI_RESID) {
-        // ---- x += delta (reference GATs_SuperGlue.py:59,64), in place on the fp16-split planes, 32 columns per chunk.
-        // The old x values of the NEXT chunk are prefetched while the current chunk is staged and stored.
-        const __half* xh_row = p.x_hi + (long long)(out_row0 + r_in_tile) * kD + n_tile * BN;
-        const __half* xl_row = p.x_lo + (long long)(out_row0 + r_in_tile) * kD + n_tile * BN;
-        uint4 xh[4], xl[4];
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          xh[j8] = *reinterpret_cast<const uint4*>(xh_row + c_begin + j8 * 8);
-          xl[j8] = *reinterpret_cast<const uint4*>(xl_row + c_begin + j8 * 8);
-        }
+      } else if (EPI == EPI_BIAS_PLANES) {
+        // ---- out planes = acc + bias, 32 columns per chunk (the residual already sits in the accumulator: identity K-block)
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
           tmem_ld32(lane_base + c0, v);
           tmem_ld_wait();
           const int col0 = n_tile * BN + c0;
-          float x[32];
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const __half* hh = reinterpret_cast<const __half*>(&xh[j8]);
-            const __half* hl = reinterpret_cast<const __half*>(&xl[j8]);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              x[j8 * 8 + e] = fmaf(__uint_as_float(v[j8 * 8 + e]), kProdInv, bb[e]) + join_f32(hh[e], hl[e]);
-          }
-          if (c0 + 32 < c_end) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              xh[j8] = *reinterpret_cast<const uint4*>(xh_row + c0 + 32 + j8 * 8);
-              xl[j8] = *reinterpret_cast<const uint4*>(xl_row + c0 + 32 + j8 * 8);
-            }
-          }
           uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
           uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
           stage_wait();
           epi_bar();
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 oh, ol;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {    // same rounding as split_f32, two elements per conversion instruction
+              const float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kProdInv, bb[2 * e]) * kPre,
+                                            fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kProdInv, bb[2 * e + 1]) * kPre);
+              const __half2 h2 = __float22half2_rn(sc);
+              const float2 back = __half22float2(h2);
+              reinterpret_cast<__half2*>(&oh)[e] = h2;
+              reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
+            }
+            *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
+            *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, sh, col0, out_row0);
+            tma_store_2d(&maps.out_lo, sl, col0, out_row0);
+            tma_store_commit();
+          }
+        }
+      } else if (EPI == EPI_RESID) {
+        // ---- x += delta (reference GATs_SuperGlue.py:59,64), in place on the fp16-split planes, 32 columns per chunk.
+        // The old x values come in with COALESCED loads (lane = (row 8i + lane/4, 16-byte piece lane%4): 8 rows x 64 B per
+        // instruction -- a thread-per-row load touches 32 lines per instruction and made this epilogue LSU-bound), are parked
+        // in the staging buffer at their final swizzled position, and each thread then reads / updates / rewrites its own row
+        // there.  A warp only touches the rows it owns, so __syncwarp is the only extra ordering.  Loads for the next chunk are
+        // issued before the current chunk is processed.
+        const int wrow = q * 32;                                    // first tile row of this warp
+        const int lrow = lane >> 2, lpiece = lane & 3;
+        const __half* xh_base = p.x_hi + (long long)(out_row0 + wrow + lrow) * kD + n_tile * BN + lpiece * 8;
+        const __half* xl_base = p.x_lo + (long long)(out_row0 + wrow + lrow) * kD + n_tile * BN + lpiece * 8;
+        if (u + unit_step < total_units) {
+          // This CTA's NEXT tile: pull the x rows into L2 now.  Every chunk ends with a proxy fence (MEMBAR) that waits for
+          // the thread's outstanding loads, so the register prefetch below can never hide more than one chunk of latency --
+          // it has to find its data in L2, not in HBM.
+          const int un = u + unit_step;
+          const int zn = un / units_per_batch, remn = un - zn * units_per_batch;
+          const long long rown = (long long)zn * p.c_batch_rows + ((remn / p.n_tiles) * CL + crank) * BM + r_in_tile;
+          const int coln = (remn % p.n_tiles) * BN + c_begin;
+#pragma unroll
+          for (int cb = 0; cb < kColsPerGroup * 2; cb += 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x_hi + rown * kD + coln) + cb));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x_lo + rown * kD + coln) + cb));
+          }
+        }
+        uint4 xh[4], xl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[i] = *reinterpret_cast<const uint4*>(xh_base + (long long)(8 * i) * kD + c_begin);
+          xl[i] = *reinterpret_cast<const uint4*>(xl_base + (long long)(8 * i) * kD + c_begin);
+        }
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
+          const bool stamp = tl && threadIdx.x == 128 && tc == 1 && c0 == c_begin + 64;
+          if (stamp) tl[58] = clock64();
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
+          uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
+          stage_wait();
+          epi_bar();
+          if (stamp) tl[59] = clock64();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<uint4*>(sh + stg64_off(wrow + 8 * i + lrow, lpiece)) = xh[i];
+            *reinterpret_cast<uint4*>(sl + stg64_off(wrow + 8 * i + lrow, lpiece)) = xl[i];
+          }
+          if (c0 + 32 < c_end) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              xh[i] = *reinterpret_cast<const uint4*>(xh_base + (long long)(8 * i) * kD + c0 + 32);
+              xl[i] = *reinterpret_cast<const uint4*>(xl_base + (long long)(8 * i) * kD + c0 + 32);
+            }
+          }
+          tmem_ld_wait();
+          __syncwarp();
+          if (stamp) tl[60] = clock64();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const uint4 oh_in = *reinterpret_cast<const uint4*>(sh + stg64_off(r_in_tile, j8));
+            const uint4 ol_in = *reinterpret_cast<const uint4*>(sl + stg64_off(r_in_tile, j8));
+            const __half* hh = reinterpret_cast<const __half*>(&oh_in);
+            const __half* hl = reinterpret_cast<const __half*>(&ol_in);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint4 oh, ol;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
+              const float xn = fmaf(__uint_as_float(v[j8 * 8 + e]), kProdInv, bb[e]) + join_f32(hh[e], hl[e]);
               __half h, l;
-              split_f32(x[j8 * 8 + e], h, l);
+              split_f32(xn, h, l);
               reinterpret_cast<__half*>(&oh)[e] = h;
               reinterpret_cast<__half*>(&ol)[e] = l;
             }
             *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
             *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
           }
+          if (stamp) tl[61] = clock64();
           fence_async_smem();
+          if (stamp) tl[62] = clock64();
           epi_bar();
           if (leader) {
             tma_store_2d(&maps.out_hi, sh, col0, out_row0);
@@ -1062,10 +1130,10 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   const bool TWO = g_cluster == 3 && even;
   if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0) return -1;
   if (p.epi != EPI_F32 && !TWO) return -1;                       // fused epilogues exist for the 2-CTA form only
-  if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM) && p.n_out != BN) return -1;
+  if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
   if (p.mn_major && (!TWO || p.K2)) return -1;
   if (p.a_conv && (!TWO || p.mn_major || p.batch != 1 || !p.a_raw)) return -1;
-  if (p.a_conv == ACV_NORM_RELU && (p.epi != EPI_RESID || p.K2 || !p.mu || !p.rstd)) return -1;
+  if (p.a_conv == ACV_NORM_RELU && ((p.epi != EPI_RESID && p.epi != EPI_BIAS_PLANES) || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   if (p.a_conv == ACV_QSCALE && (p.epi != EPI_F32_STATS || p.K2 != kD || !p.kmean)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
   if (p.epi == EPI_QKV && (p.n_out != 3 * BN || p.batch != 1 || p.ldc % 4 || !p.c || !p.out.hi || !p.bias)) return -1;
@@ -1137,7 +1205,8 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le;
   if (TWO && p.a_conv == ACV_NORM_RELU) {
-    le = launch_variant<2, true, EPI_RESID, ACV_NORM_RELU>(cfg, mp, tp);
+    le = p.epi == EPI_RESID ? launch_variant<2, true, EPI_RESID, ACV_NORM_RELU>(cfg, mp, tp)
+                            : launch_variant<2, true, EPI_BIAS_PLANES, ACV_NORM_RELU>(cfg, mp, tp);
   } else if (TWO && p.a_conv == ACV_QSCALE) {
     le = launch_variant<2, true, EPI_F32_STATS, ACV_QSCALE>(cfg, mp, tp);
   } else if (TWO) {
@@ -1151,6 +1220,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
       case EPI_SCORE_CONF: le = launch_variant<2, true, EPI_SCORE_CONF>(cfg, mp, tp); break;
       case EPI_KV: le = launch_variant<2, true, EPI_KV>(cfg, mp, tp); break;
       case EPI_QKV: le = launch_variant<2, true, EPI_QKV>(cfg, mp, tp); break;
+      case EPI_BIAS_PLANES: le = launch_variant<2, true, EPI_BIAS_PLANES>(cfg, mp, tp); break;
       default: return -1;
     }
   } else if (CL == 2) {

@@ -37,6 +37,8 @@ med = lambda v: int(np.median(v))
 print("total cycles per CTA:", med(t[:, 2] - t[:, 0]))
 print("converter (tile 1) raw-ready gaps :", [med(t[:, 3 + 2 * (k + 1)] - t[:, 3 + 2 * k]) for k in range(7)])
 print("converter (tile 1) convert time   :", [med(t[:, 4 + 2 * k] - t[:, 3 + 2 * k]) for k in range(8)])
+print("converter kb=3 (tile 1): raw-ready -> stores issued -> fence done -> arrived:", med(t[:, 56] - t[:, 9]), med(t[:, 57] - t[:, 56]), med(t[:, 10] - t[:, 57]))
+print("RESID epilogue chunk 2 of tile 1: ld+stage_wait+bar | x sts, next ldg, tmem wait | compute+sts | fence :", med(t[:, 59] - t[:, 58]), med(t[:, 60] - t[:, 59]), med(t[:, 61] - t[:, 60]), med(t[:, 62] - t[:, 61]))
 lead = t[::2]
 print("MMA data-ready gaps (tile 1, leader):", [med(lead[:, 21 + k] - lead[:, 20 + k]) for k in range(7)])
 print("MMA ready - converter done (leader, tile 1):", [med(lead[:, 20 + k] - lead[:, 4 + 2 * k]) for k in range(8)])
