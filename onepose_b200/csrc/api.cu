@@ -105,6 +105,8 @@ struct opb_matcher {
   int aconv = 1;         // A-operand converters inside the GEMM core (env OPB_ACONV, bit mask): 1 = ReLU(InstanceNorm(.)) inside mlp.3
                          // (replaces norm_relu_split; default), 2 = Q' scaling inside mlp.0 (replaces q_scale_split; measured no gain:
                          // mlp.0 has two n-tiles, so every A tile is converted twice)
+  int split_q = 1;       // 1 = k,v projection first, then the q projection with the Q' scaling in its epilogue (no fp32 Q round trip, no
+                         // q_scale_split); needs kv_half (env OPB_SPLIT_Q)
   int resid_k = 1;       // 1 = residual as an identity K-block of the mlp.3 GEMM (EPI_BIAS_PLANES), 0 = x re-read in the epilogue (EPI_RESID)
   PlaneBuf eye;          // [256,256] identity, fp16-split
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
@@ -336,11 +338,15 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   // fp16 [K | V] plane + single-pass state (tcgen05 core with its fused epilogues only); Q then lives compactly in c768[rows, 256]
   const bool kv_half = m->cfg.gemm_backend == 0 && m->fuse >= 1 && m->kv_half && m->kv_mode == 0;
   const int q_ld = kv_half ? 256 : 768;
-  if (kv_half) { p.epi = EPI_QKV; p.ldc = 256; p.out = Planes{m->kvt.hi.as<__half>(), m->kvt.hi.as<__half>(), 512}; }
+  const bool split_q = kv_half && m->split_q;
+  if (kv_half) { p.epi = EPI_QKV; p.q_tiles = 1; p.ldc = 256; p.out = Planes{m->kvt.hi.as<__half>(), m->kvt.hi.as<__half>(), 512}; }
+  if (split_q) {           // k,v projection only: rows [256, 768) of the packed weight
+    p.q_tiles = 0; p.n_out = 512; p.b1 = W.wqkv.c(kD, (size_t)256 * kD); p.bias = W.bqkv.as<float>() + 256; p.c = nullptr;
+  }
   const int pre_act = 0;   // 1: elu+1 on the Q and K columns in the GEMM epilogue -- measured slower (the 4-lane MUFU per SMSP stretches the
                           // epilogue by more than the consumers save), kept as a switch
   if (pre_act) p.elu_cols = 512;
-  if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * 768 * kD)) return rc;
+  if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * p.n_out * kD)) return rc;
   // (2) linear-attention state of every segment (:71-78)
   int rows_per_partial = kTileRows;
   if (kv_half) {
@@ -360,8 +366,15 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   launched("kv_state_reduce");
   // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79): a separate pass, or converted on the fly inside (5)
   const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
-  const bool aconv_q = fuse1 && (m->aconv & 2) && !pre_act, aconv_n = fuse1 && (m->aconv & 1);
-  if (!aconv_q) {
+  const bool aconv_q = fuse1 && (m->aconv & 2) && !pre_act && !split_q, aconv_n = fuse1 && (m->aconv & 1);
+  if (split_q) {
+    // q projection; epilogue: elu+1 and the per-head normaliser with the SOURCE segment's K mean -> Q' planes
+    GemmProblem pq{};
+    pq.L = L; pq.batch = 1; pq.rows = rows;
+    pq.a1 = x.c(kD); pq.K1 = kD; pq.b1 = W.wqkv.c(kD); pq.n_out = 256; pq.bias = W.bqkv.as<float>();
+    pq.epi = EPI_QSCALE; pq.kmean = m->kmean.as<float>(); pq.cross = cross; pq.out = m->qp.m(kD);
+    if (int rc = run_gemm(m, pq, st, 2.0 * valid_rows * 256 * kD)) return rc;
+  } else if (!aconv_q) {
     q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), q_ld, pre_act, L, cross, m->kmean.as<float>(),
                                                                                   m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
     launched("q_scale_split");
@@ -563,6 +576,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   m->cfg = *cfg;
   if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
   if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) & 3;
+  if (const char* f = getenv("OPB_SPLIT_Q")) m->split_q = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_RESID_K")) m->resid_k = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_KV_HALF")) m->kv_half = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));

@@ -29,8 +29,9 @@ enum GemmEpilogue {
                       // x_new = [hn | x] . [W1 | I]^T + b  (K2 = 256 identity block; x_hi*64 + x_lo*64 is exact in the fp32 accumulator),
                       // so the epilogue has no global loads -- every chunk of an epilogue ends in a proxy fence that waits for the
                       // thread's outstanding loads, which made the load-x-in-the-epilogue form (EPI_RESID) latency-bound
-  EPI_QKV = 9,        // q,k,v projection (n_out = 768): columns [0,256) = Q -> fp32 c[rows, ldc]; columns [256,768) = [K | V] ->
-                      // out.hi[rows, 512] = fp16(64 * [elu1(K) | V]), pad rows zero -- the single-pass operands of kv_state_h
+  EPI_QKV = 9,        // q,k,v projection (n_out = 768, q_tiles = 1): columns [0,256) = Q -> fp32 c[rows, ldc]; columns [256,768) = [K | V]
+                      // -> out.hi[rows, 512] = fp16(64 * [elu1(K) | V]), pad rows zero -- the single-pass operands of kv_state_h.
+                      // q_tiles = 0: k,v projection only (n_out = 512)
 };
 
 struct GemmProblem {
@@ -57,6 +58,7 @@ struct GemmProblem {
                                     // GEMM  C[256,256] = K_piece^T . V_piece  reads the row-major K/V planes directly (UMMA MN-major)
   // A-operand conversion inside the tcgen05 core (gemm_tc.cu ACV_*): 1 = A1 = ReLU((a_raw - mu_seg) * rstd_seg)  (K1 columns),
   // 2 = A2 = elu1(a_raw) / (elu1(a_raw) . kmean_src + eps/m) per head (K2 = 256 columns); a_raw is fp32 [rows, a_raw_ld]
+  int q_tiles;                      // EPI_QKV: leading 256-column n-tiles that are fp32 Q output (1: q,k,v projection; 0: k,v only)
   int a_conv;
   const float* a_raw;
   int a_raw_ld;

@@ -264,6 +264,7 @@ struct TcParams {
   const __half* x_lo;
   float* statpart;       // EPI_F32_STATS / EPI_KV
   int mn_major;
+  int q_tiles;           // EPI_QKV
   // A-operand converters (ACV)
   const float* mu;       // ACV_NORM_RELU: [S][512]
   const float* rstd;
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         seg = p.L.seg_of_row(row0);
         n_valid = p.L.seg_valid(seg) - (row0 - p.L.seg_start(seg));
       }
-      if (EPI == EPI_F32 || EPI == EPI_F32_STATS || (EPI == EPI_QKV && n_tile == 0)) {
+      if (EPI == EPI_F32 || EPI == EPI_F32_STATS || (EPI == EPI_QKV && n_tile < p.q_tiles)) {
         // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk, double-buffered staging
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
@@ -661,7 +662,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       } else if (EPI == EPI_QKV) {
         // ---- [K | V] tiles of the q,k,v projection -> one fp16 plane (x 2^6), 64 columns per chunk (128-byte staging rows).
         // elu+1 on K (GATs_SuperGlue.py:71-72); pad rows are zeroed so the state kernel needs no row masks.
-        const bool is_k = n_tile == 1;
+        const bool is_k = n_tile == p.q_tiles;
         const bool row_ok = r_in_tile < n_valid;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 64, ++chunk_ctr) {
@@ -694,7 +695,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           fence_async_smem();
           epi_bar();
           if (leader) {
-            tma_store_2d(&maps.out_hi, sb, col0 - BN, out_row0);
+            tma_store_2d(&maps.out_hi, sb, col0 - p.q_tiles * BN, out_row0);
             tma_store_commit();
           }
         }
@@ -942,7 +943,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const float* km = p.kmean + (long long)src * kD + col0;
             float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { x[j] = elu1(x[j]); dot = fmaf(x[j], __ldg(km + j), dot); }
+            for (int j = 0; j < 64; ++j) { x[j] = elu1_fast(x[j]); dot = fmaf(x[j], __ldg(km + j), dot); }
             const float zf = 1.f / (dot + eps_m);
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= zf;
@@ -1136,7 +1137,8 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.a_conv == ACV_NORM_RELU && ((p.epi != EPI_RESID && p.epi != EPI_BIAS_PLANES) || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   if (p.a_conv == ACV_QSCALE && (p.epi != EPI_F32_STATS || p.K2 != kD || !p.kmean)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
-  if (p.epi == EPI_QKV && (p.n_out != 3 * BN || p.batch != 1 || p.ldc % 4 || !p.c || !p.out.hi || !p.bias)) return -1;
+  if (p.epi == EPI_QKV && (p.q_tiles < 0 || p.q_tiles > 1 || p.n_out != (p.q_tiles + 2) * BN || p.batch != 1 || !p.out.hi || !p.bias ||
+                           (p.q_tiles && (p.ldc % 4 || !p.c)))) return -1;
   const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
   int conf_tma = 0;
   if (f32_out && (p.ldc % 4 || (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc))) return -1;
@@ -1170,7 +1172,9 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     ok = ok && make_map(&mp.out_f32, p.c, out_rows, p.n_out, p.ldc, 32, BM, true);
     mp.out_hi = mp.out_f32; mp.out_lo = mp.out_f32;
   } else if (p.epi == EPI_QKV) {
-    ok = ok && make_map(&mp.out_f32, p.c, out_rows, BN, p.ldc, 32, BM, true) && make_map(&mp.out_hi, p.out.hi, out_rows, 2 * BN, p.out.ld, 64, BM, false);
+    ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, 2 * BN, p.out.ld, 64, BM, false);
+    if (p.q_tiles) ok = ok && make_map(&mp.out_f32, p.c, out_rows, BN, p.ldc, 32, BM, true);
+    else mp.out_f32 = mp.out_hi;
     mp.out_lo = mp.out_hi;
   } else if (score) {
     mp.out_f32 = mp.a1h; mp.out_hi = mp.a1h; mp.out_lo = mp.a1h;
@@ -1190,7 +1194,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline;
   tp.inv_scale = p.inv_scale; tp.rowsum_part = p.rowsum_part; tp.colsum_part = p.colsum_part; tp.inv_rowsum = p.inv_rowsum;
   tp.inv_colsum = p.inv_colsum; tp.conf = p.conf; tp.conf_tma = conf_tma; tp.rowbest = p.rowbest; tp.colbest = p.colbest;
-  tp.mn_major = p.mn_major;
+  tp.mn_major = p.mn_major; tp.q_tiles = p.q_tiles;
   tp.mu = p.mu; tp.rstd = p.rstd;
   tp.kmean = p.kmean; tp.cross = p.cross; tp.x_hi = p.resid.hi; tp.x_lo = p.resid.lo; tp.statpart = p.statpart;
   const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
