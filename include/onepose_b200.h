@@ -131,9 +131,11 @@ int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const v
 int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                             float* c, int32_t rows, int32_t n_out, int32_t K, long long* timeline, int32_t dbg, void* stream);
 /* Debug: the mlp.3 GEMM of one segment with the A-operand converters on (x += ReLU((a_raw - mu) * rstd) . B^T + bias);
- * a_raw fp32 [rows,512], B planes [256,512], x planes [rows,256] updated in place, mu/rstd [512]. */
+ * a_raw fp32 [rows,512], B planes [256,512], x planes [rows,256] updated in place, mu/rstd [512]; eye planes [256,256]
+ * (optional): residual as an identity K-block instead of an epilogue re-read. */
 int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo, void* x_hi, void* x_lo, const float* mu,
-                         const float* rstd, const float* bias, int32_t rows, long long* timeline, void* stream);
+                         const float* rstd, const float* bias, const void* eye_hi, const void* eye_lo, int32_t rows,
+                         long long* timeline, void* stream);
 /* fp32 [rows, cols] -> fp16-split planes: hi = fp16(64 x), lo = fp16(64 x - hi). */
 int opb_debug_split(const float* x, void* hi, void* lo, size_t n, void* stream);
 /* Copy an internal activation buffer of the last forward to `out` (device fp32):

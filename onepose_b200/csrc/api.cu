@@ -929,19 +929,26 @@ int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  (void)dbg;
+  static float* dbg_bias = nullptr;
+  if (dbg == 9) {          // k,v projection form: fp16 plane out (EPI_QKV, q_tiles = 0); `c` is reused as the fp16 output buffer
+    if (!dbg_bias) { cudaMalloc(&dbg_bias, 1024 * sizeof(float)); cudaMemset(dbg_bias, 0, 1024 * sizeof(float)); }
+    p.epi = EPI_QKV; p.q_tiles = 0; p.bias = dbg_bias; p.out = Planes{(__half*)c, (__half*)c, n_out}; p.c = nullptr;
+  }
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 
 int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo, void* x_hi, void* x_lo, const float* mu, const float* rstd,
-                         const float* bias, int32_t rows, long long* timeline, void* stream) {
+                         const float* bias, const void* eye_hi, const void* eye_lo, int32_t rows, long long* timeline, void* stream) {
   // the mlp.3 problem of one segment: x[rows,256] += ReLU((a_raw - mu) * rstd)[rows,512] . B[256,512]^T + bias, converters on
   GemmProblem p{};
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, 512};
   p.K1 = 512; p.K2 = 0; p.rows = rows; p.n_out = 256; p.batch = 1; p.bias = bias;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
   p.epi = EPI_RESID; p.resid = CPlanes{(const __half*)x_hi, (const __half*)x_lo, kD}; p.out = Planes{(__half*)x_hi, (__half*)x_lo, kD};
+  if (eye_hi) {           // residual as an identity K-block
+    p.epi = EPI_BIAS_PLANES; p.a2 = p.resid; p.K2 = kD; p.b2 = CPlanes{(const __half*)eye_hi, (const __half*)eye_lo, kD};
+  }
   p.a_conv = 1; p.a_raw = a_raw; p.a_raw_ld = 512; p.mu = mu; p.rstd = rstd;
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);

@@ -32,7 +32,7 @@ constexpr int BM = 128, BN = 256;
 constexpr int UMMA_K = 16;
 constexpr int kStagingBytes = 16384;             // one 128-row x 128-B swizzled epilogue buffer
 constexpr int kNumStaging = 2;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 // K-block configuration: BK fp16 per smem row = one swizzle row (64: SWIZZLE_128B, 2 stages of 96 KB;
 // 32: SWIZZLE_64B, 4 stages of 48 KB -- same bytes in flight, finer-grained ring).
 // TWO = 2-CTA UMMA (cta_group::2): each CTA of a pair keeps only HALF of the B tile in its smem and the pair's
@@ -301,7 +301,7 @@ enum { ACV_NONE = 0, ACV_NORM_RELU = 1, ACV_QSCALE = 2 };
 template <int BK_, int CL, bool TWO, int EPI, int ACV = ACV_NONE>
 __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
   static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
-  static_assert(ACV == ACV_NONE || (TWO && BK_ == 64), "A-operand converters exist for the 2-CTA BK=64 form only");
+  static_assert(ACV == ACV_NONE || TWO, "A-operand converters exist for the 2-CTA form only");
   using C = Cfg<BK_, TWO>;
   constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
               mbar_expect_tx(&raw_bar[s], 2 * kABytes);
               tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
-              tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
+              if (BK == 64) tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
             } else {
               tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
               tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
@@ -480,9 +480,15 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     // the only ordering needed.  Lane = (row 4i + lane/8, 8-column group c = lane%8): reads raw chunks 2c', 2c'+1 of box c/4,
     // writes chunk c of both planes -- every shared-memory instruction touches each bank group exactly once per wavefront.
     reg_dec<kConvRegs>();
-    constexpr int kRowIters = BM / kConvWarps / 4;   // 4 rows per shared-memory instruction
+    constexpr int kLPR = BK / 8;                     // lanes per row = 8-column groups per k-block (8 at BK 64, 4 at BK 32)
+    constexpr int kRPI = 32 / kLPR;                  // rows per shared-memory instruction
+    constexpr int kRowIters = BM / kConvWarps / kRPI;
     const int cw = warp - 8;
-    const int c = lane & 7, rsub = lane >> 3;
+    const int c = lane % kLPR, rsub = lane / kLPR;
+    // BK 64: raw box b (32 fp32 columns) and plane b coincide byte for byte, row by row -> warp-local hazard only.
+    // BK 32: the raw tile is one 16 KB box (128-byte rows) and the planes are two 8 KB halves of it (64-byte rows,
+    // SWIZZLE_64B): rows move, so ALL converter warps finish reading before any of them writes (named barrier 3).
+    auto plane_off = [](int r, int cc) { return BK == 64 ? stg_off(r, cc) : stg64_off(r, cc); };
     // proxy fence + plain (remote) arrive on the leader's barrier -- the pattern CUTLASS's 2-SM transform warps use.  A
     // .release.cluster arrive compiles to MEMBAR.ALL.GPU and costs ~4k cycles per k-block (measured).
     auto conv_arrive = [crank](uint64_t* bar) {
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           continue;
         }
         const uint32_t st = smem_u32(smem) + s * kStageBytes;
-        const uint32_t rawbox = st + (c >> 2) * kABytes;
+        const uint32_t rawbox = st + ((2 * c) >> 3) * (BM * 128);
         const int kcol = (ACV == ACV_NORM_RELU ? kb : kb - nkb1) * BK + 8 * c;     // first of this lane's 8 source columns
         float pa[8], pb[8];                // per-column parameters: (mu, rstd) or (Kmean, -)
         {
@@ -525,6 +531,9 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const float* base_b = p.rstd + (long long)seg * 512 + kcol;
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(base_b)), b1 = __ldg(reinterpret_cast<const float4*>(base_b) + 1);
             pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+            // 64 * ReLU((h - mu) * rstd) = max(h * (64 rstd) - 64 mu rstd, 0): one FFMA + one FMNMX per element, pre-scale included
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { pb[j] *= kPre; pa[j] = -pa[j] * pb[j]; }
           }
         }
         mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
@@ -533,18 +542,19 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         float4 ra[kRowIters], rb[kRowIters];
 #pragma unroll
         for (int i = 0; i < kRowIters; ++i) {
-          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
-          ra[i] = lds128(rawbox + r * 128 + (((2 * (c & 3)) ^ (r & 7)) << 4));
-          rb[i] = lds128(rawbox + r * 128 + (((2 * (c & 3) + 1) ^ (r & 7)) << 4));
+          const int r = cw * (BM / kConvWarps) + kRPI * i + rsub;
+          ra[i] = lds128(rawbox + r * 128 + ((((2 * c) & 7) ^ (r & 7)) << 4));
+          rb[i] = lds128(rawbox + r * 128 + ((((2 * c + 1) & 7) ^ (r & 7)) << 4));
         }
-        __syncwarp();                      // every lane holds its raw values before any lane overwrites them
+        if (BK == 64) __syncwarp();        // every lane holds its raw values before any lane overwrites them
+        else asm volatile("bar.sync 3, %0;" ::"n"(kConvWarps * 32) : "memory");
 #pragma unroll
         for (int i = 0; i < kRowIters; ++i) {
-          const int r = cw * (BM / kConvWarps) + 4 * i + rsub;
+          const int r = cw * (BM / kConvWarps) + kRPI * i + rsub;
           float v[8] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w, rb[i].x, rb[i].y, rb[i].z, rb[i].w};
           if (ACV == ACV_NORM_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf((v[j] - pa[j]) * pb[j], 0.f);
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], pb[j], pa[j]), 0.f);     // already x 2^6
           } else {
             // one k-block = one head: the row's normaliser is a dot product over the 8 lanes that share the row
             float dot = 0.f;
@@ -555,20 +565,20 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             dot += __shfl_xor_sync(0xffffffffu, dot, 4);
             const float zf = 1.f / (dot + eps_m);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= zf;
+            for (int j = 0; j < 8; ++j) v[j] *= zf * kPre;
           }
           uint4 oh, ol;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {    // same rounding as split_f32, two elements per conversion instruction
-            const float2 sc = make_float2(v[2 * j] * kPre, v[2 * j + 1] * kPre);
+            const float2 sc = make_float2(v[2 * j], v[2 * j + 1]);
             const __half2 h2 = __float22half2_rn(sc);
             const float2 back = __half22float2(h2);
             const __half2 l2 = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
             reinterpret_cast<__half2*>(&oh)[j] = h2;
             reinterpret_cast<__half2*>(&ol)[j] = l2;
           }
-          sts128(st + stg_off(r, c), oh);
-          sts128(st + kABytes + stg_off(r, c), ol);
+          sts128(st + plane_off(r, c), oh);
+          sts128(st + kABytes + plane_off(r, c), ol);
         }
         if (tl && cw == 0 && lane == 0 && tidx == 1 && kb == 3) tl[56] = clock64();
         fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -666,14 +676,18 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const bool row_ok = r_in_tile < n_valid;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 64, ++chunk_ctr) {
+          const bool stamp = tl && threadIdx.x == 128 && tc == 2 && c0 == c_begin + 64;
+          if (stamp) tl[3] = clock64();
           uint32_t v0[32], v1[32];
           tmem_ld32(lane_base + c0, v0);
           tmem_ld32(lane_base + c0 + 32, v1);
           tmem_ld_wait();
+          if (stamp) tl[4] = clock64();
           const int col0 = n_tile * BN + c0;
           uint8_t* sb = staging + stage_sel(chunk_ctr) * kStagingBytes;
           stage_wait();
           epi_bar();
+          if (stamp) tl[5] = clock64();
 #pragma unroll
           for (int j8 = 0; j8 < 8; ++j8) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
@@ -692,12 +706,14 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             for (int e = 0; e < 4; ++e) reinterpret_cast<__half2*>(&o)[e] = __float22half2_rn(make_float2(x[2 * e], x[2 * e + 1]));
             *reinterpret_cast<uint4*>(sb + stg_off(r_in_tile, j8)) = o;
           }
+          if (stamp) tl[6] = clock64();
           fence_async_smem();
           epi_bar();
           if (leader) {
             tma_store_2d(&maps.out_hi, sb, col0 - p.q_tiles * BN, out_row0);
             tma_store_commit();
           }
+          if (stamp) tl[7] = clock64();
         }
       } else if (EPI == EPI_SCORE_SUMS || EPI == EPI_SCORE_CONF) {
         // ---- dual-softmax tail (reference GATs_SuperGlue.py:217-223).  Unit-norm operands: cos <= 1, so with the fixed
@@ -797,8 +813,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             uint4 oh, ol;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {    // same rounding as split_f32, two elements per conversion instruction
-              const float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kProdInv, bb[2 * e]) * kPre,
-                                            fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kProdInv, bb[2 * e + 1]) * kPre);
+              const float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kPreInv, bb[2 * e] * kPre),
+                                            fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kPreInv, bb[2 * e + 1] * kPre));
               const __half2 h2 = __float22half2_rn(sc);
               const float2 back = __half22float2(h2);
               reinterpret_cast<__half2*>(&oh)[e] = h2;
@@ -1097,17 +1113,17 @@ int num_sms() {
   return n;
 }
 
-template <int CL, bool TWO, int EPI, int ACV = ACV_NONE>
+template <int CL, bool TWO, int EPI, int ACV = ACV_NONE, int BKV = 64>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg0, const Maps& mp, const TcParams& tp) {
   static bool attr_done = false;
-  auto* kern = gemm_tc_kernel<64, CL, TWO, EPI, ACV>;
+  auto* kern = gemm_tc_kernel<BKV, CL, TWO, EPI, ACV>;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, TWO>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BKV, TWO>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = cfg0;
-  cfg.dynamicSmemBytes = Cfg<64, TWO>::kSmemBytes;
+  cfg.dynamicSmemBytes = Cfg<BKV, TWO>::kSmemBytes;
   return cudaLaunchKernelEx(&cfg, kern, mp, tp);
 }
 
@@ -1125,7 +1141,14 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     g_cluster = c ? atoi(c) : 3;
     if (g_cluster < 1 || g_cluster > 3) g_cluster = 3;
   }
-  constexpr int BK = 64;
+  static int g_acv_bk = 0;
+  if (!g_acv_bk) {
+    const char* c = getenv("OPB_ACV_BK");
+    g_acv_bk = (c && atoi(c) == 64) ? 64 : 32;
+  }
+  // converter variants: 32-wide K-blocks, 6 stages -- the raw-tile round trip (TMA flight + conversion + MMA) is a latency chain
+  // per stage, and twice the stages at half the size keep the tensor pipe fed (3 x 64-wide stages were latency-bound)
+  const int BK = (p.a_conv == ACV_NORM_RELU && p.epi == EPI_BIAS_PLANES) ? g_acv_bk : 64;
   const bool even = (p.rows / BM) % 2 == 0;
   const int CL = (g_cluster >= 2 && even) ? 2 : 1;
   const bool TWO = g_cluster == 3 && even;
@@ -1210,6 +1233,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   cudaError_t le;
   if (TWO && p.a_conv == ACV_NORM_RELU) {
     le = p.epi == EPI_RESID ? launch_variant<2, true, EPI_RESID, ACV_NORM_RELU>(cfg, mp, tp)
+         : BK == 32         ? launch_variant<2, true, EPI_BIAS_PLANES, ACV_NORM_RELU, 32>(cfg, mp, tp)
                             : launch_variant<2, true, EPI_BIAS_PLANES, ACV_NORM_RELU>(cfg, mp, tp);
   } else if (TWO && p.a_conv == ACV_QSCALE) {
     le = launch_variant<2, true, EPI_F32_STATS, ACV_QSCALE>(cfg, mp, tp);

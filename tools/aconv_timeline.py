@@ -6,6 +6,7 @@ import numpy as np, torch
 from onepose_b200 import _lib
 lib = _lib.load()
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+resid_k = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 torch.manual_seed(0)
 a = torch.randn(rows, 512, device="cuda")
 w = torch.randn(256, 512, device="cuda") / 512 ** 0.5
@@ -16,6 +17,9 @@ bias = torch.randn(256, device="cuda") * 0.1
 wp = [torch.empty(256, 512, dtype=torch.float16, device="cuda") for _ in range(2)]
 xp = [torch.empty(rows, 256, dtype=torch.float16, device="cuda") for _ in range(2)]
 lib.opb_debug_split(w.data_ptr(), wp[0].data_ptr(), wp[1].data_ptr(), w.numel(), None)
+eye = torch.eye(256, device="cuda")
+ep = [torch.empty(256, 256, dtype=torch.float16, device="cuda") for _ in range(2)]
+lib.opb_debug_split(eye.data_ptr(), ep[0].data_ptr(), ep[1].data_ptr(), eye.numel(), None)
 n_ctas = 148
 tl = torch.zeros(n_ctas, 64, dtype=torch.int64, device="cuda")
 for it in range(3):
@@ -23,7 +27,7 @@ for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = lib.opb_debug_gemm_aconv(a.data_ptr(), wp[0].data_ptr(), wp[1].data_ptr(), xp[0].data_ptr(), xp[1].data_ptr(), mu.data_ptr(), rstd.data_ptr(),
-                                  bias.data_ptr(), rows, tl.data_ptr(), None)
+                                  bias.data_ptr(), ep[0].data_ptr() if resid_k else None, ep[1].data_ptr() if resid_k else None, rows, tl.data_ptr(), None)
     e1.record(); torch.cuda.synchronize()
     assert rc == 0, rc
 ms = e0.elapsed_time(e1)

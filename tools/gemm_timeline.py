@@ -23,9 +23,10 @@ for it in range(3):
     assert rc == 0
 ms = e0.elapsed_time(e1)
 print(f"GEMM {rows}x{n_out}x{K}: {ms*1e3:.1f} us, {2*rows*n_out*K/ms/1e9:.1f} TFLOP/s algorithmic ({6*rows*n_out*K/ms/1e9:.0f} executed), {n_tiles} tiles on {n_ctas} CTAs")
-ref = (a.double() @ b.double().T).float()
 print("dbg variant", dbg)
-print("max rel err vs fp64:", float((c - ref).abs().max() / ref.abs().max()))
+if dbg != 9:
+    ref = (a.double() @ b.double().T).float()
+    print("max rel err vs fp64:", float((c - ref).abs().max() / ref.abs().max()))
 t = tl.cpu().numpy()
 nkb = K // 64
 d = lambda i, j: np.median(t[:, i] - t[:, j])
@@ -34,4 +35,6 @@ print(f"median cycles per CTA: total {d(2,0):.0f} | setup {d(1,0):.0f} | setup->
 print("data-ready gaps (tile 0):", [int(np.median(t[:, 20+k+1]-t[:, 20+k])) for k in range(min(nkb,16)-1)])
 print("per tile: accum-ready interval:", [int(d(40+2*(i+1), 40+2*i)) for i in range(ntl-1)])
 print("per tile: epilogue duration   :", [int(d(41+2*i, 40+2*i)) for i in range(ntl)])
+if dbg == 9:
+    print("EPI_QKV chunk (tile 2, 2nd chunk of group 0): tmem ld+wait | stage_wait+bar | compute+sts | fence+bar+store:", int(d(4,3)), int(d(5,4)), int(d(6,5)), int(d(7,6)))
 print("epilogue chunk phases (tile 1; ld, wait_read+bar, stage+fence+bar, next):", [[int(d(4+4*c,3+4*c)), int(d(5+4*c,4+4*c)), int(d(6+4*c,5+4*c)), int(d(7+4*c,6+4*c)) if c<3 else -1] for c in range(4)])
