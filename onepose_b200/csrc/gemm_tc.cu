@@ -237,8 +237,6 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
 constexpr uint32_t kIdesc2MN = kIdesc2 | (1u << 15) | (1u << 16);                                           // A and B MN-major
 
-// elu(x)+1 on the hardware exponential (ex2.approx, ~2^-22 relative: the order of the fp16 split every consumer applies next)
-__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -741,7 +739,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = row_ok && (col0 + j) < M;
-            const float e = ok ? __expf((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
+            const float e = ok ? exp_fast((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
             if (EPI == EPI_SCORE_SUMS) {
               o[j] = e;
               rs += e;

@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(256) gats_aggregate_frames8(__half* __restrict
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // lanes 0..7 hold the leaf logits
     mx = fmaxf(__shfl_sync(0xffffffffu, mx, 0), e_self);
-    const float p = lane < 8 ? expf(e - mx) : 0.f;
-    const float p_self = include_self ? expf(e_self - mx) : 0.f;
+    const float p = lane < 8 ? exp_fast(e - mx) : 0.f;
+    const float p_self = include_self ? exp_fast(e_self - mx) : 0.f;
     float ps = p;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) gats_aggregate_frames8(__half* __restrict
       float v = acc[j];
       if (!include_self) v = v * 0.5f + h3[j];
       else if (additional) v += h3[j];
-      v = v > 0.f ? v : expm1f(v);  // ELU (GATs.py:69-70)
+      v = v > 0.f ? v : exp_fast(v) - 1.f;  // ELU (GATs.py:69-70); absolute error ~1e-7, the order of the fp16 split below
       __half hh, ll;
       split_f32(v, hh, ll);
       reinterpret_cast<__half*>(&oh[j >> 2])[j & 3] = hh;
@@ -779,7 +779,7 @@ __global__ void score_row_sums(const float* __restrict__ s, Layout L, float inv_
   const int b = (int)(w / L.N), n = (int)(w % L.N);
   const float* row = s + ((long long)b * L.n_pad + n) * L.m_pad;
   float acc = 0.f;
-  for (int m = lane; m < L.M; m += 32) acc += __expf((row[m] - 1.f) * inv_scale);
+  for (int m = lane; m < L.M; m += 32) acc += exp_fast((row[m] - 1.f) * inv_scale);
   acc = warp_sum(acc);
   if (lane == 0) rowsum[b * L.n_pad + n] = 1.f / acc;       // stored as the inverse
 }
@@ -792,7 +792,7 @@ __global__ void score_col_sums(const float* __restrict__ s, Layout L, float inv_
   const float* col = s + (long long)b * L.n_pad * L.m_pad + m;
   float acc = 0.f;
   if (m < L.M)
-    for (int n = threadIdx.y; n < L.N; n += 8) acc += __expf((col[(long long)n * L.m_pad] - 1.f) * inv_scale);
+    for (int n = threadIdx.y; n < L.N; n += 8) acc += exp_fast((col[(long long)n * L.m_pad] - 1.f) * inv_scale);
   part[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && m < L.M) {
@@ -843,7 +843,7 @@ __global__ void conf_argmax_simt(const float* __restrict__ s, Layout L, float in
   for (int n = n0; n < min(n0 + 32, L.N); ++n) {
     float c = 0.f;
     if (mv) {
-      float e = __expf((s[((long long)b * L.n_pad + n) * L.m_pad + m] - 1.f) * inv_scale);
+      float e = exp_fast((s[((long long)b * L.n_pad + n) * L.m_pad + m] - 1.f) * inv_scale);
       c = (e * rowsum[b * L.n_pad + n]) * (e * inv_cs);
       if (conf) conf[((long long)b * L.N + n) * L.M + m] = c;
       unsigned long long pk = pack_arg(c, n);

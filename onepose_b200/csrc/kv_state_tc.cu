@@ -83,8 +83,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-// elu(x)+1 with the hardware exponential (ex2.approx, ~2^-22 relative -- the same order as the fp16 split that follows)
-__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
 
 // byte offset of channel c (0..255), row r (0..31) inside one MN-major SWIZZLE_128B plane of a stage
 __device__ __forceinline__ uint32_t plane_off(int r, int c) {
