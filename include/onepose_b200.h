@@ -130,6 +130,10 @@ int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const v
 /* Same through the tcgen05 core with a per-CTA clock64 timeline (device int64 [n_ctas][64]); tuning aid. */
 int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                             float* c, int32_t rows, int32_t n_out, int32_t K, long long* timeline, int32_t dbg, void* stream);
+/* Debug: the fp16 linear-attention state kernel on a caller-supplied plane kvh [frames*(n_pad+m_pad), 512] (pad rows must be
+ * zero); partial [rows/256][4][64*64+64]. */
+int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, float* partial, void* stream);
+
 /* Debug: the mlp.3 GEMM of one segment with the A-operand converters on (x += ReLU((a_raw - mu) * rstd) . B^T + bias);
  * a_raw fp32 [rows,512], B planes [256,512], x planes [rows,256] updated in place, mu/rstd [512]; eye planes [256,256]
  * (optional): residual as an identity K-block instead of an epilogue re-read. */

@@ -46,6 +46,7 @@ SYMBOLS = {
     "opb_segmented_mean_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "opb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "opb_debug_gemm_timeline": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "opb_debug_kv_state_h": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "opb_debug_gemm_aconv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "opb_debug_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "opb_debug_read": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),

@@ -33,6 +33,8 @@ struct DevBuf {
     cudaError_t e = cudaMalloc(&p, need);
     if (e != cudaSuccess) return e;
     bytes = need;
+    static const int fill = getenv("OPB_WS_FILL") ? atoi(getenv("OPB_WS_FILL")) : -1;   // debug: 0 = zero every buffer, 255 = poison (NaN)
+    if (fill >= 0) e = cudaMemset(p, fill, need);
     if (zero) e = cudaMemset(p, 0, need);
     return e;
   }
@@ -258,7 +260,7 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
 static int run_gats(opb_matcher* m, const Layout& L, XView x, int gi, cudaStream_t st) {
   const long long warps = (long long)L.M * L.B;
   if (warps == 0) return 0;
-  if (m->Lf == 8 && L.B > 1)   // leaves loaded once per point and reused across the frames of the chunk
+  if (m->Lf == 8)   // leaves loaded once per point and reused across the frames of the chunk (any B: one code path, frame-independent results)
     gats_aggregate_frames8<<<(unsigned)(((long long)L.M * ((L.B + kGatsFramesPerWarp - 1) / kGatsFramesPerWarp) * 32 + 255) / 256), 256, 0, st>>>(
         x.hi, x.lo, L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
         m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
@@ -952,6 +954,13 @@ int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo,
   p.a_conv = 1; p.a_raw = a_raw; p.a_raw_ld = 512; p.mu = mu; p.rstd = rstd;
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
+}
+
+int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, float* partial, void* stream) {
+  Layout L;
+  L.B = frames; L.N = n; L.M = m_pts; L.n_pad = (n + kSegPad - 1) / kSegPad * kSegPad; L.m_pad = (m_pts + kSegPad - 1) / kSegPad * kSegPad;
+  L.R = L.n_pad + L.m_pad;
+  return launch_kv_state_h((const __half*)kvh, L, partial, (cudaStream_t)stream) == 0 ? OPB_OK : OPB_E_CUDA;
 }
 
 int opb_debug_split(const float* x, void* hi, void* lo, size_t n, void* stream) {

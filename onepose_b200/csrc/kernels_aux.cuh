@@ -139,8 +139,8 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   mx = fmaxf(mx, e_self);
-  float p = (lane < n_leaf) ? expf(e - mx) : 0.f;
-  float p_self = include_self ? expf(e_self - mx) : 0.f;
+  float p = (lane < n_leaf) ? exp_fast(e - mx) : 0.f;
+  float p_self = include_self ? exp_fast(e_self - mx) : 0.f;
   float denom = warp_sum(p) + p_self;
   float inv = 1.f / denom;
   float acc[8];
@@ -171,7 +171,7 @@ __global__ void gats_aggregate(__half* __restrict__ x_hi, __half* __restrict__ x
     float v = acc[j];
     if (!include_self) v = v * 0.5f + h3[j];
     else if (additional) v += h3[j];
-    v = v > 0.f ? v : expm1f(v);  // ELU (GATs.py:69-70)
+    v = v > 0.f ? v : exp_fast(v) - 1.f;  // ELU (GATs.py:69-70)
     __half h, l;
     split_f32(v, h, l);
     reinterpret_cast<__half*>(&oh[j >> 2])[j & 3] = h;

@@ -350,6 +350,10 @@ __global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constan
           ks[2 * e + 1] += f.y;
         }
       }
+      // The arrive releases the stage to the TMA producer and must not overtake the loads above: ptxas sinks the FADDs that
+      // consume them below the arrive, so nothing in issue order guarantees they have returned.  Without the fence the K sums
+      // picked up rows of the NEXT use of the stage (seen as run-to-run differences of the K mean).
+      __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[buf]);
     }
