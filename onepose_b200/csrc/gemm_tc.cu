@@ -1142,10 +1142,10 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   static int g_acv_bk = 0;
   if (!g_acv_bk) {
     const char* c = getenv("OPB_ACV_BK");
-    g_acv_bk = (c && atoi(c) == 64) ? 64 : 32;
+    g_acv_bk = (c && atoi(c) == 32) ? 32 : 64;
   }
-  // converter variants: 32-wide K-blocks, 6 stages -- the raw-tile round trip (TMA flight + conversion + MMA) is a latency chain
-  // per stage, and twice the stages at half the size keep the tensor pipe fed (3 x 64-wide stages were latency-bound)
+  // converter variants: a 32-wide K-block / 6-stage form exists (OPB_ACV_BK=32; the raw-tile round trip -- TMA flight, conversion,
+  // MMA -- is a latency chain per stage) but measured slightly slower end to end than 64-wide / 3 stages (3274 vs 3365 frames/s)
   const int BK = (p.a_conv == ACV_NORM_RELU && p.epi == EPI_BIAS_PLANES) ? g_acv_bk : 64;
   const bool even = (p.rows / BM) % 2 == 0;
   const int CL = (g_cluster >= 2 && even) ? 2 : 1;
