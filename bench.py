@@ -288,11 +288,11 @@ def main():
     pk = peaks()
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     dom_tflops = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
-    ncu_path = os.path.join(ROOT, "profiles", "r1_v4_ncu_summary_big_launches.json")
+    ncu_path = os.path.join(ROOT, "profiles", "r1_v5_ncu_summary.json")
     traffic = None
     if os.path.exists(ncu_path):                     # DRAM bytes of one launch of that variant from the committed ncu --set full capture
         for k in json.load(open(ncu_path))["launches"]:
-            if "1, 1>" in k["kernel"]:
+            if "gemm_tc_kernel<64, 2, 1, 1, 0>" in k["kernel"] and k["dram_read_MB"] is not None:   # <BK, cluster, 2-CTA, EPI_F32_STATS, no converter>
                 traffic = (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
 
     # ---------------- per-rank records over NCCL (the path's only collective) ----------------
@@ -307,7 +307,7 @@ def main():
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 semantics via fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate" if args.backend != "simt" else "f32 (SIMT cross-check core)",
+            "dtype": "f32 semantics: fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate (linear-attention state: single fp16 pass, mean over rows)" if args.backend != "simt" else "f32 (SIMT cross-check core)",
             "data": "synthetic",
             "config": {"workload": f"synthetic frames of one object, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2] shape)",
                        "frames_per_step": B, "gemm_backend": args.backend,
