@@ -109,6 +109,8 @@ struct opb_matcher {
                          // mlp.0 has two n-tiles, so every A tile is converted twice)
   int split_q = 1;       // 1 = k,v projection first, then the q projection with the Q' scaling in its epilogue (no fp32 Q round trip, no
                          // q_scale_split); needs kv_half (env OPB_SPLIT_Q)
+  int tail_fuse = 0;     // 1 = dual-softmax tail as two score-GEMM epilogues with the default layer pipeline (env OPB_TAIL_FUSE; same code
+                         // as fuse level 2's tail, which the GPU suite covers; not yet re-measured after the epilogue rework)
   int resid_k = 1;       // 1 = residual as an identity K-block of the mlp.3 GEMM (EPI_BIAS_PLANES), 0 = x re-read in the epilogue (EPI_RESID)
   PlaneBuf eye;          // [256,256] identity, fp16-split
   int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
@@ -506,7 +508,7 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     launched("l2_normalize_split");
   }
   const float inv_scale = 1.f / m->cfg.scale_factor;
-  if (m->cfg.gemm_backend == 0 && m->fuse >= 2) {
+  if (m->cfg.gemm_backend == 0 && (m->fuse >= 2 || (m->fuse >= 1 && m->tail_fuse))) {
     // ---- fused tail: two passes of the batched score GEMM, nothing N x M ever read back
     const int n_tiles = L.m_pad / 256, q_groups = L.n_pad / 32;
     GemmProblem ps{};
@@ -579,6 +581,7 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
   if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) & 3;
   if (const char* f = getenv("OPB_SPLIT_Q")) m->split_q = atoi(f) != 0 ? 1 : 0;
+  if (const char* f = getenv("OPB_TAIL_FUSE")) m->tail_fuse = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_RESID_K")) m->resid_k = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_KV_HALF")) m->kv_half = atoi(f) != 0 ? 1 : 0;
   if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
