@@ -23,6 +23,19 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 with no C++/torch types (cgo / ctypes / JNI bind it)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "onepose_b200.h"\nint main(void) { opb_config c; (void)c; return 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_config_struct_matches_header():
     header = open(os.path.join(ROOT, "include", "onepose_b200.h")).read()
     body = re.search(r"typedef struct opb_config \{(.*?)\} opb_config;", header, re.S).group(1)
