@@ -8,13 +8,16 @@
 // computes in fp32 (GATs_SuperGlue.py:191-193) and the contract is 1e-4 abs on conf.
 //
 // Persistent grid (one CTA per SM), static round-robin tile schedule (n-tile fastest so CTAs that
-// share an A row-tile run together).  384 threads:
-//   warp 0    TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B boxes -> 2-stage smem ring
-//   warp 1    MMA issuer     one lane: tcgen05.mma kind::f16, tcgen05.commit -> mbarriers
+// share an A row-tile run together).  Default form: 2-CTA UMMA (cta_group::2, a CTA pair = two adjacent row tiles, each
+// CTA keeps half of the B tile), 384 threads:
+//   warp 0    TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B boxes -> 3-stage smem ring (64 KB per stage)
+//   warp 1    MMA issuer     one lane (leader CTA): tcgen05.mma kind::f16, tcgen05.commit -> mbarriers of both CTAs
 //   warp 2    TMEM owner     512 columns = 2 accumulator buffers x 256 (epilogue of tile i overlaps
 //                            the main loop of tile i+1)
 //   warps 4-11 epilogue      two groups of 4 warps (each group = the 4 TMEM lane quarters) splitting the tile's columns:
 //                            tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
+// Converter variants (ACV_*, 512 threads): warps 4-7 = one epilogue group, warps 8-15 = A-operand converters that turn a raw
+// fp32 tile landed by TMA into the (hi, lo) planes in place (see the ACV enum); setmaxnreg rebalances the registers.
 #include <cuda.h>
 
 #include <cstdlib>
