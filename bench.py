@@ -186,7 +186,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step (batch of one object)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per GNN chunk (0 = library default)")
-    ap.add_argument("--backend", default="tcgen05", choices=["tcgen05", "simt", "tcgen05_unfused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -209,7 +208,7 @@ def main():
     from onepose_b200 import GATsSuperGlue, synthetic
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
-    model = GATsSuperGlue(hp, gemm_backend=args.backend).eval()
+    model = GATsSuperGlue(hp).eval()
     model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()})
     model = model.to(dev)
     if args.chunk:
@@ -307,10 +306,10 @@ def main():
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 semantics: fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate (linear-attention state: single fp16 pass, mean over rows)" if args.backend != "simt" else "f32 (SIMT cross-check core)",
+            "dtype": "f32 semantics: fp16 hi/lo split x3 tcgen05 passes, fp32 accumulate (linear-attention state: single fp16 pass, mean over rows)",
             "data": "synthetic",
             "config": {"workload": f"synthetic frames of one object, N2D={N2D} N3D={N3D} L={NLEAF} D={DIM} (BASELINE configs[2] shape)",
-                       "frames_per_step": B, "gemm_backend": args.backend,
+                       "frames_per_step": B,
                        "l2": "256 MB buffer written between timed iterations (outside the event pair); query batches rotated",
                        "sharding": "one object per rank, no data-path collective"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * DIM * N2D * 4,

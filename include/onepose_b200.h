@@ -41,10 +41,8 @@ typedef struct opb_config {
   float match_threshold;         /* 0.2  (GATs_SuperGlue.py:227)                        */
   int32_t include_self;          /* GATs.py:48                                          */
   int32_t additional;            /* GATs.py:61                                          */
-  int32_t with_linear_transform; /* GATs.py:56 -- only 0 is implemented                */
+  int32_t with_linear_transform; /* GATs.py:56-57,64-65                                 */
   int32_t device;                /* CUDA device ordinal                                 */
-  int32_t gemm_backend;          /* 0 = tcgen05 with fused epilogues (product); tests only: 1 = SIMT fp32 GEMM + unfused
-                                    helper kernels, 2 = tcgen05 GEMM + unfused helper kernels */
 } opb_config;
 
 /* Replaces GATsSuperGlue.__init__ (GATs_SuperGlue.py:145-177). */
@@ -67,76 +65,92 @@ int opb_finalize_weights(opb_matcher* m);
 int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_db,
                    int32_t M, int32_t L, void* stream);
 
+/* Size the chunk workspace for calls of up to `frames` frames of up to N query points each (no allocation on the
+ * hot path beyond a workspace sized with the object).  Optional: opb_forward grows the workspace itself on first use / when a
+ * call exceeds what was reserved (a one-time cudaMalloc + device synchronisation). */
+int opb_reserve_workspace(opb_matcher* m, int32_t frames, int32_t N);
+
 /* Replaces GATsSuperGlue.forward (GATs_SuperGlue.py:179-241) for B query frames of
  * the current object.  desc2d_query: device fp32 [B, 256, N] (channel-first, as in
- * the reference).  Outputs (device): matches0 int64 [B,N], matches1 int64 [B,M],
- * mscores0 fp32 [B,N], mscores1 fp32 [B,M]; conf fp32 [B,N,M] or NULL to skip
- * materialising the confidence matrix.  Asynchronous on `stream`. */
-int opb_forward(opb_matcher* m, const float* desc2d_query, int32_t B, int32_t N,
+ * the reference).  n2d_lengths: device int32 [B] = valid query points of each frame (SuperPoint yields a different count per
+ * frame, src/sfm/extract_features.py:19-24; columns >= n2d_lengths[b] of frame b are ignored) or NULL = N everywhere.
+ * Outputs (device): matches0 int64 [B,N], matches1 int64 [B,M], mscores0 fp32 [B,N], mscores1 fp32 [B,M]; conf fp32 [B,N,M]
+ * or NULL to skip materialising the confidence matrix.  Entries of a frame beyond its length are -1 / 0.
+ * Asynchronous on `stream`; no host synchronisation. */
+int opb_forward(opb_matcher* m, const float* desc2d_query, const int32_t* n2d_lengths, int32_t B, int32_t N,
                 int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                 float* conf, void* stream);
 
-/* Same call with HOST buffers (pinned or pageable): H2D of the query descriptors,
- * forward, D2H of matches/scores; returns after the stream has been synchronised.  The
- * confidence matrix is always materialised on the device (the reference returns it) and copied
- * to conf_host only if that is non-NULL (inference.py:146 discards it).  This is the
- * end-to-end leg bench.py times. */
-int opb_forward_host(opb_matcher* m, const float* desc2d_query_host, int32_t B, int32_t N,
+/* Same call with HOST buffers (pinned or pageable): H2D of the query descriptors (and lengths, may be NULL),
+ * forward, D2H of matches/scores; returns after the stream has been synchronised.  The confidence matrix is
+ * materialised on the device if conf_host is non-NULL (then also copied back) or materialize_conf != 0
+ * (the reference always computes it; inference.py:146 discards it).  This is the end-to-end leg bench.py times. */
+int opb_forward_host(opb_matcher* m, const float* desc2d_query_host, const int32_t* n2d_lengths_host, int32_t B, int32_t N,
                      int64_t* matches0_host, int64_t* matches1_host, float* mscores0_host,
-                     float* mscores1_host, float* conf_host, void* stream);
+                     float* mscores1_host, float* conf_host, int32_t materialize_conf, void* stream);
 
-/* Range guard of the fp16-split operand format: synchronises `stream` and returns OPB_E_RANGE if any opb_forward since the
- * last check produced an activation outside |x| < 1023 (or a NaN); OPB_OK otherwise.  opb_forward_host calls it itself. */
+/* Range guard of the fp16-split operand format (|x| < 1023 per plane element).  A call that produced an activation outside the
+ * range (or a NaN) reports "no match" (-1 / 0) for every point on the device, and the error is delivered to the host lazily:
+ *   opb_poll_range   never blocks: OPB_E_RANGE if a finished earlier call raised the flag, OPB_OK otherwise (also while
+ *                    the last call is still running);
+ *   opb_check_range  waits for the last opb_forward and reports.  opb_forward_host calls it itself.
+ * Reporting clears the flag. */
 int opb_check_range(opb_matcher* m, void* stream);
+int opb_poll_range(opb_matcher* m);
 
 /* Number of kernels opb_forward launched in its last call (bench.py "gpu_launches"). */
 int opb_last_launch_count(const opb_matcher* m);
 
-/* Measurement hook for bench.py: with profiling on, every GEMM launch of opb_forward is
- * bracketed by CUDA events on the launch stream.  opb_get_profile() synchronises and returns the
- * summed GEMM time, the ALGORITHMIC FLOPs those launches performed (2*valid_rows*n_out*K, each
- * logical MMA counted once although it executes as 3 fp16 passes), their count, and the time of the
+/* Measurement hook for bench.py: with profiling on, every launch of opb_forward is followed by a CUDA event on the launch
+ * stream.  opb_get_profile() synchronises and returns the summed GEMM time, the ALGORITHMIC FLOPs those launches performed
+ * (2*valid_rows*n_out*K, each logical MMA counted once although it executes as 3 fp16 passes), their count, and the time of the
  * whole forward (first to last kernel).  Profiling perturbs timing slightly: never on in timed runs. */
 int opb_set_profiling(opb_matcher* m, int32_t enable);
 int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches, double* total_ms);
-/* Same for the launches whose profile name starts with `prefix` ("gemm epi1" = the mlp.0 GEMM, "kv_state", ...). */
+/* Same for the launches whose profile name starts with `prefix` ("gemm epi1 " = the mlp.0 GEMM, "kv_state", ...). */
 int opb_get_profile_entry(opb_matcher* m, const char* prefix, double* ms, double* flops, int32_t* launches);
-
-/* Which element-wise consumers ride in the GEMM epilogues (gemm_backend 0 only): 0 = none, 1 = those that measured
- * faster in-stream on B200 (InstanceNorm partial sums, residual add, L2 normalise; default), 2 = all (K/V planes +
- * tensor-core KV state, Q scaling, dual-softmax tail).  All levels give the same results to fp32 rounding. */
-int opb_set_fuse_level(opb_matcher* m, int32_t level);
 
 /* GNN layers 0 (GATs) and the 3D side of layer 1 (self) depend only on the per-object constants; by default they
  * are evaluated once per opb_forward call and shared by its frames.  enable = 0 evaluates them per frame like the
  * reference does (same results up to fp32 rounding; used by the tests). */
 int opb_set_hoist(opb_matcher* m, int32_t enable);
 
-/* Frames processed together through the GNN (L2-residency knob); 0 = default. */
+/* Frames processed together through the GNN (workspace-size knob); 0 = default (32). */
 int opb_set_chunk_frames(opb_matcher* m, int32_t frames);
 
-/* Offline producer: segmented mean of multi-view descriptors
- * (reference src/sfm/postprocess/feature_process.py:297-305 mean_descriptors, fp64):
+/* ---- adjacent producers: the per-object feature files the path consumes ---- */
+/* mean_descriptors (reference src/sfm/postprocess/feature_process.py:297-305, fp64):
  * desc device f64 [sum(seg_len), D], seg_len device int64 [M] -> out device f64 [M, D]. */
 int opb_segmented_mean_f64(const double* desc, const int64_t* seg_len, int32_t M, int32_t D,
                            double* out, void* stream);
+/* mean_scores (feature_process.py:308-317, fp64): scores device f64 [sum(seg_len)] -> out device f64 [M]
+ * (numpy's pairwise summation order reproduced, bit-identical). */
+int opb_segmented_mean_scores_f64(const double* scores, const int64_t* seg_len, int32_t M, double* out, void* stream);
+/* Column gather of pad_features3d_random / build_features3d_leaves (reference src/utils/data_utils.py:143-205):
+ * desc device fp32 [dim, n_src] (channel-first), scores device fp32 [n_src] (may be NULL), idx device int64 [n_idx] = source
+ * column of each output column (n_src = the all-ones / zero-score dustbin; NULL = identity) -> desc_out [dim, n_out],
+ * scores_out [n_out]; output columns >= n_idx are all-ones / zero padding. */
+int opb_gather_features3d(const float* desc, const float* scores, int32_t dim, int64_t n_src, const int64_t* idx, int64_t n_idx,
+                          float* desc_out, float* scores_out, int64_t n_out, void* stream);
 
-/* ---- test hooks (used by tests/ only; stable but not part of the drop-in surface) ---- */
-/* C[rows, n_out] (fp32, ld = n_out) = A . B^T with fp16-split operands, through the
- * selected GEMM core.  a_hi/a_lo [rows, K], b_hi/b_lo [n_out, K]; rows % 128 == 0,
- * K % 64 == 0, n_out % 128 == 0.  backend as opb_config.gemm_backend. */
+/* ---- test hooks (used by tests/ and tools/ only; stable but not part of the drop-in surface) ---- */
+/* Programmatic dependent launch on (default) / off for every launch of the library (A/B measurements). */
+int opb_debug_set_pdl(int32_t enable);
+/* C[rows, n_out] (fp32, ld = n_out) = A . B^T with fp16-split operands.  a_hi/a_lo [rows, K], b_hi/b_lo [n_out, K];
+ * rows % 256 == 0, K % 64 == 0, n_out % 256 == 0.  backend 0 = the tcgen05 core, 1 = SIMT fp32 FFMA cross-check
+ * (rows, n_out % 128 == 0, K % 16 == 0). */
 int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                    float* c, int32_t rows, int32_t n_out, int32_t K, int32_t backend, void* stream);
 /* Same through the tcgen05 core with a per-CTA clock64 timeline (device int64 [n_ctas][64]); tuning aid. */
 int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
-                            float* c, int32_t rows, int32_t n_out, int32_t K, long long* timeline, int32_t dbg, void* stream);
-/* Debug: the fp16 linear-attention state kernel on a caller-supplied plane kvh [frames*(n_pad+m_pad), 512] (pad rows must be
- * zero); partial [rows/256][4][64*64+64]. */
-int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, float* partial, void* stream);
-
-/* Debug: the mlp.3 GEMM of one segment with the A-operand converters on (x += ReLU((a_raw - mu) * rstd) . B^T + bias);
- * a_raw fp32 [rows,512], B planes [256,512], x planes [rows,256] updated in place, mu/rstd [512]; eye planes [256,256]
- * (optional): residual as an identity K-block instead of an epilogue re-read. */
+                            float* c, int32_t rows, int32_t n_out, int32_t K, long long* timeline, void* stream);
+/* The fp16 linear-attention state kernel on a caller-supplied plane kvh [frames*(n_pad+m_pad), 512] (pad rows must be
+ * zero); slabs_per_group = 0: the library's own choice; *n_groups = number of partial states; partial [n_groups][4][64*64+64]
+ * (NULL: size query only). */
+int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, int32_t slabs_per_group, float* partial,
+                         int32_t* n_groups, void* stream);
+/* The mlp.3 GEMM of one segment with the A-operand converters on: x = [ReLU((a_raw - mu) * rstd) | x] . [B | I]^T + bias;
+ * a_raw fp32 [rows,512], B planes [256,512], x planes [rows,256] updated in place, mu/rstd [512], eye planes [256,256]. */
 int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo, void* x_hi, void* x_lo, const float* mu,
                          const float* rstd, const float* bias, const void* eye_hi, const void* eye_lo, int32_t rows,
                          long long* timeline, void* stream);

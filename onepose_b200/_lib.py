@@ -20,36 +20,41 @@ class OpbConfig(C.Structure):
     _fields_ = [
         ("descriptor_dim", C.c_int32), ("num_heads", C.c_int32), ("scale_factor", C.c_float),
         ("match_threshold", C.c_float), ("include_self", C.c_int32), ("additional", C.c_int32),
-        ("with_linear_transform", C.c_int32), ("device", C.c_int32), ("gemm_backend", C.c_int32),
+        ("with_linear_transform", C.c_int32), ("device", C.c_int32),
     ]
 
 
 # every symbol include/onepose_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
+_I = C.c_int32
 SYMBOLS = {
     "opb_create": (C.c_int, [C.POINTER(OpbConfig), C.POINTER(_P)]),
     "opb_destroy": (None, [_P]),
     "opb_last_error": (C.c_char_p, [_P]),
     "opb_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     "opb_finalize_weights": (C.c_int, [_P]),
-    "opb_set_object": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
-    "opb_forward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
-    "opb_forward_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "opb_set_object": (C.c_int, [_P, _P, _P, _I, _I, _P]),
+    "opb_reserve_workspace": (C.c_int, [_P, _I, _I]),
+    "opb_forward": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "opb_forward_host": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
     "opb_check_range": (C.c_int, [_P, _P]),
+    "opb_poll_range": (C.c_int, [_P]),
     "opb_last_launch_count": (C.c_int, [_P]),
-    "opb_set_chunk_frames": (C.c_int, [_P, C.c_int32]),
-    "opb_set_hoist": (C.c_int, [_P, C.c_int32]),
-    "opb_set_fuse_level": (C.c_int, [_P, C.c_int32]),
-    "opb_set_profiling": (C.c_int, [_P, C.c_int32]),
-    "opb_get_profile_entry": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
-    "opb_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
-    "opb_segmented_mean_f64": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
-    "opb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
-    "opb_debug_gemm_timeline": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
-    "opb_debug_kv_state_h": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
-    "opb_debug_gemm_aconv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
+    "opb_set_chunk_frames": (C.c_int, [_P, _I]),
+    "opb_set_hoist": (C.c_int, [_P, _I]),
+    "opb_set_profiling": (C.c_int, [_P, _I]),
+    "opb_get_profile_entry": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
+    "opb_get_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double)]),
+    "opb_segmented_mean_f64": (C.c_int, [_P, _P, _I, _I, _P, _P]),
+    "opb_segmented_mean_scores_f64": (C.c_int, [_P, _P, _I, _P, _P]),
+    "opb_gather_features3d": (C.c_int, [_P, _P, _I, C.c_int64, _P, C.c_int64, _P, _P, C.c_int64, _P]),
+    "opb_debug_set_pdl": (C.c_int, [_I]),
+    "opb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "opb_debug_gemm_timeline": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "opb_debug_kv_state_h": (C.c_int, [_P, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
+    "opb_debug_gemm_aconv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "opb_debug_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
-    "opb_debug_read": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
+    "opb_debug_read": (C.c_int, [_P, _I, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
 }
 
 _lib = None

@@ -1,5 +1,6 @@
 // C ABI of the B200-native GATsSPG matcher (see include/onepose_b200.h).
 // Host-side state: packed weights, per-object constants, chunk workspace, launch sequence.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,12 +20,17 @@
 namespace opb {
 
 constexpr int kDefaultChunk = 32;   // frames pushed through the GNN together (measured: 4 -> 1340, 8 -> 1650, 16 -> 2390, 32 -> 2550 frames/s)
+constexpr int kQPassFrames = 16;    // granularity of the query-side layer-1 pass when the queries stream in from the host
 
 static thread_local std::string g_create_error;
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(bool on) { g_pdl = on; }
 
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool grew = false;      // set by ensure() when it (re)allocated: the caller orders the fill against its stream
   cudaError_t ensure(size_t need, bool zero = false) {
     if (need <= bytes) return cudaSuccess;
     if (p) cudaFree(p);
@@ -33,8 +39,7 @@ struct DevBuf {
     cudaError_t e = cudaMalloc(&p, need);
     if (e != cudaSuccess) return e;
     bytes = need;
-    static const int fill = getenv("OPB_WS_FILL") ? atoi(getenv("OPB_WS_FILL")) : -1;   // debug: 0 = zero every buffer, 255 = poison (NaN)
-    if (fill >= 0) e = cudaMemset(p, fill, need);
+    grew = true;
     if (zero) e = cudaMemset(p, 0, need);
     return e;
   }
@@ -71,7 +76,7 @@ struct AttnLayerW {       // one AttentionPropagation (reference GATs_SuperGlue.
   PlaneBuf wqkv;          // [768,256]  rows: Q | K | V, head-contiguous output channels
   DevBuf bqkv;            // [768]
   PlaneBuf w0a;           // [512,256]  mlp.0.weight[:, :256]
-  DevBuf w0m;             // fp32 [512,256] = mlp.0.weight[:, 256:] @ merge.weight (head-contiguous inputs)
+  PlaneBuf w0m;           // [512,256]  mlp.0.weight[:, 256:] @ merge.weight (head-contiguous inputs): A operand of the G-fold GEMM
   DevBuf b0f;             // [512] = mlp.0.weight[:,256:] @ merge.bias + mlp.0.bias
   PlaneBuf w1;            // [256,512]  mlp.3.weight
   DevBuf b1;              // [256]
@@ -87,11 +92,14 @@ struct opb_matcher {
   std::map<std::string, std::vector<float>> host_w;
   bool weights_ready = false;
   bool object_ready = false;
+  int num_sms = 148;
   // packed weights
   AttnLayerW attn[8];
   DevBuf wa2, wa3;        // [4][256] each (GATs: W a[:256], W a[256:])
+  PlaneBuf wlin;          // [4][256][256]: W^T of the GATs layers (with_linear_transform only)
   PlaneBuf wf;            // final_proj [256,256]
   DevBuf bf;
+  PlaneBuf eye;           // [256,256] identity, fp16-split (residual as an identity K-block of the mlp.3 GEMM)
   // per-object constants
   int M = 0, Lf = 0, m_pad = 0;
   DevBuf leaves;          // fp32 [M*Lf, 256] point-major
@@ -100,28 +108,19 @@ struct opb_matcher {
   // workspace (chunk)
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
-  PlaneBuf x, qp, hn, pn, g, xo, xq, kvt;
-  DevBuf kvpieces, rowsum_part, colsum_part, ksum_part;
-  int kv_mode = 0;       // 0 = tcgen05 KV-state kernel, 1 = mma.sync variant (env OPB_KV_MODE)
-  int kv_half = 1;       // 1 = [K | V] leave the QKV GEMM as one fp16 plane and the state is a single tensor-core pass (env OPB_KV_HALF)
-  int aconv = 1;         // A-operand converters inside the GEMM core (env OPB_ACONV, bit mask): 1 = ReLU(InstanceNorm(.)) inside mlp.3
-                         // (replaces norm_relu_split; default), 2 = Q' scaling inside mlp.0 (replaces q_scale_split; measured no gain:
-                         // mlp.0 has two n-tiles, so every A tile is converted twice)
-  int split_q = 1;       // 1 = k,v projection first, then the q projection with the Q' scaling in its epilogue (no fp32 Q round trip, no
-                         // q_scale_split); needs kv_half (env OPB_SPLIT_Q)
-  int tail_fuse = 0;     // 1 = dual-softmax tail as two score-GEMM epilogues with the default layer pipeline (env OPB_TAIL_FUSE; same code
-                         // as fuse level 2's tail, which the GPU suite covers; not yet re-measured after the epilogue rework)
-  int resid_k = 1;       // 1 = residual as an identity K-block of the mlp.3 GEMM (EPI_BIAS_PLANES), 0 = x re-read in the epilogue (EPI_RESID)
-  PlaneBuf eye;          // [256,256] identity, fp16-split
-  int fuse = 1;          // 0 = no fused epilogues, 1 = the fused epilogues that measured faster in-stream (stats, residual,
-                         // L2 norm), 2 = everything fused (K/V planes + tensor-core KV state, Q scaling, dual-softmax tail)
-  bool hoist = true;     // evaluate the frame-invariant layers once per call (object_prologue)
-  DevBuf c768, hid, kvpart, kvmean, kmean, statpart, mu, rstd, score, rowsum, colsum, rowbest, colbest;
+  bool hoist = true;      // evaluate the frame-invariant layers once per call (object_prologue)
+  PlaneBuf x, qp, pn, g, xo, xq, bd, lin_a, lin_b;
+  DevBuf kvt;             // fp16 [rows, 512]
+  DevBuf hid, kvpart, kmean, statpart, mu, rstd, rowsum_part, colsum_part, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
+  int* range_host = nullptr;                    // pinned copy of the flag, written at the end of every opb_forward
+  cudaEvent_t range_ev = nullptr;
+  bool range_pending = false;
+  cudaStream_t last_stream = nullptr;
   // host-call staging
-  DevBuf st_q, st_m0, st_m1, st_s0, st_s1, st_conf;
+  DevBuf st_q, st_m0, st_m1, st_s0, st_s1, st_conf, st_len;
   cudaStream_t copy_stream = nullptr;          // opb_forward_host: H2D of chunk i+1 overlaps the compute of chunk i
-  std::vector<cudaEvent_t> h2d_ev;              // one per chunk; consumed by the chunk loop of opb_forward
+  std::vector<cudaEvent_t> h2d_ev;              // one per piece; consumed by the chunk loop of opb_forward
   int h2d_pending = 0;
   Layout last_layout{};
   // profiling (bench.py roofline leg)
@@ -160,12 +159,14 @@ static void split_host(const std::vector<double>& w, std::vector<__half>& hi, st
   for (size_t i = 0; i < w.size(); ++i) split_f32((float)w[i], hi[i], lo[i]);
 }
 
-static int upload_planes(opb_matcher* m, PlaneBuf& dst, const std::vector<double>& w) {
+// weight uploads are synchronous copies on the legacy stream; opb_finalize_weights ends with a device synchronisation so that
+// they are ordered against whatever (non-blocking) stream the caller uses afterwards
+static int upload_planes(opb_matcher* m, PlaneBuf& dst, const std::vector<double>& w, size_t off_elems = 0, size_t total_elems = 0) {
   std::vector<__half> hi, lo;
   split_host(w, hi, lo);
-  CK(m, dst.ensure(w.size()));
-  CK(m, cudaMemcpy(dst.hi.p, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  CK(m, cudaMemcpy(dst.lo.p, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CK(m, dst.ensure(total_elems ? total_elems : w.size()));
+  CK(m, cudaMemcpy(dst.hi.as<__half>() + off_elems, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CK(m, cudaMemcpy(dst.lo.as<__half>() + off_elems, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
   return 0;
 }
 static int upload_f32(opb_matcher* m, DevBuf& dst, const std::vector<double>& w) {
@@ -203,21 +204,27 @@ static void prof_mark(opb_matcher* m, cudaStream_t st, const char* name, double 
   m->ev_name.push_back(name);
 }
 
-// One launch of the selected GEMM core.  `flops` = algorithmic FLOPs.
-static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, double flops) {
-  int rc;
-  if (m->cfg.gemm_backend == 1) rc = launch_gemm_simt(p, st);
-  else rc = launch_gemm_tc(p, st);
+// One launch of the tcgen05 GEMM core.  `flops` = algorithmic FLOPs.
+static int run_gemm(opb_matcher* m, const GemmProblem& p, cudaStream_t st, double flops, const char* what) {
+  const int rc = launch_gemm_tc(p, st);
   if (m->profiling) {
     char tag[96];
-    snprintf(tag, sizeof tag, "gemm epi%d%s n%d k%d", p.epi, p.mn_major ? "mn" : "", p.n_out, p.K1 + p.K2);
+    snprintf(tag, sizeof tag, "gemm epi%d n%d k%d %s", p.epi, p.n_out, p.K1 + p.K2, what);
     prof_mark(m, st, tag, flops);
   }
   m->launches++;
-  if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (rc=%d, backend=%d): %s", rc,
-                           m->cfg.gemm_backend, cudaGetErrorString(cudaGetLastError()));
+  if (rc != 0) return fail(m, rc == -1 ? OPB_E_INVALID : OPB_E_CUDA, "GEMM launch failed (%s, rc=%d): %s", what, rc,
+                           cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
+
+#define LAUNCH(m, st, name, ...)                                                                                    \
+  do {                                                                                                              \
+    cudaError_t _le = launch_k(__VA_ARGS__);                                                                        \
+    if (_le != cudaSuccess) return fail(m, OPB_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_le));    \
+    (m)->launches++;                                                                                                \
+    prof_mark(m, st, name, 0.0);                                                                                    \
+  } while (0)
 
 static int ensure_workspace(opb_matcher* m, int frames, int N) {
   if (frames <= m->ws_frames && N <= m->ws_N) return 0;
@@ -229,30 +236,31 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   const size_t S = 2 * (size_t)frames;
   CK(m, m->x.ensure(rows * kD, true));
   CK(m, m->qp.ensure(rows * kD, true));
-  CK(m, m->hn.ensure(rows * 512, true));
   CK(m, m->pn.ensure(rows * kD, true));
   CK(m, m->g.ensure(S * 512 * kD));
+  CK(m, m->bd.ensure(S * kD * kD, true));          // block-diagonal state operand: off-diagonal blocks stay zero for the buffer's lifetime
   CK(m, m->xo.ensure((size_t)m->m_pad * kD, true));
   CK(m, m->xq.ensure((size_t)frames * n_pad * kD, true));
-  CK(m, m->c768.ensure(rows * 768 * sizeof(float)));
+  CK(m, m->kvt.ensure(rows * 512 * sizeof(__half), true));
   CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
-  CK(m, m->kvpart.ensure(rows / kTileRows * kHeads * kKVPartial * sizeof(float)));
-  CK(m, m->kvmean.ensure(S * kHeads * kDh * kDh * sizeof(float)));
+  CK(m, m->kvpart.ensure(rows / 256 * kHeads * kKVPartial * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
   CK(m, m->statpart.ensure(rows / 32 * 512 * 2 * sizeof(float)));
-  CK(m, m->kvt.ensure(rows * 512, true));
-  CK(m, m->ksum_part.ensure(rows / 32 * 256 * sizeof(float)));
-  CK(m, m->kvpieces.ensure(rows / 256 * 256 * 256 * sizeof(float)));
   CK(m, m->mu.ensure(S * 512 * sizeof(float)));
   CK(m, m->rstd.ensure(S * 512 * sizeof(float)));
-  CK(m, m->score.ensure((size_t)frames * n_pad * m->m_pad * sizeof(float)));
   CK(m, m->rowsum.ensure((size_t)frames * n_pad * sizeof(float)));
-  CK(m, m->rowsum_part.ensure((size_t)frames * (m->m_pad / 256) * n_pad * sizeof(float)));
+  CK(m, m->rowsum_part.ensure((size_t)frames * (m->m_pad / 256) * 2 * n_pad * sizeof(float)));
   CK(m, m->colsum_part.ensure((size_t)frames * (n_pad / 32) * m->m_pad * sizeof(float)));
   CK(m, m->colsum.ensure((size_t)frames * m->m_pad * sizeof(float)));
   CK(m, m->rowbest.ensure((size_t)frames * n_pad * sizeof(unsigned long long)));
   CK(m, m->colbest.ensure((size_t)frames * m->m_pad * sizeof(unsigned long long)));
   CK(m, m->range_flag.ensure(sizeof(int), true));
+  if (m->cfg.with_linear_transform) {
+    CK(m, m->lin_a.ensure((size_t)frames * m->m_pad * kD, true));
+    CK(m, m->lin_b.ensure((size_t)frames * m->m_pad * kD, true));
+  }
+  // (re)allocation fills ran on the legacy stream: order them against the caller's (possibly non-blocking) stream once
+  CK(m, cudaDeviceSynchronize());
   m->ws_frames = frames;
   m->ws_N = N;
   return 0;
@@ -262,166 +270,90 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
 static int run_gats(opb_matcher* m, const Layout& L, XView x, int gi, cudaStream_t st) {
   const long long warps = (long long)L.M * L.B;
   if (warps == 0) return 0;
-  if (m->Lf == 8)   // leaves loaded once per point and reused across the frames of the chunk (any B: one code path, frame-independent results)
-    gats_aggregate_frames8<<<(unsigned)(((long long)L.M * ((L.B + kGatsFramesPerWarp - 1) / kGatsFramesPerWarp) * 32 + 255) / 256), 256, 0, st>>>(
-        x.hi, x.lo, L, m->leaves.as<float>(), m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
-        m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
-  else
-    gats_aggregate<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-        x.hi, x.lo, L, m->leaves.as<float>(), m->Lf, m->s2.as<float>() + (size_t)gi * m->M * m->Lf,
-        m->wa3.as<float>() + gi * kD, m->cfg.include_self, m->cfg.additional, 0.2f);
-  m->launches++;
-  prof_mark(m, st, "gats_aggregate", 0.0);
+  const bool lin = m->cfg.with_linear_transform != 0;
+  GatsOut out{lin ? m->lin_a.hi.as<__half>() : x.hi, lin ? m->lin_a.lo.as<__half>() : x.lo, lin ? 1 : 0};
+  const float* s2 = m->s2.as<float>() + (size_t)gi * m->M * m->Lf;
+  const float* wa3 = m->wa3.as<float>() + gi * kD;
+  if (m->Lf == 8) {   // leaves loaded once per point and reused across 8 frames of the chunk (any B: one code path, frame-independent results)
+    const long long w8 = (long long)L.M * ((L.B + kGatsFramesPerWarp - 1) / kGatsFramesPerWarp);
+    LAUNCH(m, st, "gats_aggregate", gats_aggregate_frames8, dim3((unsigned)((w8 * 32 + 255) / 256)), dim3(256), 0, st, (const __half*)x.hi,
+           (const __half*)x.lo, L, (const float*)m->leaves.as<float>(), s2, wa3, (int)m->cfg.include_self, (int)m->cfg.additional, 0.2f, out);
+  } else {
+    LAUNCH(m, st, "gats_aggregate", gats_aggregate, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, (const __half*)x.hi,
+           (const __half*)x.lo, L, (const float*)m->leaves.as<float>(), m->Lf, s2, wa3, (int)m->cfg.include_self, (int)m->cfg.additional, 0.2f,
+           out);
+  }
+  if (!lin) return 0;
+  // with_linear_transform (GATs.py:56-57,64-65): t = pre . W on the tensor cores over the compact 3D rows, then ELU (+ h3)
+  Layout Lc{};
+  Lc.B = L.B; Lc.N = 0; Lc.M = L.M; Lc.n_pad = 0; Lc.m_pad = L.m_pad; Lc.R = L.m_pad;
+  GemmProblem p{};
+  p.L = Lc; p.batch = 1; p.rows = Lc.rows();
+  p.a1 = m->lin_a.c(kD); p.K1 = kD; p.b1 = m->wlin.c(kD, (size_t)gi * kD * kD); p.n_out = kD;
+  p.epi = EPI_BIAS_PLANES; p.out = m->lin_b.m(kD);
+  if (int rc = run_gemm(m, p, st, 2.0 * L.B * (double)L.M * kD * kD, "gats.W")) return rc;
+  const long long n = (long long)L.B * L.M * 32;
+  LAUNCH(m, st, "gats_lin_finish", gats_lin_finish, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const __half*)m->lin_b.hi.as<__half>(),
+         (const __half*)m->lin_b.lo.as<__half>(), x.hi, x.lo, L, (int)(m->cfg.include_self && m->cfg.additional));
   return 0;
 }
 
 // One AttentionPropagation layer (reference GATs_SuperGlue.py:55-64, :104-113) on every segment of `x`:
-// both sides of all frames in ONE set of launches (the layer's weights are shared by the two sides).
+// both sides of all frames in ONE set of 8 launches (the layer's weights are shared by the two sides).
 static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& W, int cross, cudaStream_t st) {
   const int rows = L.rows();
   const int S = L.segs();
-  const int tiles = rows / kTileRows;
   const double valid_rows = (double)L.B * (L.N + L.M);
-  __half *xh = x.hi, *xl = x.lo;
-  auto launched = [&](const char* name = "aux") { m->launches++; prof_mark(m, st, name, 0.0); };
-  if (m->cfg.gemm_backend == 0 && m->fuse >= 2) {
-    // ---------------- fully fused tcgen05 pipeline ----------------
-    // (1) [K | V] projection; epilogue: elu+1 on K, pad rows zeroed -> fp16-split planes kv[rows, 512], plus the
-    //     per-32-row column sums of K (for the K mean)
-    GemmProblem pk{};
-    pk.L = L; pk.batch = 1; pk.rows = rows;
-    pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
-    pk.bias = W.bqkv.as<float>() + 256; pk.elu_cols = 256;
-    pk.epi = EPI_KV; pk.out = m->kvt.m(512); pk.statpart = m->ksum_part.as<float>();
-    if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD)) return rc;
-    // (2) linear-attention state on the tensor cores (:77): per 256-row piece  K_piece^T V_piece, reading the row-major
-    //     planes as MN-major UMMA operands (reduction index = row)
-    GemmProblem ps{};
-    ps.batch = rows / 256; ps.rows = 256; ps.n_out = 256; ps.K1 = 256; ps.mn_major = 1;
-    ps.a1 = m->kvt.c(512); ps.b1 = m->kvt.c(512, 256);
-    ps.a_batch_k = 256; ps.b_batch_k = 256;
-    ps.c = m->kvpieces.as<float>(); ps.ldc = 256; ps.c_batch_elems = 256 * 256; ps.epi = EPI_F32;
-    if (int rc = run_gemm(m, ps, st, 2.0 * valid_rows * kD * kDh)) return rc;
-    kv_reduce_pieces<<<dim3(S * kHeads, 17), 256, 0, st>>>(m->kvpieces.as<float>(), m->ksum_part.as<float>(), L, m->kvmean.as<float>(),
-                                                          m->kmean.as<float>());
-    launched("kv_reduce_pieces");
-    // (3) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
-    g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
-    launched("g_fold");
-    // (4) q projection; epilogue: elu+1, per-head normaliser with the SOURCE segment's K mean -> Q' planes (:78-79)
-    GemmProblem pq{};
-    pq.L = L; pq.batch = 1; pq.rows = rows;
-    pq.a1 = x.c(kD); pq.K1 = kD; pq.b1 = W.wqkv.c(kD); pq.n_out = 256; pq.bias = W.bqkv.as<float>();
-    pq.epi = EPI_QSCALE; pq.kmean = m->kmean.as<float>(); pq.cross = cross; pq.out = m->qp.m(kD);
-    if (int rc = run_gemm(m, pq, st, 2.0 * valid_rows * 256 * kD)) return rc;
-    // (5) hidden = [x | Q'] . [W0a | G_seg]^T + b; epilogue also emits the InstanceNorm partial sums (:126)
-    GemmProblem p2{};
-    p2.L = L; p2.batch = 1; p2.rows = rows;
-    p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
-    p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
-    p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
-    p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
-    if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
-    in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
-    launched("in_stats_final");
-    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
-                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-    launched("norm_relu_split");
-    // (6) delta = mlp.3(hn); epilogue: x += delta + bias, re-split, in place (:59/:64)
-    GemmProblem p3{};
-    p3.L = L; p3.batch = 1; p3.rows = rows;
-    p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256; p3.bias = W.b1.as<float>();
-    p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
-    return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
-  }
-  // (1) q,k,v projections (GATs_SuperGlue.py:96-99), all three from the segment's own rows
-  GemmProblem p{};
-  p.L = L; p.batch = 1; p.rows = rows;
-  p.a1 = x.c(kD); p.K1 = kD; p.K2 = 0; p.b1 = W.wqkv.c(kD); p.n_out = 768;
-  p.bias = W.bqkv.as<float>(); p.c = m->c768.as<float>(); p.ldc = 768;
-  // fp16 [K | V] plane + single-pass state (tcgen05 core with its fused epilogues only); Q then lives compactly in c768[rows, 256]
-  const bool kv_half = m->cfg.gemm_backend == 0 && m->fuse >= 1 && m->kv_half && m->kv_mode == 0;
-  const int q_ld = kv_half ? 256 : 768;
-  const bool split_q = kv_half && m->split_q;
-  if (kv_half) { p.epi = EPI_QKV; p.q_tiles = 1; p.ldc = 256; p.out = Planes{m->kvt.hi.as<__half>(), m->kvt.hi.as<__half>(), 512}; }
-  if (split_q) {           // k,v projection only: rows [256, 768) of the packed weight
-    p.q_tiles = 0; p.n_out = 512; p.b1 = W.wqkv.c(kD, (size_t)256 * kD); p.bias = W.bqkv.as<float>() + 256; p.c = nullptr;
-  }
-  const int pre_act = 0;   // 1: elu+1 on the Q and K columns in the GEMM epilogue -- measured slower (the 4-lane MUFU per SMSP stretches the
-                          // epilogue by more than the consumers save), kept as a switch
-  if (pre_act) p.elu_cols = 512;
-  if (int rc = run_gemm(m, p, st, 2.0 * valid_rows * p.n_out * kD)) return rc;
-  // (2) linear-attention state of every segment (:71-78)
-  int rows_per_partial = kTileRows;
-  if (kv_half) {
-    if (launch_kv_state_h(m->kvt.hi.as<__half>(), L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_h launch failed");
-    rows_per_partial = 256;
-  } else if (m->cfg.gemm_backend == 1) {          // SIMT cross-check path: plain FFMA kernel
-    kv_state_partial<<<tiles, 256, 0, st>>>(m->c768.as<float>(), 768, 256, 512, 0, L, m->kvpart.as<float>());
-  } else if (m->kv_mode == 1) {                   // warp-level mma.sync variant (kept for comparison)
-    kv_state_partial_mma<<<tiles, 256, kKvSmemBytes, st>>>(m->c768.as<float>(), 768, 256, 512, pre_act, L, m->kvpart.as<float>());
-  } else {                                        // tcgen05: conversion + UMMA in one kernel, one partial per 256-row slab
-    if (launch_kv_state_tc(m->c768.as<float>(), 768, 256, 512, pre_act, L, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_tc launch failed");
-    rows_per_partial = 256;
-  }
-  launched("kv_state_partial");
-  kv_state_reduce<<<dim3(S * kHeads, (kKVPartial + 255) / 256), 256, 0, st>>>(m->kvpart.as<float>(), L, rows_per_partial, m->kvmean.as<float>(),
-                                                                             m->kmean.as<float>());
-  launched("kv_state_reduce");
-  // (3) Q' = elu1(q) * Z with the SOURCE segment's K mean (:78-79): a separate pass, or converted on the fly inside (5)
-  const bool fuse1 = m->cfg.gemm_backend == 0 && m->fuse >= 1;
-  const bool aconv_q = fuse1 && (m->aconv & 2) && !pre_act && !split_q, aconv_n = fuse1 && (m->aconv & 1);
-  if (split_q) {
-    // q projection; epilogue: elu+1 and the per-head normaliser with the SOURCE segment's K mean -> Q' planes
-    GemmProblem pq{};
-    pq.L = L; pq.batch = 1; pq.rows = rows;
-    pq.a1 = x.c(kD); pq.K1 = kD; pq.b1 = W.wqkv.c(kD); pq.n_out = 256; pq.bias = W.bqkv.as<float>();
-    pq.epi = EPI_QSCALE; pq.kmean = m->kmean.as<float>(); pq.cross = cross; pq.out = m->qp.m(kD);
-    if (int rc = run_gemm(m, pq, st, 2.0 * valid_rows * 256 * kD)) return rc;
-  } else if (!aconv_q) {
-    q_scale_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), q_ld, pre_act, L, cross, m->kmean.as<float>(),
-                                                                                  m->qp.hi.as<__half>(), m->qp.lo.as<__half>());
-    launched("q_scale_split");
-  }
-  // (4) dynamic weight G = KVmean_src (x) folded merge/mlp.0 weight
-  g_fold<<<dim3(512 / 64, kHeads, S), 256, 0, st>>>(m->kvmean.as<float>(), W.w0m.as<float>(), L, cross, m->g.hi.as<__half>(), m->g.lo.as<__half>());
-  launched("g_fold");
-  // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122)
+  // (1) k,v projection (:96-99), rows [256, 768) of the packed weight; epilogue: elu+1 on K, pad rows zeroed, ONE fp16 plane
+  //     kvt[rows, 512] = fp16(64 * [elu1(K) | V]) -- the single-pass operands of the state kernel
+  GemmProblem pk{};
+  pk.L = L; pk.batch = 1; pk.rows = rows;
+  pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
+  pk.bias = W.bqkv.as<float>() + 256;
+  pk.epi = EPI_QKV; pk.out = Planes{m->kvt.as<__half>(), m->kvt.as<__half>(), 512};
+  if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD, "kv_proj")) return rc;
+  // (2) linear-attention state of every segment (:71-78): per-row-group partial states on the tensor cores ...
+  const KvGroups G = kv_groups_for(L, m->num_sms);
+  if (launch_kv_state_h(m->kvt.as<__half>(), L, G, m->kvpart.as<float>(), st)) return fail(m, OPB_E_CUDA, "kv_state_h launch failed");
+  m->launches++;
+  prof_mark(m, st, "kv_state_h", 0.0);
+  // ... reduced per segment into Kmean and the block-diagonal operand of the G fold (indexed by DESTINATION segment)
+  LAUNCH(m, st, "kv_state_reduce", kv_state_reduce, dim3(S * kHeads, (kKVPartial + 255) / 256), dim3(256), 0, st, (const float*)m->kvpart.as<float>(), L,
+         G, cross, m->kmean.as<float>(), m->bd.hi.as<__half>(), m->bd.lo.as<__half>());
+  // (3) q projection; epilogue: elu+1 and the per-head normaliser with the SOURCE segment's K mean -> Q' planes (:78-79)
+  GemmProblem pq{};
+  pq.L = L; pq.batch = 1; pq.rows = rows;
+  pq.a1 = x.c(kD); pq.K1 = kD; pq.b1 = W.wqkv.c(kD); pq.n_out = 256; pq.bias = W.bqkv.as<float>();
+  pq.epi = EPI_QSCALE; pq.kmean = m->kmean.as<float>(); pq.cross = cross; pq.out = m->qp.m(kD);
+  if (int rc = run_gemm(m, pq, st, 2.0 * valid_rows * 256 * kD, "q_proj")) return rc;
+  // (4) dynamic weight G[s] = W0m . blockdiag(KVmean_src(s))^T  -- merge and the message half of mlp.0 folded into one
+  //     per-segment [512, 256] weight (4 x 64x64x512 MACs per segment), as a batched tcgen05 GEMM over the segments
+  GemmProblem pg{};
+  pg.batch = S; pg.rows = 512; pg.n_out = kD; pg.K1 = kD;
+  pg.a1 = W.w0m.c(kD); pg.a_batch_rows = 0;
+  pg.b1 = m->bd.c(kD); pg.b_batch_rows = kD;
+  pg.epi = EPI_BIAS_PLANES; pg.out = m->g.m(kD);
+  if (int rc = run_gemm(m, pg, st, 2.0 * S * 512.0 * kD * kDh, "g_fold")) return rc;
+  // (5) hidden = mlp.0([x ; message]) = [x | Q'] . [W0a | G_seg]^T + b   (:101,:113,:122); epilogue also emits the InstanceNorm
+  //     partial sums (:126)
   GemmProblem p2{};
   p2.L = L; p2.batch = 1; p2.rows = rows;
   p2.a1 = x.c(kD); p2.K1 = kD; p2.b1 = W.w0a.c(kD);
   p2.a2 = m->qp.c(kD); p2.K2 = kD; p2.b2 = m->g.c(kD); p2.b2_per_seg = 1;
   p2.n_out = 512; p2.bias = W.b0f.as<float>(); p2.c = m->hid.as<float>(); p2.ldc = 512;
-  if (fuse1) { p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>(); }   // InstanceNorm partial sums in the epilogue
-  if (aconv_q) { p2.a_conv = 2; p2.a_raw = m->c768.as<float>(); p2.a_raw_ld = q_ld; p2.kmean = m->kmean.as<float>(); p2.cross = cross; }
-  if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512)) return rc;
+  p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
+  if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512, "mlp0")) return rc;
   // (6) InstanceNorm statistics per segment (:126)
-  if (!fuse1) {
-    in_stats_partial<<<dim3(tiles, 4), 128, 0, st>>>(m->hid.as<float>(), L, m->statpart.as<float>());
-    launched("in_stats_partial");
-  }
-  in_stats_final<<<dim3(S, 16), dim3(32, 8), 0, st>>>(m->statpart.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>());
-  launched("in_stats_final");
-  if (!aconv_n) {
-    norm_relu_split<<<(unsigned)(((long long)rows * 64 + 255) / 256), 256, 0, st>>>(m->hid.as<float>(), L, m->mu.as<float>(), m->rstd.as<float>(),
-                                                                                    m->hn.hi.as<__half>(), m->hn.lo.as<__half>());
-    launched("norm_relu_split");
-  }
-  // (7) delta = mlp.3(hn); x += delta  (:122, :59/:64); with converters hn = ReLU(InstanceNorm(hid)) is formed inside the GEMM
+  LAUNCH(m, st, "in_stats_final", in_stats_final, dim3(S, 16), dim3(32, 8), 0, st, (const float*)m->statpart.as<float>(), L, m->mu.as<float>(),
+         m->rstd.as<float>());
+  // (7) x <- x + mlp.3(ReLU(IN(hidden)))  (:122, :59/:64): the converters form hn inside the GEMM, the residual is an identity K-block
   GemmProblem p3{};
   p3.L = L; p3.batch = 1; p3.rows = rows;
-  p3.a1 = m->hn.c(512); p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256;
-  p3.bias = W.b1.as<float>(); p3.c = m->c768.as<float>(); p3.ldc = 256;
-  if (fuse1) {                                       // residual add + re-split in the epilogue, in place
-    p3.epi = EPI_RESID; p3.resid = x.c(kD); p3.out = x.m(kD);
-    if (m->resid_k) { p3.epi = EPI_BIAS_PLANES; p3.a2 = x.c(kD); p3.K2 = kD; p3.b2 = m->eye.c(kD); }   // x_new = [hn | x].[W1 | I]^T + b
-    if (aconv_n) { p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>(); }
-    return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512);
-  }
-  if (int rc = run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512)) return rc;
-  residual_update<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, xl, m->c768.as<float>(), (long long)rows * kD / 8);
-  launched("residual_update");
-  return 0;
+  p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256; p3.bias = W.b1.as<float>();
+  p3.epi = EPI_BIAS_PLANES; p3.out = x.m(kD);
+  p3.a2 = x.c(kD); p3.K2 = kD; p3.b2 = m->eye.c(kD); p3.b2_lo_zero = 1;
+  p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>();
+  return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512, "mlp3");
 }
 
 // Object prologue: GNN layers 0 (GATs) and the 3D side of layer 1 (self-attention) depend only on the per-object
@@ -429,57 +361,51 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
 // evaluated ONCE per opb_forward call -- on a single copy of the object's rows -- and shared by all frames of the
 // call instead of once per frame.  Result: m->xo = 3D-point state entering layer 2.
 static int object_prologue(opb_matcher* m, cudaStream_t st) {
-  Layout Lo;
+  Layout Lo{};
   Lo.B = 1; Lo.N = 0; Lo.M = m->M; Lo.n_pad = 0; Lo.m_pad = m->m_pad; Lo.R = m->m_pad;
-  CK(m, cudaMemcpyAsync(m->xo.hi.p, m->db.hi.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
-  CK(m, cudaMemcpyAsync(m->xo.lo.p, m->db.lo.p, (size_t)m->m_pad * kD * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  LAUNCH(m, st, "assemble_layout", assemble_layout, dim3(148 * 2, 1), dim3(256), 0, st, (const __half*)nullptr, (const __half*)nullptr,
+         (const __half*)m->db.hi.as<__half>(), (const __half*)m->db.lo.as<__half>(), m->xo.hi.as<__half>(), m->xo.lo.as<__half>(), Lo);
   if (int rc = run_gats(m, Lo, m->xo.view(), 0, st)) return rc;
   return run_attn_layer(m, Lo, m->xo.view(), m->attn[0], /*cross=*/0, st);
 }
 
 // GNN + tail for `fb` frames starting at frame f0 of the call.
-constexpr int kQPassFrames = 16;
-
-static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
+static int forward_chunk(opb_matcher* m, const float* q_cf, const int* nlen, int N, int fb, int64_t* m0, int64_t* m1, float* s0, float* s1,
                          float* conf, cudaStream_t st, int piece, int h2d_first) {
-  Layout L;
+  Layout L{};
   L.B = fb; L.N = N; L.M = m->M; L.n_pad = round_up(N, kSegPad); L.m_pad = m->m_pad; L.R = L.n_pad + L.m_pad;
+  L.nlen = nlen;
   m->last_layout = L;
   const int rows = L.rows();
   const double valid_rows = (double)fb * (N + L.M);
   __half *xh = m->x.hi.as<__half>(), *xl = m->x.lo.as<__half>();
-  auto launched = [&](const char* name = "aux") { m->launches++; prof_mark(m, st, name, 0.0); };
 
   int first_layer = 0;
   if (m->hoist) {
-    // layer 1 (self) for the query side only, on a compact [fb*n_pad, 256] buffer; layer 0 does not touch queries
-    // in sub-batches of `piece` frames: with host input (opb_forward_host) each sub-batch starts as soon as ITS descriptors
+    // layer 1 (self) for the query side only, on a compact [fb*n_pad, 256] buffer; layer 0 does not touch queries.
+    // In sub-batches of `piece` frames: with host input (opb_forward_host) each sub-batch starts as soon as ITS descriptors
     // have landed, so the H2D copy of the rest runs under this pass
-    for (int s0 = 0, si = 0; s0 < fb; s0 += piece, ++si) {
-      const int sb = std::min(piece, fb - s0);
+    for (int p0 = 0, si = 0; p0 < fb; p0 += piece, ++si) {
+      const int sb = std::min(piece, fb - p0);
       if (h2d_first + si < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[h2d_first + si], 0));
-      Layout Lq;
+      Layout Lq{};
       Lq.B = sb; Lq.N = N; Lq.M = 0; Lq.n_pad = L.n_pad; Lq.m_pad = 0; Lq.R = L.n_pad;
-      XView xq = m->xq.view((size_t)s0 * L.n_pad);
-      transpose_cf_to_rows<0><<<dim3((N + 31) / 32, sb), dim3(32, 8), 0, st>>>(q_cf + (size_t)s0 * kD * N, N, (long long)kD * N, xq.hi, xq.lo, nullptr,
-                                                                               Lq.R, 0);
-      launched("transpose_cf_to_rows");
+      Lq.nlen = nlen ? nlen + p0 : nullptr;
+      XView xq = m->xq.view((size_t)p0 * L.n_pad);
+      LAUNCH(m, st, "transpose_cf_to_rows", transpose_cf_to_rows<0>, dim3(L.n_pad / 32, sb), dim3(32, 8), 0, st, q_cf + (size_t)p0 * kD * N, N, N,
+             (long long)kD * N, Lq.nlen, L.n_pad, xq.hi, xq.lo, (float*)nullptr, (long long)Lq.R, 0);
       if (int rc = run_attn_layer(m, Lq, xq, m->attn[0], 0, st)) return rc;
     }
     // assemble the full layout: query rows from xq, 3D rows from the object prologue
-    CK(m, cudaMemcpy2DAsync(xh, (size_t)L.R * kD * sizeof(__half), m->xq.hi.p, (size_t)L.n_pad * kD * sizeof(__half),
-                            (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
-    CK(m, cudaMemcpy2DAsync(xl, (size_t)L.R * kD * sizeof(__half), m->xq.lo.p, (size_t)L.n_pad * kD * sizeof(__half),
-                            (size_t)L.n_pad * kD * sizeof(__half), fb, cudaMemcpyDeviceToDevice, st));
-    broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->xo.hi.as<__half>(), m->xo.lo.as<__half>(), xh, xl, L);
-    launched("broadcast_object_rows");
+    LAUNCH(m, st, "assemble_layout", assemble_layout, dim3(148 * 2, fb), dim3(256), 0, st, (const __half*)m->xq.hi.as<__half>(),
+           (const __half*)m->xq.lo.as<__half>(), (const __half*)m->xo.hi.as<__half>(), (const __half*)m->xo.lo.as<__half>(), xh, xl, L);
     first_layer = 2;
   } else {
     // inputs: query descriptors [fb,256,N] channel-first -> q segments; object rows -> d segments
-    transpose_cf_to_rows<0><<<dim3((N + 31) / 32, fb), dim3(32, 8), 0, st>>>(q_cf, N, (long long)kD * N, xh, xl, nullptr, L.R, 0);
-    launched("transpose_cf_to_rows");
-    broadcast_object_rows<<<dim3(148 * 2, fb), 256, 0, st>>>(m->db.hi.as<__half>(), m->db.lo.as<__half>(), xh, xl, L);
-    launched("broadcast_object_rows");
+    LAUNCH(m, st, "transpose_cf_to_rows", transpose_cf_to_rows<0>, dim3(L.n_pad / 32, fb), dim3(32, 8), 0, st, q_cf, N, N, (long long)kD * N, nlen,
+           L.n_pad, xh, xl, (float*)nullptr, (long long)L.R, 0);
+    LAUNCH(m, st, "assemble_layout", assemble_layout, dim3(148 * 2, fb), dim3(256), 0, st, (const __half*)nullptr, (const __half*)nullptr,
+           (const __half*)m->db.hi.as<__half>(), (const __half*)m->db.lo.as<__half>(), xh, xl, L);
   }
 
   for (int layer = first_layer; layer < 12; ++layer) {
@@ -491,65 +417,40 @@ static int forward_chunk(opb_matcher* m, const float* q_cf, int N, int fb, int64
     }
   }
 
-  range_check<<<(unsigned)(((long long)rows * kD / 8 + 255) / 256), 256, 0, st>>>(xh, (long long)rows * kD / 8, m->range_flag.as<int>());
-  launched("range_check");
+  LAUNCH(m, st, "range_check", range_check, dim3((unsigned)(((long long)rows * kD / 8 + 255) / 256)), dim3(256), 0, st, (const __half*)xh,
+         (long long)rows * kD / 8, m->range_flag.as<int>());
 
   // ---- tail (GATs_SuperGlue.py:209-237) ----
   GemmProblem pf{};
   pf.L = L; pf.batch = 1; pf.rows = rows;
   pf.a1 = m->x.c(kD); pf.K1 = kD; pf.b1 = m->wf.c(kD); pf.n_out = 256;
-  pf.bias = m->bf.as<float>(); pf.c = m->c768.as<float>(); pf.ldc = 256;
-  if (m->cfg.gemm_backend == 0 && m->fuse >= 1) {
-    pf.epi = EPI_L2NORM; pf.out = m->pn.m(kD);       // F.normalize fused into the final_proj epilogue (:209-213)
-    if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
-  } else {
-    if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD)) return rc;
-    l2_normalize_split<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(m->c768.as<float>(), rows, m->pn.hi.as<__half>(), m->pn.lo.as<__half>());
-    launched("l2_normalize_split");
-  }
-  const float inv_scale = 1.f / m->cfg.scale_factor;
-  if (m->cfg.gemm_backend == 0 && (m->fuse >= 2 || (m->fuse >= 1 && m->tail_fuse))) {
-    // ---- fused tail: two passes of the batched score GEMM, nothing N x M ever read back
-    const int n_tiles = L.m_pad / 256, q_groups = L.n_pad / 32;
-    GemmProblem ps{};
-    ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
-    ps.a1 = m->pn.c(kD); ps.K1 = kD; ps.b1 = m->pn.c(kD, (size_t)L.n_pad * kD);
-    ps.a_batch_rows = L.R; ps.b_batch_rows = L.R;
-    ps.inv_scale = inv_scale;
-    ps.epi = EPI_SCORE_SUMS; ps.rowsum_part = m->rowsum_part.as<float>(); ps.colsum_part = m->colsum_part.as<float>();
-    if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
-    score_sums_finalize<<<dim3((L.n_pad + L.m_pad + 255) / 256, fb), 256, 0, st>>>(m->rowsum_part.as<float>(), m->colsum_part.as<float>(), L, n_tiles,
-                                                                                  q_groups, m->rowsum.as<float>(), m->colsum.as<float>());
-    launched("score_sums_finalize");
-    CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
-    CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
-    ps.epi = EPI_SCORE_CONF; ps.inv_rowsum = m->rowsum.as<float>(); ps.inv_colsum = m->colsum.as<float>();
-    ps.conf = conf; ps.rowbest = m->rowbest.as<unsigned long long>(); ps.colbest = m->colbest.as<unsigned long long>();
-    if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
-  } else {
-  // cos[b][n][m] = <P_q[n], P_d[m]>   (batched over frames)
+  pf.bias = m->bf.as<float>();
+  pf.epi = EPI_L2NORM; pf.out = m->pn.m(kD);       // F.normalize fused into the final_proj epilogue (:209-213)
+  if (int rc = run_gemm(m, pf, st, 2.0 * valid_rows * kD * kD, "final_proj")) return rc;
+  // dual softmax + arg-max as two passes of the batched score GEMM (one batch = one frame); the cos matrix is never stored
+  const int n_parts = (L.m_pad / 256) * 2, q_groups = L.n_pad / 32;
   GemmProblem ps{};
   ps.L = L; ps.batch = fb; ps.rows = L.n_pad; ps.n_out = L.m_pad;
   ps.a1 = m->pn.c(kD); ps.K1 = kD; ps.b1 = m->pn.c(kD, (size_t)L.n_pad * kD);
-  ps.a_batch_rows = L.R; ps.b_batch_rows = L.R; ps.c_batch_elems = (long long)L.n_pad * L.m_pad;
-  ps.c = m->score.as<float>(); ps.ldc = L.m_pad;
-  if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD)) return rc;
-  score_row_sums<<<(unsigned)(((long long)fb * N * 32 + 255) / 256), 256, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>());
-  launched("score_row_sums");
-  score_col_sums<<<dim3((L.M + 31) / 32, fb), dim3(32, 8), 0, st>>>(m->score.as<float>(), L, inv_scale, m->colsum.as<float>());
-  launched("score_col_sums");
-  CK(m, cudaMemsetAsync(m->rowbest.p, 0, (size_t)fb * N * sizeof(unsigned long long), st));
-  CK(m, cudaMemsetAsync(m->colbest.p, 0, (size_t)fb * L.M * sizeof(unsigned long long), st));
-  conf_argmax_simt<<<dim3((L.M + 127) / 128, (N + 31) / 32, fb), 128, 0, st>>>(m->score.as<float>(), L, inv_scale, m->rowsum.as<float>(),
-                                                                              m->colsum.as<float>(), conf,
-                                                                              m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
-  launched("conf_argmax_simt");
-  }
-  mutual_match<<<fb, 256, 0, st>>>(m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>(), N, L.M, m->cfg.match_threshold,
-                                   reinterpret_cast<long long*>(m0), reinterpret_cast<long long*>(m1), s0, s1);
-  launched("mutual_match");
-  CK(m, cudaGetLastError());
+  ps.a_batch_rows = L.R; ps.b_batch_rows = L.R;
+  ps.inv_scale = 1.f / m->cfg.scale_factor;
+  ps.epi = EPI_SCORE_SUMS; ps.rowsum_part = m->rowsum_part.as<float>(); ps.colsum_part = m->colsum_part.as<float>();
+  if (int rc = run_gemm(m, ps, st, 2.0 * fb * (double)N * L.M * kD, "score_sums")) return rc;
+  LAUNCH(m, st, "score_sums_finalize", score_sums_finalize, dim3((L.n_pad + L.m_pad + 255) / 256, fb), dim3(256), 0, st,
+         (const float*)m->rowsum_part.as<float>(), (const float*)m->colsum_part.as<float>(), L, n_parts, q_groups, m->rowsum.as<float>(),
+         m->colsum.as<float>(), m->rowbest.as<unsigned long long>(), m->colbest.as<unsigned long long>());
+  ps.epi = EPI_SCORE_CONF; ps.inv_rowsum = m->rowsum.as<float>(); ps.inv_colsum = m->colsum.as<float>();
+  ps.conf = conf; ps.rowbest = m->rowbest.as<unsigned long long>(); ps.colbest = m->colbest.as<unsigned long long>();
+  if (int rc = run_gemm(m, ps, st, 0.0, "score_conf")) return rc;      // recomputation: its FLOPs are not algorithmic
+  LAUNCH(m, st, "mutual_match", mutual_match, dim3(fb), dim3(256), 0, st, (const unsigned long long*)m->rowbest.as<unsigned long long>(),
+         (const unsigned long long*)m->colbest.as<unsigned long long>(), L, m->cfg.match_threshold, (const int*)m->range_flag.as<int>(),
+         reinterpret_cast<long long*>(m0), reinterpret_cast<long long*>(m1), s0, s1);
   return 0;
+}
+
+static int chunk_of(const opb_matcher* m, int B) {
+  int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
+  return chunk > B ? B : chunk;
 }
 
 }  // namespace opb
@@ -561,8 +462,6 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   if (!cfg || !out) return fail(nullptr, OPB_E_INVALID, "null argument");
   if (cfg->descriptor_dim != kD || cfg->num_heads != kHeads)
     return fail(nullptr, OPB_E_INVALID, "only descriptor_dim=256, num_heads=4 are supported (got %d, %d)", cfg->descriptor_dim, cfg->num_heads);
-  if (cfg->with_linear_transform)
-    return fail(nullptr, OPB_E_NOT_IMPLEMENTED, "with_linear_transform=True is not implemented (released model uses False)");
   if (!(cfg->scale_factor > 0.f)) return fail(nullptr, OPB_E_INVALID, "scale_factor must be > 0");
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -574,17 +473,14 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   if (prop.major != 10) return fail(nullptr, OPB_E_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
-  e = cudaFuncSetAttribute(kv_state_partial_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBytes);
-  if (e != cudaSuccess) return fail(nullptr, OPB_E_CUDA, "cudaFuncSetAttribute(kv_state_partial_mma): %s", cudaGetErrorString(e));
   auto* m = new opb_matcher();
   m->cfg = *cfg;
-  if (const char* f = getenv("OPB_KV_MODE")) m->kv_mode = atoi(f) == 1 ? 1 : 0;
-  if (const char* f = getenv("OPB_ACONV")) m->aconv = atoi(f) & 3;
-  if (const char* f = getenv("OPB_SPLIT_Q")) m->split_q = atoi(f) != 0 ? 1 : 0;
-  if (const char* f = getenv("OPB_TAIL_FUSE")) m->tail_fuse = atoi(f) != 0 ? 1 : 0;
-  if (const char* f = getenv("OPB_RESID_K")) m->resid_k = atoi(f) != 0 ? 1 : 0;
-  if (const char* f = getenv("OPB_KV_HALF")) m->kv_half = atoi(f) != 0 ? 1 : 0;
-  if (const char* f = getenv("OPB_FUSE")) m->fuse = atoi(f) < 0 ? 0 : (atoi(f) > 2 ? 2 : atoi(f));
+  m->num_sms = prop.multiProcessorCount;
+  if (cudaMallocHost(&m->range_host, sizeof(int)) != cudaSuccess || cudaEventCreateWithFlags(&m->range_ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete m;
+    return fail(nullptr, OPB_E_CUDA, "pinned flag / event allocation failed");
+  }
+  *m->range_host = 0;
   *out = m;
   return OPB_OK;
 }
@@ -592,18 +488,20 @@ int opb_create(const opb_config* cfg, opb_matcher** out) {
 void opb_destroy(opb_matcher* m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
+  cudaDeviceSynchronize();
   for (auto& a : m->attn) { a.wqkv.release(); a.bqkv.release(); a.w0a.release(); a.w0m.release(); a.b0f.release(); a.w1.release(); a.b1.release(); }
-  DevBuf* bufs[] = {&m->wa2, &m->wa3, &m->bf, &m->leaves, &m->s2, &m->c768, &m->hid, &m->kvpart, &m->kvmean, &m->kmean, &m->statpart,
-                    &m->mu, &m->rstd, &m->score, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
-                    &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf};
+  DevBuf* bufs[] = {&m->wa2, &m->wa3, &m->bf, &m->leaves, &m->s2, &m->kvt, &m->hid, &m->kvpart, &m->kmean, &m->statpart,
+                    &m->mu, &m->rstd, &m->rowsum_part, &m->colsum_part, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
+                    &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf, &m->st_len};
   for (auto* b : bufs) b->release();
-  PlaneBuf* pb[] = {&m->wf, &m->db, &m->x, &m->qp, &m->hn, &m->pn, &m->g, &m->xo, &m->xq, &m->kvt, &m->eye};
-  m->kvpieces.release(); m->rowsum_part.release(); m->colsum_part.release(); m->ksum_part.release();
+  PlaneBuf* pb[] = {&m->wf, &m->wlin, &m->db, &m->x, &m->qp, &m->pn, &m->g, &m->xo, &m->xq, &m->bd, &m->lin_a, &m->lin_b, &m->eye};
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   for (auto e : m->h2d_ev) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->ev_fwd0) { cudaEventDestroy(m->ev_fwd0); cudaEventDestroy(m->ev_fwd1); }
+  if (m->range_ev) cudaEventDestroy(m->range_ev);
+  if (m->range_host) cudaFreeHost(m->range_host);
   delete m;
 }
 
@@ -640,6 +538,12 @@ int opb_finalize_weights(opb_matcher* m) {
         }
         wa2[gi * kD + c] = s2;
         wa3[gi * kD + c] = s3;
+      }
+      if (m->cfg.with_linear_transform) {     // B operand of  t = pre . W :  B[o][c] = W[c][o]
+        std::vector<double> wt((size_t)kD * kD);
+        for (int c = 0; c < kD; ++c)
+          for (int o = 0; o < kD; ++o) wt[(size_t)o * kD + c] = (*W)[(size_t)c * kD + o];
+        if (int rc = upload_planes(m, m->wlin, wt, (size_t)gi * kD * kD, (size_t)4 * kD * kD)) return rc;
       }
       continue;
     }
@@ -679,7 +583,7 @@ int opb_finalize_weights(opb_matcher* m) {
     if (int rc = upload_planes(m, A.wqkv, wqkv)) return rc;
     if (int rc = upload_f32(m, A.bqkv, bqkv)) return rc;
     if (int rc = upload_planes(m, A.w0a, w0a)) return rc;
-    if (int rc = upload_f32(m, A.w0m, w0m)) return rc;
+    if (int rc = upload_planes(m, A.w0m, w0m)) return rc;
     if (int rc = upload_f32(m, A.b0f, b0f)) return rc;
     if (int rc = upload_planes(m, A.w1, w1)) return rc;
     if (int rc = upload_f32(m, A.b1, b1d)) return rc;
@@ -696,6 +600,7 @@ int opb_finalize_weights(opb_matcher* m) {
   if (int rc = upload_f32(m, m->bf, std::vector<double>(bfv->begin(), bfv->end()))) return rc;
   if (int rc = upload_f32(m, m->wa2, wa2)) return rc;
   if (int rc = upload_f32(m, m->wa3, wa3)) return rc;
+  CK(m, cudaDeviceSynchronize());
   m->weights_ready = true;
   m->object_ready = false;  // s2 depends on the weights
   return OPB_OK;
@@ -712,24 +617,28 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
   if (m_pad != m->m_pad) { m->ws_frames = 0; m->ws_N = 0; }  // workspace depends on m_pad
   m->M = M; m->Lf = Lf; m->m_pad = m_pad;
   const long long n_leaf_rows = (long long)M * Lf;
+  m->leaves.grew = m->db.hi.grew = m->db.lo.grew = m->s2.grew = false;
   CK(m, m->leaves.ensure((size_t)n_leaf_rows * kD * sizeof(float)));
   CK(m, m->db.ensure((size_t)m_pad * kD));
-  CK(m, cudaMemsetAsync(m->db.hi.p, 0, (size_t)m_pad * kD * sizeof(__half), st));
-  CK(m, cudaMemsetAsync(m->db.lo.p, 0, (size_t)m_pad * kD * sizeof(__half), st));
   CK(m, m->s2.ensure((size_t)4 * n_leaf_rows * sizeof(float)));
-  transpose_cf_to_rows<1><<<dim3((unsigned)((n_leaf_rows + 31) / 32), 1), dim3(32, 8), 0, st>>>(desc2d_db, (int)n_leaf_rows, 0, nullptr, nullptr,
-                                                                                           m->leaves.as<float>(), 0, 0);
-  transpose_cf_to_rows<0><<<dim3((M + 31) / 32, 1), dim3(32, 8), 0, st>>>(desc3d_db, M, 0, m->db.hi.as<__half>(), m->db.lo.as<__half>(), nullptr, 0, 0);
-  gats_leaf_logits<<<148 * 4, 256, 0, st>>>(m->leaves.as<float>(), n_leaf_rows, m->wa2.as<float>(), m->s2.as<float>());
+  if (m->leaves.grew || m->db.hi.grew || m->s2.grew) CK(m, cudaDeviceSynchronize());   // frees of the old buffers vs work in flight
+  launch_k(transpose_cf_to_rows<1>, dim3((unsigned)((n_leaf_rows + 31) / 32), 1), dim3(32, 8), 0, st, desc2d_db, (int)n_leaf_rows, (int)n_leaf_rows, 0ll,
+           (const int*)nullptr, (int)n_leaf_rows, (__half*)nullptr, (__half*)nullptr, m->leaves.as<float>(), 0ll, 0);
+  // rows [M, m_pad) of the object planes are written as zero by the transpose (MODE 0 pads to rows_out)
+  launch_k(transpose_cf_to_rows<0>, dim3(m_pad / 32, 1), dim3(32, 8), 0, st, desc3d_db, (int)M, (int)M, 0ll, (const int*)nullptr, m_pad,
+           m->db.hi.as<__half>(), m->db.lo.as<__half>(), (float*)nullptr, 0ll, 0);
+  launch_k(gats_leaf_logits, dim3(148 * 4), dim3(256), 0, st, (const float*)m->leaves.as<float>(), n_leaf_rows, (const float*)m->wa2.as<float>(),
+           m->s2.as<float>());
   CK(m, cudaGetLastError());
   m->object_ready = true;
   return OPB_OK;
 }
 
-int opb_set_fuse_level(opb_matcher* m, int32_t level) {
-  if (!m || level < 0 || level > 2) return OPB_E_INVALID;
-  m->fuse = level;
-  return OPB_OK;
+int opb_reserve_workspace(opb_matcher* m, int32_t frames, int32_t N) {
+  if (!m || frames <= 0 || N <= 0) return OPB_E_INVALID;
+  if (!m->object_ready) return fail(m, OPB_E_STATE, "opb_reserve_workspace needs an object (the workspace depends on M)");
+  CK(m, cudaSetDevice(m->cfg.device));
+  return ensure_workspace(m, chunk_of(m, frames), N);
 }
 
 int opb_set_hoist(opb_matcher* m, int32_t enable) {
@@ -744,16 +653,15 @@ int opb_set_chunk_frames(opb_matcher* m, int32_t frames) {
   return OPB_OK;
 }
 
-int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m0, int64_t* m1, float* s0, float* s1, float* conf,
-                void* stream) {
+int opb_forward(opb_matcher* m, const float* q, const int32_t* n2d_lengths, int32_t B, int32_t N, int64_t* m0, int64_t* m1, float* s0, float* s1,
+                float* conf, void* stream) {
   if (!m) return OPB_E_INVALID;
   if (!m->weights_ready || !m->object_ready) return fail(m, OPB_E_STATE, "opb_forward needs weights and an object (finalize_weights, set_object)");
   if (!q || !m0 || !m1 || !s0 || !s1 || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward: bad argument (B=%d, N=%d)", B, N);
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
-  if (chunk > B) chunk = B;
-  if (int rc = ensure_workspace(m, chunk, N)) return rc;
+  const int chunk = chunk_of(m, B);
+  if (int rc = ensure_workspace(m, chunk, N)) return rc;   // no-op once opb_reserve_workspace / an earlier call has sized it
   m->launches = 0;
   if (m->profiling) {
     m->ev_used = 0;
@@ -773,10 +681,15 @@ int opb_forward(opb_matcher* m, const float* q, int32_t B, int32_t N, int64_t* m
     if (!m->hoist)                                          // per-frame evaluation consumes the whole chunk at once
       for (int si = 0; si * piece < fb; ++si)
         if (ci * ppc + si < m->h2d_pending) CK(m, cudaStreamWaitEvent(st, m->h2d_ev[ci * ppc + si], 0));
-    int rc = forward_chunk(m, q + (size_t)f0 * kD * N, N, fb, m0 + (size_t)f0 * N, m1 + (size_t)f0 * m->M, s0 + (size_t)f0 * N,
-                           s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st, piece, ci * ppc);
+    int rc = forward_chunk(m, q + (size_t)f0 * kD * N, n2d_lengths ? n2d_lengths + f0 : nullptr, N, fb, m0 + (size_t)f0 * N, m1 + (size_t)f0 * m->M,
+                           s0 + (size_t)f0 * N, s1 + (size_t)f0 * m->M, conf ? conf + (size_t)f0 * N * m->M : nullptr, st, piece, ci * ppc);
     if (rc) return rc;
   }
+  // deferred range report: the flag travels to pinned host memory behind the call; opb_poll_range() reads it without blocking
+  CK(m, cudaMemcpyAsync(m->range_host, m->range_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(m, cudaEventRecord(m->range_ev, st));
+  m->range_pending = true;
+  m->last_stream = st;
   if (m->profiling) cudaEventRecord(m->ev_fwd1, st);
   m->last_launches = m->launches;
   return OPB_OK;
@@ -800,16 +713,16 @@ int opb_get_profile(opb_matcher* m, double* gemm_ms, double* gemm_flops, int32_t
   for (size_t i = 0; i < m->ev_flops.size(); ++i) {
     float t = 0;
     CK(m, cudaEventElapsedTime(&t, i == 0 ? m->ev_fwd0 : m->ev_pool[i - 1], m->ev_pool[i]));
-    if (m->ev_flops[i] > 0) { ms += t; fl += m->ev_flops[i]; ++n_gemm; }
+    if (m->ev_name[i].compare(0, 4, "gemm") == 0) { ms += t; fl += m->ev_flops[i]; ++n_gemm; }
     auto& a = agg[m->ev_name[i]];
     a.first += t; a.second.first += m->ev_flops[i]; a.second.second++;
   }
   float tot = 0;
   CK(m, cudaEventElapsedTime(&tot, m->ev_fwd0, m->ev_fwd1));
-  if (getenv("OPB_PROFILE_DUMP")) {
+  if (getenv("OPB_PROFILE_DUMP")) {   // measurement aid only: prints the table, selects nothing
     fprintf(stderr, "[opb profile] forward %.3f ms, GEMM %.3f ms in %d launches\n", tot, ms, n_gemm);
     for (auto& kv : agg)
-      fprintf(stderr, "[opb profile] %-28s %4d launches %8.3f ms %5.1f%%  %7.1f TFLOP/s algorithmic\n", kv.first.c_str(), kv.second.second.second,
+      fprintf(stderr, "[opb profile] %-36s %4d launches %8.3f ms %5.1f%%  %7.1f TFLOP/s algorithmic\n", kv.first.c_str(), kv.second.second.second,
               kv.second.first, 100.0 * kv.second.first / tot, kv.second.second.first / (kv.second.first * 1e-3) / 1e12);
   }
   if (gemm_ms) *gemm_ms = ms;
@@ -837,23 +750,26 @@ int opb_get_profile_entry(opb_matcher* m, const char* prefix, double* ms_out, do
   return OPB_OK;
 }
 
-int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int64_t* m0h, int64_t* m1h, float* s0h, float* s1h, float* confh,
-                     void* stream) {
+int opb_forward_host(opb_matcher* m, const float* qh, const int32_t* n2d_lengths_host, int32_t B, int32_t N, int64_t* m0h, int64_t* m1h, float* s0h,
+                     float* s1h, float* confh, int32_t materialize_conf, void* stream) {
   if (!m) return OPB_E_INVALID;
   if (!m->object_ready) return fail(m, OPB_E_STATE, "opb_forward_host needs an object");
   if (!qh || !m0h || !m1h || !s0h || !s1h || B <= 0 || N <= 0) return fail(m, OPB_E_INVALID, "opb_forward_host: bad argument");
   CK(m, cudaSetDevice(m->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t M = m->M;
+  const bool want_conf = confh != nullptr || materialize_conf != 0;
+  DevBuf* stg[] = {&m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf, &m->st_len};
+  for (auto* b : stg) b->grew = false;
   CK(m, m->st_q.ensure((size_t)B * kD * N * sizeof(float)));
   CK(m, m->st_m0.ensure((size_t)B * N * sizeof(int64_t)));
   CK(m, m->st_m1.ensure((size_t)B * M * sizeof(int64_t)));
   CK(m, m->st_s0.ensure((size_t)B * N * sizeof(float)));
   CK(m, m->st_s1.ensure((size_t)B * M * sizeof(float)));
-  CK(m, m->st_conf.ensure((size_t)B * N * M * sizeof(float)));  // conf is always materialised (reference returns it)
-  // H2D per chunk on a side stream: the copy of chunk i+1 runs under the compute of chunk i
-  int chunk = m->chunk_frames > 0 ? m->chunk_frames : kDefaultChunk;
-  if (chunk > B) chunk = B;
+  if (want_conf) CK(m, m->st_conf.ensure((size_t)B * N * M * sizeof(float)));
+  if (n2d_lengths_host) CK(m, m->st_len.ensure((size_t)B * sizeof(int32_t)));
+  // H2D per piece on a side stream: the copy of piece i+1 runs under the compute of piece i
+  const int chunk = chunk_of(m, B);
   if (!m->copy_stream) CK(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   const int piece = std::min(chunk, kQPassFrames);
   const int ppc = (chunk + piece - 1) / piece;
@@ -866,6 +782,7 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   }
   CK(m, cudaEventRecord(m->h2d_ev[n_ev], st));                           // staging buffer reuse: wait for earlier work on `st`
   CK(m, cudaStreamWaitEvent(m->copy_stream, m->h2d_ev[n_ev], 0));
+  if (n2d_lengths_host) CK(m, cudaMemcpyAsync(m->st_len.p, n2d_lengths_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, m->copy_stream));
   for (int ci = 0; ci < n_chunks; ++ci) {
     const int c0 = ci * chunk, cb = std::min(chunk, B - c0);
     for (int si = 0; si < ppc; ++si) {
@@ -878,8 +795,8 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
     }
   }
   m->h2d_pending = n_ev;
-  const int frc = opb_forward(m, m->st_q.as<float>(), B, N, m->st_m0.as<int64_t>(), m->st_m1.as<int64_t>(), m->st_s0.as<float>(),
-                              m->st_s1.as<float>(), m->st_conf.as<float>(), stream);
+  const int frc = opb_forward(m, m->st_q.as<float>(), n2d_lengths_host ? m->st_len.as<int32_t>() : nullptr, B, N, m->st_m0.as<int64_t>(),
+                              m->st_m1.as<int64_t>(), m->st_s0.as<float>(), m->st_s1.as<float>(), want_conf ? m->st_conf.as<float>() : nullptr, stream);
   m->h2d_pending = 0;
   if (frc) return frc;
   CK(m, cudaMemcpyAsync(m0h, m->st_m0.p, (size_t)B * N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -891,79 +808,130 @@ int opb_forward_host(opb_matcher* m, const float* qh, int32_t B, int32_t N, int6
   return opb_check_range(m, stream);
 }
 
+// Consume the range flag.  After a synchronisation of the stream the pinned copy written behind the last opb_forward is current.
+static int consume_range_flag(opb_matcher* m) {
+  m->range_pending = false;
+  if (*m->range_host == 0) return OPB_OK;
+  *m->range_host = 0;
+  CK(m, cudaMemsetAsync(m->range_flag.p, 0, sizeof(int), m->last_stream));
+  return fail(m, OPB_E_RANGE, "an activation left the fp16-split operand range (|x| >= 1023) or became NaN: the matches of that call were "
+                              "reported as -1 (no match)");
+}
+
 int opb_check_range(opb_matcher* m, void* stream) {
-  if (!m || !m->range_flag.p) return OPB_OK;
-  int flag = 0;
-  CK(m, cudaMemcpyAsync(&flag, m->range_flag.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CK(m, cudaStreamSynchronize((cudaStream_t)stream));
-  if (flag) {
-    CK(m, cudaMemsetAsync(m->range_flag.p, 0, sizeof(int), (cudaStream_t)stream));
-    return fail(m, OPB_E_RANGE, "an activation left the fp16-split operand range (|x| >= 1023) or became NaN: results of this call are invalid");
-  }
-  return OPB_OK;
+  if (!m || !m->range_flag.p || !m->range_pending) return OPB_OK;
+  (void)stream;
+  CK(m, cudaEventSynchronize(m->range_ev));
+  return consume_range_flag(m);
+}
+
+int opb_poll_range(opb_matcher* m) {
+  if (!m || !m->range_pending) return OPB_OK;
+  const cudaError_t q = cudaEventQuery(m->range_ev);
+  if (q == cudaErrorNotReady) return OPB_OK;               // the call is still running: report on a later poll / check
+  if (q != cudaSuccess) return fail(m, OPB_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
+  return consume_range_flag(m);
 }
 
 int opb_last_launch_count(const opb_matcher* m) { return m ? m->last_launches : 0; }
+
+// ---- adjacent producers ------------------------------------------------------------------
+static int scan_offsets(const int64_t* seg_len, int32_t M, long long** offs, cudaStream_t st) {
+  if (cudaMallocAsync(offs, (size_t)M * sizeof(long long), st) != cudaSuccess) return OPB_E_CUDA;
+  exclusive_scan_i64<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(seg_len), *offs, M);
+  return OPB_OK;
+}
 
 int opb_segmented_mean_f64(const double* desc, const int64_t* seg_len, int32_t M, int32_t D, double* out, void* stream) {
   if (!desc || !seg_len || !out || M <= 0 || D <= 0) return OPB_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   long long* offs = nullptr;
-  if (cudaMallocAsync(&offs, (size_t)M * sizeof(long long), st) != cudaSuccess) return OPB_E_CUDA;
-  exclusive_scan_i64_single<<<1, 1, 0, st>>>(reinterpret_cast<const long long*>(seg_len), offs, M);
+  if (int rc = scan_offsets(seg_len, M, &offs, st)) return rc;
   segmented_mean_f64<<<(unsigned)(((long long)M * 32 + 255) / 256), 256, 0, st>>>(desc, reinterpret_cast<const long long*>(seg_len), offs, M, D, out);
   cudaFreeAsync(offs, st);
   return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
 }
 
-int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out, int32_t K,
-                   int32_t backend, void* stream) {
+int opb_segmented_mean_scores_f64(const double* scores, const int64_t* seg_len, int32_t M, double* out, void* stream) {
+  if (!scores || !seg_len || !out || M <= 0) return OPB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long* offs = nullptr;
+  if (int rc = scan_offsets(seg_len, M, &offs, st)) return rc;
+  segmented_mean_scores_f64<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(scores, reinterpret_cast<const long long*>(seg_len), offs, M, out);
+  cudaFreeAsync(offs, st);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
+}
+
+int opb_gather_features3d(const float* desc, const float* scores, int32_t dim, int64_t n_src, const int64_t* idx, int64_t n_idx, float* desc_out,
+                          float* scores_out, int64_t n_out, void* stream) {
+  if (!desc || !desc_out || dim <= 0 || n_src < 0 || n_out <= 0 || n_idx < 0 || n_idx > n_out) return OPB_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned gx = (unsigned)((n_out + 255) / 256);
+  gather_columns_f32<<<dim3(gx, (unsigned)dim), 256, 0, st>>>(desc, dim, (long long)n_src, reinterpret_cast<const long long*>(idx), (long long)n_idx,
+                                                              desc_out, (long long)n_out);
+  if (scores && scores_out)
+    gather_scores_f32<<<gx, 256, 0, st>>>(scores, (long long)n_src, reinterpret_cast<const long long*>(idx), (long long)n_idx, scores_out, (long long)n_out);
+  return cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_E_CUDA;
+}
+
+// ---- test hooks ---------------------------------------------------------------------------
+int opb_debug_set_pdl(int32_t enable) {
+  set_pdl_enabled(enable != 0);
+  return OPB_OK;
+}
+
+static GemmProblem plain_problem(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out, int32_t K) {
   GemmProblem p{};
   p.a1 = CPlanes{(const __half*)a_hi, (const __half*)a_lo, K};
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
   p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
-  p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
+  return p;
+}
+
+int opb_debug_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out, int32_t K,
+                   int32_t backend, void* stream) {
+  GemmProblem p = plain_problem(a_hi, a_lo, b_hi, b_lo, c, rows, n_out, K);
   int rc = backend == 1 ? launch_gemm_simt(p, (cudaStream_t)stream) : launch_gemm_tc(p, (cudaStream_t)stream);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 
 int opb_debug_gemm_timeline(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* c, int32_t rows, int32_t n_out,
-                            int32_t K, long long* timeline, int32_t dbg, void* stream) {
-  GemmProblem p{};
-  p.a1 = CPlanes{(const __half*)a_hi, (const __half*)a_lo, K};
-  p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, K};
-  p.K1 = K; p.K2 = 0; p.rows = rows; p.n_out = n_out; p.batch = 1; p.c = c; p.ldc = n_out;
-  p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  static float* dbg_bias = nullptr;
-  if (dbg == 9) {          // k,v projection form: fp16 plane out (EPI_QKV, q_tiles = 0); `c` is reused as the fp16 output buffer
-    if (!dbg_bias) { cudaMalloc(&dbg_bias, 1024 * sizeof(float)); cudaMemset(dbg_bias, 0, 1024 * sizeof(float)); }
-    p.epi = EPI_QKV; p.q_tiles = 0; p.bias = dbg_bias; p.out = Planes{(__half*)c, (__half*)c, n_out}; p.c = nullptr;
-  }
+                            int32_t K, long long* timeline, void* stream) {
+  GemmProblem p = plain_problem(a_hi, a_lo, b_hi, b_lo, c, rows, n_out, K);
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 
 int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo, void* x_hi, void* x_lo, const float* mu, const float* rstd,
                          const float* bias, const void* eye_hi, const void* eye_lo, int32_t rows, long long* timeline, void* stream) {
-  // the mlp.3 problem of one segment: x[rows,256] += ReLU((a_raw - mu) * rstd)[rows,512] . B[256,512]^T + bias, converters on
+  // the mlp.3 problem of one segment: x[rows,256] = [ReLU((a_raw - mu) * rstd) | x] . [B | I]^T + bias, converters on
+  if (!eye_hi || !eye_lo) return OPB_E_INVALID;
   GemmProblem p{};
   p.b1 = CPlanes{(const __half*)b_hi, (const __half*)b_lo, 512};
-  p.K1 = 512; p.K2 = 0; p.rows = rows; p.n_out = 256; p.batch = 1; p.bias = bias;
+  p.K1 = 512; p.rows = rows; p.n_out = 256; p.batch = 1; p.bias = bias;
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
-  p.epi = EPI_RESID; p.resid = CPlanes{(const __half*)x_hi, (const __half*)x_lo, kD}; p.out = Planes{(__half*)x_hi, (__half*)x_lo, kD};
-  if (eye_hi) {           // residual as an identity K-block
-    p.epi = EPI_BIAS_PLANES; p.a2 = p.resid; p.K2 = kD; p.b2 = CPlanes{(const __half*)eye_hi, (const __half*)eye_lo, kD};
-  }
+  p.epi = EPI_BIAS_PLANES; p.out = Planes{(__half*)x_hi, (__half*)x_lo, kD};
+  p.a2 = CPlanes{(const __half*)x_hi, (const __half*)x_lo, kD}; p.K2 = kD; p.b2 = CPlanes{(const __half*)eye_hi, (const __half*)eye_lo, kD};
+  p.b2_lo_zero = 1;
   p.a_conv = 1; p.a_raw = a_raw; p.a_raw_ld = 512; p.mu = mu; p.rstd = rstd;
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);
 }
 
-int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, float* partial, void* stream) {
-  Layout L;
+int opb_debug_kv_state_h(const void* kvh, int32_t frames, int32_t n, int32_t m_pts, int32_t slabs_per_group, float* partial, int32_t* n_groups,
+                         void* stream) {
+  Layout L{};
   L.B = frames; L.N = n; L.M = m_pts; L.n_pad = (n + kSegPad - 1) / kSegPad * kSegPad; L.m_pad = (m_pts + kSegPad - 1) / kSegPad * kSegPad;
   L.R = L.n_pad + L.m_pad;
-  return launch_kv_state_h((const __half*)kvh, L, partial, (cudaStream_t)stream) == 0 ? OPB_OK : OPB_E_CUDA;
+  KvGroups G = kv_groups_for(L, 148);
+  if (slabs_per_group > 0) {
+    G.slabs = slabs_per_group;
+    G.gq = (L.n_pad / 256 + G.slabs - 1) / G.slabs;
+    G.gd = (L.m_pad / 256 + G.slabs - 1) / G.slabs;
+  }
+  if (n_groups) *n_groups = frames * (G.gq + G.gd);
+  if (!partial) return OPB_OK;                    // size query
+  return launch_kv_state_h((const __half*)kvh, L, G, partial, (cudaStream_t)stream) == 0 ? OPB_OK : OPB_E_CUDA;
 }
 
 int opb_debug_split(const float* x, void* hi, void* lo, size_t n, void* stream) {

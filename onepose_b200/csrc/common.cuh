@@ -28,6 +28,7 @@ constexpr float kHalfMax = 65504.0f;
 // (reference GATs_SuperGlue.py:126 and :77-78 reduce over the point dimension).
 struct Layout {
   int B, N, M, n_pad, m_pad, R;
+  const int* nlen;   // device int32 [B]: valid query rows of each frame (ragged batch, every entry in [0, N]) or nullptr: N everywhere
   __host__ __device__ int rows() const { return B * R; }
   __host__ __device__ int segs() const { return 2 * B; }
   __host__ __device__ int seg_of_row(int row) const {
@@ -35,8 +36,12 @@ struct Layout {
     return 2 * b + ((row - b * R) >= n_pad ? 1 : 0);
   }
   __host__ __device__ int seg_start(int seg) const { return (seg >> 1) * R + ((seg & 1) ? n_pad : 0); }
-  __host__ __device__ int seg_valid(int seg) const { return (seg & 1) ? M : N; }
   __host__ __device__ int seg_padded(int seg) const { return (seg & 1) ? m_pad : n_pad; }
+#ifdef __CUDACC__
+  // valid query rows of frame b / valid rows of a segment (device only: nlen lives in device memory)
+  __device__ int n_of(int b) const { return nlen ? min(max(__ldg(nlen + b), 0), N) : N; }
+  __device__ int seg_valid(int seg) const { return (seg & 1) ? M : n_of(seg >> 1); }
+#endif
   // attention source segment: 'self' -> itself, 'cross' -> the other side of the frame
   // (reference GATs_SuperGlue.py:57-58, :62-63)
   __host__ __device__ int src_seg(int seg, int cross) const { return cross ? (seg ^ 1) : seg; }
@@ -48,6 +53,18 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 // exp / elu+1 on the bare hardware exponential: ex2.approx.ftz (max rel. error ~2^-22, the order of the fp16 split every
 // consumer applies next).  __expf wraps the same instruction in denormal-range handling that costs ~10 predicated
 // instructions per element -- measured 4x on the element-wise epilogues.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Programmatic dependent launch (every kernel of the path is launched with programmatic stream serialization): wait until the
+// previous launch of the stream has completed and its writes are visible, then allow the next launch to begin its own set-up.
+// Nothing before this call may touch global memory.
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ float exp_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));

@@ -1,6 +1,6 @@
 // SIMT fp32 GEMM over fp16-split operands: the arithmetic cross-check of the tcgen05 core.
 // Reconstructs x = hi + lo*2^-11 in the loader and runs a classic 128x128x16 register-tiled
-// FFMA kernel.  Not the product path (opb_config.gemm_backend = 1 selects it for tests).
+// FFMA kernel.  Not on the product path: reachable through opb_debug_gemm only (arithmetic cross-check of the tcgen05 core).
 #include "gemm_common.cuh"
 
 namespace opb {
@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmProblem p) {
       if (p.bias) {
         o.x += p.bias[c]; o.y += p.bias[c + 1]; o.z += p.bias[c + 2]; o.w += p.bias[c + 3];
       }
-      if (c < p.elu_cols) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
       *reinterpret_cast<float4*>(cz + (long long)r * p.ldc + c) = o;
     }
   }

@@ -1,4 +1,4 @@
-// tcgen05 / TMA GEMM core for sm_100a -- persistent, warp-specialised, TMEM double-buffered.
+// tcgen05 / TMA GEMM core for sm_100a -- persistent, warp-specialised, 2-CTA UMMA, TMEM double-buffered.
 //
 //   C[128 x 256 tile] = sum_k A_tile . B_tile^T     A, B: fp16-split planes (hi, lo; common.cuh), K-major
 //
@@ -7,17 +7,18 @@
 // which reproduces fp32 products to ~2^-22 relative (tools/precision_ladder.py); the reference
 // computes in fp32 (GATs_SuperGlue.py:191-193) and the contract is 1e-4 abs on conf.
 //
-// Persistent grid (one CTA per SM), static round-robin tile schedule (n-tile fastest so CTAs that
-// share an A row-tile run together).  Default form: 2-CTA UMMA (cta_group::2, a CTA pair = two adjacent row tiles, each
-// CTA keeps half of the B tile), 384 threads:
-//   warp 0    TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B boxes -> 3-stage smem ring (64 KB per stage)
-//   warp 1    MMA issuer     one lane (leader CTA): tcgen05.mma kind::f16, tcgen05.commit -> mbarriers of both CTAs
-//   warp 2    TMEM owner     512 columns = 2 accumulator buffers x 256 (epilogue of tile i overlaps
-//                            the main loop of tile i+1)
-//   warps 4-11 epilogue      two groups of 4 warps (each group = the 4 TMEM lane quarters) splitting the tile's columns:
-//                            tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
-// Converter variants (ACV_*, 512 threads): warps 4-7 = one epilogue group, warps 8-15 = A-operand converters that turn a raw
-// fp32 tile landed by TMA into the (hi, lo) planes in place (see the ACV enum); setmaxnreg rebalances the registers.
+// Persistent grid (one CTA per SM), static round-robin tile schedule (n-tile fastest so CTAs that share an A row-tile run
+// together).  A CTA pair (cluster of 2, tcgen05 cta_group::2) works on two adjacent row tiles; each CTA keeps its own A tile
+// and HALF of the B tile in shared memory -- the shared-memory port, not the tensor pipe, limited the 1-CTA form.  384 threads:
+//   warp 0     TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B boxes -> 3-stage smem ring (64 KB per stage)
+//   warp 1     MMA issuer     one lane of the leader CTA: tcgen05.mma kind::f16, tcgen05.commit -> mbarriers of both CTAs
+//   warp 2     TMEM owner     512 columns = 2 accumulator buffers x 256 (epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 4-11 epilogue       two groups of 4 warps (each group = the 4 TMEM lane quarters) splitting the tile's columns:
+//                             tcgen05.ld -> registers -> fused op -> swizzled smem staging -> TMA store
+// Converter variant (ACV_NORM_RELU, 512 threads): warps 4-7 = one epilogue group, warps 8-15 = A-operand converters that turn a
+// raw fp32 tile landed by TMA into the (hi, lo) planes in place; setmaxnreg rebalances the registers.
+// Every kernel starts with griddepcontrol.wait after its on-chip set-up (programmatic dependent launch: the set-up of launch
+// i+1 overlaps the tail of launch i).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -31,31 +32,21 @@
 namespace opb {
 namespace {
 
-constexpr int BM = 128, BN = 256;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int UMMA_K = 16;
+constexpr int kStages = 3;
+constexpr int kABytes = BM * BK * 2;             // one plane of this CTA's A tile (16 KB)
+constexpr int kBBytes = (BN / 2) * BK * 2;       // one plane of this CTA's HALF of the B tile (16 KB)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
 constexpr int kStagingBytes = 16384;             // one 128-row x 128-B swizzled epilogue buffer
 constexpr int kNumStaging = 2;
-constexpr int kMaxStages = 6;
-// K-block configuration: BK fp16 per smem row = one swizzle row (64: SWIZZLE_128B, 2 stages of 96 KB;
-// 32: SWIZZLE_64B, 4 stages of 48 KB -- same bytes in flight, finer-grained ring).
-// TWO = 2-CTA UMMA (cta_group::2): each CTA of a pair keeps only HALF of the B tile in its smem and the pair's
-// tensor cores share it, which cuts the per-SM smem traffic (UMMA operand reads + TMA fills) from 240 KB to
-// 160 KB per 64-wide K-block -- the smem port, not the tensor pipe, was the measured limit of the 1-CTA form.
-template <int BK_, bool TWO = false>
-struct Cfg {
-  static constexpr int BK = BK_;
-  static constexpr int kStages = (BK_ == 64 ? 2 : 4) + (TWO ? (BK_ == 64 ? 1 : 2) : 0);
-  static constexpr int kABytes = BM * BK_ * 2;
-  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK_ * 2;     // B bytes resident per CTA
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint64_t kLayoutType = BK_ == 64 ? 2 : 4;      // UMMA LayoutType: SWIZZLE_128B / SWIZZLE_64B
-  static constexpr uint32_t kSBO = 8 * BK_ * 2;                   // bytes between 8-row groups
-};
+constexpr int kExtraBytes = 1024;                // per-tile scratch of the score epilogue (inverse column sums of the tile)
+constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + kExtraBytes;
+constexpr uint32_t kSBO = 8 * BK * 2;            // bytes between 8-row groups of a K-major SWIZZLE_128B operand
 constexpr int kTmemCols = 512;
 // warps 0-3: TMA / MMA / TMEM / spare.  Plain variants: warps 4-11 = two epilogue groups of 4 warps (384 threads).
-// Converter variants (ACV): warps 4-7 = one epilogue group, warps 8-15 = eight A-operand converter warps (512 threads,
-// 128 registers per thread at launch; the converters hand 24 registers each to the epilogue group via setmaxnreg).
+// Converter variant: warps 4-7 = one epilogue group, warps 8-15 = eight A-operand converter warps (512 threads, 128 registers
+// per thread at launch; the converters hand 24 registers each to the epilogue group via setmaxnreg).
 constexpr int threads_of(int acv) { return acv ? 512 : 384; }
 constexpr int kConvWarps = 8;
 constexpr int kConvRegs = 104, kEpiRegsAcv = 176;   // 128 + 176 + 2 x 104 = 512 = 4 warpgroups x 128
@@ -95,19 +86,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-// ---- 2-CTA (cta_group::2) forms
+// 2-CTA (cta_group::2) forms
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c_inner, int c_outer) {
   // data lands in THIS CTA's smem; the transaction bytes are credited to the leader CTA's mbarrier (peer bit cleared)
   asm volatile(
@@ -163,17 +142,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -183,17 +151,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-// 16 lanes x 32 columns: thread t holds rows (t/4, t/4+8), column pairs 8i + 2(t%4) + {0,1}, i = 0..3:
-//   r[4i+0..1] = (row t/4, cols 8i+2(t%4)+{0,1}),  r[4i+2..3] = (row t/4+8, same columns)
-__device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -214,32 +171,17 @@ __device__ __forceinline__ void epi_bar_id(int id) { asm volatile("bar.sync %0, 
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = bytes between 8-row groups | swizzle mode
-template <typename C>
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {   // C = Cfg<...>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(C::kSBO >> 4) << 32;
+  d |= (uint64_t)(kSBO >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= C::kLayoutType << 61;
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// MN-major, SWIZZLE_128B operand: atoms of 64 (MN, contiguous 128 B) x 8 (K rows); LBO = bytes between MN atoms
-// (here 8 KB: one 64-channel x 64-row TMA box per atom column), SBO = 1024 B between the 8-row K atoms.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the CTA pair
-constexpr uint32_t kIdesc2MN = kIdesc2 | (1u << 15) | (1u << 16);                                           // A and B MN-major
-
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M = 256 across the CTA pair, N = BN
+constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -249,23 +191,19 @@ __device__ __forceinline__ uint32_t stg64_off(int r, int j) { return (uint32_t)(
 struct TcParams {
   int K1, K2;            // reduction split (multiples of BK)
   int b2_per_seg;
+  int b2_lo_zero;        // skip the A_hi . B_lo pass of the K2 block (identity K-block: B_lo == 0)
   int n_out;
   int m_tiles, n_tiles, batch;
   long long a_batch_rows, b_batch_rows;
   int c_batch_rows;      // output rows per batch (C is [batch*rows, ldc])
+  int seg_rows;          // rows are rows of the activation layout L (segment-aware masking); 0: plain matrix
   Layout L;
   const float* bias;
-  int elu_cols;          // columns [0, elu_cols) get elu(x)+1 after the bias (K projection)
   long long* tl;         // optional timeline buffer (debug)
-  long long a_batch_k, b_batch_k;   // reduction-dimension offset per batch (KV-state GEMM)
   // fused epilogues
   const float* kmean;    // EPI_QSCALE
   int cross;
-  const __half* x_hi;    // EPI_RESID (ld = 256)
-  const __half* x_lo;
-  float* statpart;       // EPI_F32_STATS / EPI_KV
-  int mn_major;
-  int q_tiles;           // EPI_QKV
+  float* statpart;       // EPI_F32_STATS
   // A-operand converters (ACV)
   const float* mu;       // ACV_NORM_RELU: [S][512]
   const float* rstd;
@@ -276,7 +214,7 @@ struct TcParams {
   const float* inv_rowsum;
   const float* inv_colsum;
   float* conf;
-  int conf_tma;          // 1: conf goes out through the 3-D tensor map (M % 4 == 0), 0: per-thread stores
+  int conf_tma;          // 1: conf goes out through the 3-D tensor map (M % 4 == 0), 0: plain stores from the staged chunk
   unsigned long long* rowbest;
   unsigned long long* colbest;
 };
@@ -289,22 +227,14 @@ struct Maps {
 };
 
 // A-operand conversion: instead of fp16-split planes prepared by a separate kernel, the TMA producer lands the RAW fp32
-// tile (128 rows x 64 columns = exactly the 32 KB of the stage's A_hi + A_lo planes) and four converter warps rewrite it
+// tile (128 rows x 64 columns = exactly the 32 KB of the stage's A_hi + A_lo planes) and eight converter warps rewrite it
 // IN PLACE as the (hi, lo) planes the UMMA descriptors expect -- the pointwise op between two GEMMs runs on data that is
 // already on the SM, and its 4 KB/row HBM round trip disappears:
 //   ACV_NORM_RELU  A  = ReLU((hid - mu_seg) * rstd_seg)          mlp.3 reads mlp.0's fp32 output (GATs_SuperGlue.py:126-127)
-//   ACV_QSCALE     A2 = elu1(q) / (elu1(q) . Kmean_src + eps/m)  mlp.0 reads the raw Q projection   (:71,:78-79)
-enum { ACV_NONE = 0, ACV_NORM_RELU = 1, ACV_QSCALE = 2 };
+enum { ACV_NONE = 0, ACV_NORM_RELU = 1 };
 
-// CL = thread-block-cluster size along the row-tile dimension (1 or 2).  With CL = 2 the two CTAs of a
-// cluster work on adjacent row tiles of the same n-tile: each loads its own A tile and HALF of the shared
-// B tile, multicast into both CTAs' smem -- halving the per-SM L2 read traffic for the B operand.
-template <int BK_, int CL, bool TWO, int EPI, int ACV = ACV_NONE>
+template <int EPI, int ACV = ACV_NONE>
 __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
-  static_assert(!TWO || CL == 2, "2-CTA UMMA needs a 2-CTA cluster");
-  static_assert(ACV == ACV_NONE || TWO, "A-operand converters exist for the 2-CTA form only");
-  using C = Cfg<BK_, TWO>;
-  constexpr int BK = C::BK, kStages = C::kStages, kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + kStages * kStageBytes;
@@ -313,124 +243,93 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
   uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint64_t* raw_bar = tmem_empty_bar + 2;            // [kStages] raw fp32 A tile has landed (ACV)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(raw_bar + kMaxStages);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(raw_bar + kStages);
+  float* extra = reinterpret_cast<float*>(staging + kNumStaging * kStagingBytes + 256);   // kExtraBytes of per-tile scratch
 
   // Epilogue groups: the TMEM -> registers -> staging -> TMA-store chain of one 32-column chunk is a serial latency chain
   // (tcgen05.ld, two named barriers, proxy fence), so ONE group of 4 warps drains a 128 x 256 tile in ~8.5k cycles no matter
   // how little it computes.  Two groups (each: 4 warps = the 4 TMEM lane quarters) split the tile's columns and overlap
-  // their chains.  The score epilogues keep one group (their row accumulators span the whole tile).
-  // With A-operand converters, warps 8-11 convert and one group drains the accumulator.
-  constexpr int kEpiGroups = (TWO && ACV == ACV_NONE && EPI != EPI_SCORE_SUMS && EPI != EPI_SCORE_CONF) ? 2 : 1;
+  // their chains.  With A-operand converters, warps 8-15 convert and one group drains the accumulator.
+  constexpr int kEpiGroups = ACV == ACV_NONE ? 2 : 1;
   constexpr int kColsPerGroup = BN / kEpiGroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb1 = p.K1 / BK, nkb = (p.K1 + p.K2) / BK;
-  // work unit = CL adjacent row tiles x one n-tile; this CTA takes row tile (CL*mgroup + crank)
-  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int units_per_batch = (p.m_tiles / CL) * p.n_tiles;
+  // work unit = 2 adjacent row tiles x one n-tile; this CTA takes row tile (2*mgroup + crank)
+  const int crank = (int)cluster_ctarank();
+  const int units_per_batch = (p.m_tiles / 2) * p.n_tiles;
   const int total_units = units_per_batch * p.batch;
-  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  const int unit0 = blockIdx.x / 2, unit_step = gridDim.x / 2;
   long long* tl = p.tl ? p.tl + (long long)blockIdx.x * 64 : nullptr;
   if (tl && threadIdx.x == 0) tl[0] = clock64();
 
   if (threadIdx.x == 0) {
     // full: the TMA transaction arrive (+ with converters: one arrive per converter warp of BOTH CTAs, on the leader)
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 1 + 2 * kConvWarps : 1); mbar_init(&empty_bar[s], TWO ? 1 : CL); mbar_init(&raw_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], (TWO ? 8 : 4) * kEpiGroups); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 1 + 2 * kConvWarps : 1); mbar_init(&empty_bar[s], 1); mbar_init(&raw_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * kEpiGroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a1h); prefetch_tmap(&maps.a1l); prefetch_tmap(&maps.b1h); prefetch_tmap(&maps.b1l);
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
     if (ACV) prefetch_tmap(&maps.a_raw);
-    if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF || EPI == EPI_QKV) prefetch_tmap(&maps.out_f32);
-    if (EPI != EPI_F32 && EPI != EPI_F32_STATS && EPI != EPI_SCORE_CONF && EPI != EPI_SCORE_SUMS) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
+    if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF) prefetch_tmap(&maps.out_f32);
+    if (EPI == EPI_QKV || EPI == EPI_QSCALE || EPI == EPI_L2NORM || EPI == EPI_BIAS_PLANES) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
   if (warp == 2) {
-    if (TWO) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // peer barriers are initialised before any multicast can land
+  cluster_sync_all();                  // peer barriers are initialised before any remote arrive / 2-CTA load can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  griddep_sync();                      // results of the previous launch are visible from here on; let the next launch set up
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;   // k-block counter across all tiles of this CTA
-      constexpr int kBHalf = TWO ? kBBytes : kBBytes / CL;      // bytes of the B tile this CTA fetches
-      constexpr int kBRowsLoad = BN / CL;
+      constexpr int kBRowsLoad = BN / 2;
       for (int u = unit0; u < total_units; u += unit_step) {
         const int z = u / units_per_batch, rem = u - z * units_per_batch;
-        const int m_tile = (rem / p.n_tiles) * CL + crank, n_tile = rem % p.n_tiles;
+        const int m_tile = (rem / p.n_tiles) * 2 + crank, n_tile = rem % p.n_tiles;
         const int row0 = m_tile * BM;
         const int a_row = (int)(z * p.a_batch_rows) + row0;
         const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
-        const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // CL adjacent row tiles share a segment (segments are 256-row aligned)
+        const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // the pair's row tiles share a segment (segments are 256-row aligned)
         const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN + crank * kBRowsLoad;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           const bool first = kb < nkb1;
-          const bool conv = ACV == ACV_NORM_RELU ? first : (ACV == ACV_QSCALE && !first);   // this k-block's A tile comes in raw
-          if (!TWO) mbar_expect_tx(&full_bar[s], kStageBytes);
-          else if (crank == 0) mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);   // leader arms for both CTAs' loads
+          const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
+          if (crank == 0) mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);   // leader arms for both CTAs' loads
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
-          const int kca = kc + (int)(z * p.a_batch_k), kcb = kc + (int)(z * p.b_batch_k);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
           const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
-          if (TWO && p.mn_major) {
-            // operands are row-major [reduction row][channel] planes: box = 64 channels x 64 rows, two boxes per 128 channels
-            const int ach = m_tile * BM, bch = n_tile * BN + crank * kBRowsLoad;
-#pragma unroll
-            for (int bx = 0; bx < 2; ++bx) {
-              tma_load_2d_2sm(st + bx * 8192, mah, &full_bar[s], ach + bx * 64, kca);
-              tma_load_2d_2sm(st + kABytes + bx * 8192, mal, &full_bar[s], ach + bx * 64, kca);
-              tma_load_2d_2sm(st + 2 * kABytes + bx * 8192, mbh, &full_bar[s], bch + bx * 64, kcb);
-              tma_load_2d_2sm(st + 2 * kABytes + kBBytes + bx * 8192, mbl, &full_bar[s], bch + bx * 64, kcb);
-            }
-            continue;
-          }
-          if (TWO) {
-            if (conv) {
-              // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
-              mbar_expect_tx(&raw_bar[s], 2 * kABytes);
-              tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
-              if (BK == 64) tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
-            } else {
-              tma_load_2d_2sm(st, mah, &full_bar[s], kca, a_row);
-              tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kca, a_row);
-            }
-            tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kcb, brow);
-            tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kcb, brow);
-            continue;
-          }
-          tma_load_2d(st, mah, &full_bar[s], kca, a_row);
-          tma_load_2d(st + kABytes, mal, &full_bar[s], kca, a_row);
-          if (CL == 1) {
-            tma_load_2d(st + 2 * kABytes, mbh, &full_bar[s], kcb, brow);
-            tma_load_2d(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kcb, brow);
+          if (conv) {
+            // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
+            mbar_expect_tx(&raw_bar[s], 2 * kABytes);
+            tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
+            tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
           } else {
-            tma_load_2d_mc(st + 2 * kABytes + crank * kBHalf, mbh, &full_bar[s], kcb, brow, (uint16_t)0x3);
-            tma_load_2d_mc(st + 2 * kABytes + kBBytes + crank * kBHalf, mbl, &full_bar[s], kcb, brow, (uint16_t)0x3);
+            tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
+            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
           }
+          tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
+          tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (2-CTA mode: the leader CTA issues for the pair) =====================
-    if (lane == 0 && (!TWO || crank == 0)) {
+    // ===================== MMA issuer (the leader CTA issues for the pair) =====================
+    if (lane == 0 && crank == 0) {
       uint32_t it = 0, tc = 0;
       for (int u = unit0; u < total_units; u += unit_step, ++tc) {
         const uint32_t buf = tc & 1;
@@ -444,34 +343,19 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           tc_fence_after();
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
           const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + 2 * kABytes, sb_l = sb_h + kBBytes;
+          const bool skip_lo = p.b2_lo_zero && kb >= nkb1;          // B_lo == 0: the A_hi.B_lo pass adds exact zeros
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
-            const uint64_t ah = make_desc<C>(sa_h + koff), al = make_desc<C>(sa_l + koff);
-            const uint64_t bh = make_desc<C>(sb_h + koff), bl = make_desc<C>(sb_l + koff);
-            if (TWO && p.mn_major) {
-              const uint32_t ko = k * 2048;         // 16 reduction rows = two 8-row atoms
-              const uint64_t mah_ = make_desc_mn(sa_h + ko), mal_ = make_desc_mn(sa_l + ko);
-              const uint64_t mbh_ = make_desc_mn(sb_h + ko), mbl_ = make_desc_mn(sb_l + ko);
-              tc_mma_f16_2sm(d, mah_, mbh_, kIdesc2MN, (uint32_t)((kb | k) != 0));
-              tc_mma_f16_2sm(d, mah_, mbl_, kIdesc2MN, 1u);
-              tc_mma_f16_2sm(d, mal_, mbh_, kIdesc2MN, 1u);
-            } else if (TWO) {
-              tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
-              tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
-              tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
-            } else {
-              tc_mma_f16(d, ah, bh, kIdesc, (uint32_t)((kb | k) != 0));
-              tc_mma_f16(d, ah, bl, kIdesc, 1u);
-              tc_mma_f16(d, al, bh, kIdesc, 1u);
-            }
+            const uint64_t ah = make_desc(sa_h + koff), al = make_desc(sa_l + koff);
+            const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
+            tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
+            if (!skip_lo) tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
+            tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
           }
-          if (TWO) tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);   // frees the stage in both CTAs
-          else if (CL == 1) tc_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
-          else tc_commit_mc(&empty_bar[s], (uint16_t)0x3);        // ... in BOTH CTAs (the peer multicasts into our stage)
+          tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);              // frees the stage in both CTAs
         }
-        if (TWO) tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);   // accumulator halves complete in both CTAs
-        else tc_commit(&tmem_full_bar[buf]);                          // accumulator complete
+        tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);          // accumulator halves complete in both CTAs
       }
     }
   } else if (ACV != ACV_NONE && warp >= 8) {
@@ -481,37 +365,27 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     // the only ordering needed.  Lane = (row 4i + lane/8, 8-column group c = lane%8): reads raw chunks 2c', 2c'+1 of box c/4,
     // writes chunk c of both planes -- every shared-memory instruction touches each bank group exactly once per wavefront.
     reg_dec<kConvRegs>();
-    constexpr int kLPR = BK / 8;                     // lanes per row = 8-column groups per k-block (8 at BK 64, 4 at BK 32)
+    constexpr int kLPR = BK / 8;                     // lanes per row = 8-column groups per k-block
     constexpr int kRPI = 32 / kLPR;                  // rows per shared-memory instruction
     constexpr int kRowIters = BM / kConvWarps / kRPI;
     const int cw = warp - 8;
     const int c = lane % kLPR, rsub = lane / kLPR;
-    // BK 64: raw box b (32 fp32 columns) and plane b coincide byte for byte, row by row -> warp-local hazard only.
-    // BK 32: the raw tile is one 16 KB box (128-byte rows) and the planes are two 8 KB halves of it (64-byte rows,
-    // SWIZZLE_64B): rows move, so ALL converter warps finish reading before any of them writes (named barrier 3).
-    auto plane_off = [](int r, int cc) { return BK == 64 ? stg_off(r, cc) : stg64_off(r, cc); };
     // proxy fence + plain (remote) arrive on the leader's barrier -- the pattern CUTLASS's 2-SM transform warps use.  A
     // .release.cluster arrive compiles to MEMBAR.ALL.GPU and costs ~4k cycles per k-block (measured).
     auto conv_arrive = [crank](uint64_t* bar) {
-      if (TWO && crank != 0) mbar_arrive_remote(bar, 0);
+      if (crank != 0) mbar_arrive_remote(bar, 0);
       else mbar_arrive(bar);
     };
     uint32_t it = 0, raw_phase = 0, tidx = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++tidx) {
       const int z = u / units_per_batch, rem = u - z * units_per_batch;
-      const int m_tile = (rem / p.n_tiles) * CL + crank;
+      const int m_tile = (rem / p.n_tiles) * 2 + crank;
       const int row0 = m_tile * BM;
       const int seg = p.L.seg_of_row(row0);
-      int src = 0;
-      float eps_m = 0.f;
-      if (ACV == ACV_QSCALE) {
-        src = p.L.src_seg(seg, p.cross);
-        eps_m = 1e-6f / (float)max(p.L.seg_valid(src), 1);
-      }
       (void)z;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % kStages;
-        const bool conv = ACV == ACV_NORM_RELU ? kb < nkb1 : kb >= nkb1;
+        const bool conv = kb < nkb1;
         if (!conv) {
           // plain TMA k-block: nothing to convert, but the barrier's arrival count is fixed -- arrive once the stage's
           // previous use has been consumed (so the arrival lands in the right phase)
@@ -522,20 +396,18 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         }
         const uint32_t st = smem_u32(smem) + s * kStageBytes;
         const uint32_t rawbox = st + ((2 * c) >> 3) * (BM * 128);
-        const int kcol = (ACV == ACV_NORM_RELU ? kb : kb - nkb1) * BK + 8 * c;     // first of this lane's 8 source columns
-        float pa[8], pb[8];                // per-column parameters: (mu, rstd) or (Kmean, -)
+        const int kcol = kb * BK + 8 * c;            // first of this lane's 8 source columns
+        float pa[8], pb[8];                          // per-column parameters: (-64 mu rstd, 64 rstd)
         {
-          const float* base_a = ACV == ACV_NORM_RELU ? p.mu + (long long)seg * 512 + kcol : p.kmean + (long long)src * kD + kcol;
+          const float* base_a = p.mu + (long long)seg * 512 + kcol;
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(base_a)), a1 = __ldg(reinterpret_cast<const float4*>(base_a) + 1);
           pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
-          if (ACV == ACV_NORM_RELU) {
-            const float* base_b = p.rstd + (long long)seg * 512 + kcol;
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(base_b)), b1 = __ldg(reinterpret_cast<const float4*>(base_b) + 1);
-            pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
-            // 64 * ReLU((h - mu) * rstd) = max(h * (64 rstd) - 64 mu rstd, 0): one FFMA + one FMNMX per element, pre-scale included
+          const float* base_b = p.rstd + (long long)seg * 512 + kcol;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(base_b)), b1 = __ldg(reinterpret_cast<const float4*>(base_b) + 1);
+          pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+          // 64 * ReLU((h - mu) * rstd) = max(h * (64 rstd) - 64 mu rstd, 0): one FFMA + one FMNMX per element, pre-scale included
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { pb[j] *= kPre; pa[j] = -pa[j] * pb[j]; }
-          }
+          for (int j = 0; j < 8; ++j) { pb[j] *= kPre; pa[j] = -pa[j] * pb[j]; }
         }
         mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
         raw_phase ^= 1u << s;
@@ -547,27 +419,13 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           ra[i] = lds128(rawbox + r * 128 + ((((2 * c) & 7) ^ (r & 7)) << 4));
           rb[i] = lds128(rawbox + r * 128 + ((((2 * c + 1) & 7) ^ (r & 7)) << 4));
         }
-        if (BK == 64) __syncwarp();        // every lane holds its raw values before any lane overwrites them
-        else asm volatile("bar.sync 3, %0;" ::"n"(kConvWarps * 32) : "memory");
+        __syncwarp();                      // every lane holds its raw values before any lane overwrites them
 #pragma unroll
         for (int i = 0; i < kRowIters; ++i) {
           const int r = cw * (BM / kConvWarps) + kRPI * i + rsub;
           float v[8] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w, rb[i].x, rb[i].y, rb[i].z, rb[i].w};
-          if (ACV == ACV_NORM_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], pb[j], pa[j]), 0.f);     // already x 2^6
-          } else {
-            // one k-block = one head: the row's normaliser is a dot product over the 8 lanes that share the row
-            float dot = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] = elu1_fast(v[j]); dot = fmaf(v[j], pa[j], dot); }
-            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-            const float zf = 1.f / (dot + eps_m);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= zf * kPre;
-          }
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], pb[j], pa[j]), 0.f);     // already x 2^6
           uint4 oh, ol;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {    // same rounding as split_f32, two elements per conversion instruction
@@ -578,12 +436,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             reinterpret_cast<__half2*>(&oh)[j] = h2;
             reinterpret_cast<__half2*>(&ol)[j] = l2;
           }
-          sts128(st + plane_off(r, c), oh);
-          sts128(st + kABytes + plane_off(r, c), ol);
+          sts128(st + stg_off(r, c), oh);
+          sts128(st + kABytes + stg_off(r, c), ol);
         }
-        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb == 3) tl[56] = clock64();
         fence_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
-        if (tl && cw == 0 && lane == 0 && tidx == 1 && kb == 3) tl[57] = clock64();
         __syncwarp();
         if (lane == 0) conv_arrive(&full_bar[s]);
         if (tl && cw == 0 && lane == 0 && tidx == 1 && kb < 8) tl[4 + 2 * kb] = clock64();
@@ -610,7 +466,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     uint32_t tc = 0, chunk_ctr = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++tc) {
       const int z = u / units_per_batch, rem = u - z * units_per_batch;
-      const int m_tile = (rem / p.n_tiles) * CL + crank, n_tile = rem % p.n_tiles;
+      const int m_tile = (rem / p.n_tiles) * 2 + crank, n_tile = rem % p.n_tiles;
       const uint32_t buf = tc & 1;
       mbar_wait(&tmem_full_bar[buf], (tc >> 1) & 1);
       if (tl && threadIdx.x == 128 && tc < 8) tl[40 + 2 * tc] = clock64();
@@ -620,12 +476,12 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       const int row0 = m_tile * BM;                               // within the batch
       int n_valid = BM;                                           // valid rows of this tile (segment-aware launches)
       int seg = 0;
-      if (p.L.R > 0) {
+      if (p.seg_rows) {
         seg = p.L.seg_of_row(row0);
         n_valid = p.L.seg_valid(seg) - (row0 - p.L.seg_start(seg));
       }
-      if (EPI == EPI_F32 || EPI == EPI_F32_STATS || (EPI == EPI_QKV && n_tile < p.q_tiles)) {
-        // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk, double-buffered staging
+      if (EPI == EPI_F32 || EPI == EPI_F32_STATS) {
+        // ---- fp32 tile out through swizzled staging + TMA store, 32 columns per chunk
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
@@ -646,7 +502,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             }
-            if (col0 < p.elu_cols) { o.x = elu1_fast(o.x); o.y = elu1_fast(o.y); o.z = elu1_fast(o.z); o.w = elu1_fast(o.w); }
             *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = o;
           }
           fence_async_smem();
@@ -671,24 +526,20 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           }
         }
       } else if (EPI == EPI_QKV) {
-        // ---- [K | V] tiles of the q,k,v projection -> one fp16 plane (x 2^6), 64 columns per chunk (128-byte staging rows).
+        // ---- [K | V] tiles of the k,v projection -> one fp16 plane (x 2^6), 64 columns per chunk (128-byte staging rows).
         // elu+1 on K (GATs_SuperGlue.py:71-72); pad rows are zeroed so the state kernel needs no row masks.
-        const bool is_k = n_tile == p.q_tiles;
+        const bool is_k = n_tile == 0;
         const bool row_ok = r_in_tile < n_valid;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 64, ++chunk_ctr) {
-          const bool stamp = tl && threadIdx.x == 128 && tc == 2 && c0 == c_begin + 64;
-          if (stamp) tl[3] = clock64();
           uint32_t v0[32], v1[32];
           tmem_ld32(lane_base + c0, v0);
           tmem_ld32(lane_base + c0 + 32, v1);
           tmem_ld_wait();
-          if (stamp) tl[4] = clock64();
           const int col0 = n_tile * BN + c0;
           uint8_t* sb = staging + stage_sel(chunk_ctr) * kStagingBytes;
           stage_wait();
           epi_bar();
-          if (stamp) tl[5] = clock64();
 #pragma unroll
           for (int j8 = 0; j8 < 8; ++j8) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
@@ -707,48 +558,84 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             for (int e = 0; e < 4; ++e) reinterpret_cast<__half2*>(&o)[e] = __float22half2_rn(make_float2(x[2 * e], x[2 * e + 1]));
             *reinterpret_cast<uint4*>(sb + stg_off(r_in_tile, j8)) = o;
           }
-          if (stamp) tl[6] = clock64();
           fence_async_smem();
           epi_bar();
           if (leader) {
-            tma_store_2d(&maps.out_hi, sb, col0 - p.q_tiles * BN, out_row0);
+            tma_store_2d(&maps.out_hi, sb, col0, out_row0);
             tma_store_commit();
           }
-          if (stamp) tl[7] = clock64();
         }
-      } else if (EPI == EPI_SCORE_SUMS || EPI == EPI_SCORE_CONF) {
-        // ---- dual-softmax tail (reference GATs_SuperGlue.py:217-223).  Unit-norm operands: cos <= 1, so with the fixed
-        // shift  e = exp((cos - 1)/scale)  softmax(s,1)*softmax(s,2) = e^2 / (colsum*rowsum)  needs no running max.
-        const int N = p.L.N, M = p.L.M;
+      } else if (EPI == EPI_SCORE_SUMS) {
+        // ---- dual-softmax tail, pass 1 (reference GATs_SuperGlue.py:217-218).  Unit-norm operands: cos <= 1, so with the
+        // fixed shift  e = exp((cos - 1)/scale)  softmax(s,1)*softmax(s,2) = e^2 / (colsum*rowsum)  needs no running max.
+        // Nothing is stored but the partial sums: row sums per (tile half, row) in registers; column sums over the warp's 32
+        // rows by a transposing butterfly (31 shuffles per 32 x 32 block, no shared memory, no barriers).
+        const int Nz = p.L.n_of(z), M = p.L.M;
         const int row = row0 + r_in_tile;                          // query index inside frame z
-        const bool row_ok = row < N;
-        const int t = t_in_grp, qq = t >> 5, cc = t & 31;          // column-pass role: (32-row quarter, column)
-        float rs = 0.f;                                            // SUMS: row sum over this tile's columns
-        float irs = 0.f;
-        unsigned long long rbest = 0ull;
-        if (EPI == EPI_SCORE_CONF && row_ok) irs = __ldg(p.inv_rowsum + (long long)z * p.L.n_pad + row);
+        const bool row_ok = row < Nz;
+        const float ea = kProdInv * p.inv_scale * 1.4426950408889634f, eb = -p.inv_scale * 1.4426950408889634f;
+        float rs = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_ctr) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(lane_base + c0, v);
           tmem_ld_wait();
           const int col0 = n_tile * BN + c0;
-          uint8_t* sb = staging + (chunk_ctr & 1) * kStagingBytes;
-          if (EPI == EPI_SCORE_CONF && p.conf_tma) {
-            if (leader) tma_store_wait_read<1>();
-            epi_bar();
-          }
-          float o[32];
+          float e[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool ok = row_ok && (col0 + j) < M;
-            const float e = ok ? exp_fast((__uint_as_float(v[j]) * kProdInv - 1.f) * p.inv_scale) : 0.f;
-            if (EPI == EPI_SCORE_SUMS) {
-              o[j] = e;
-              rs += e;
-            } else {
-              const float ics = ok ? __ldg(p.inv_colsum + (long long)z * p.L.m_pad + col0 + j) : 0.f;
-              const float c = (e * irs) * (e * ics);
+            e[j] = ok ? ex2_fast(fmaf(__uint_as_float(v[j]), ea, eb)) : 0.f;
+            rs += e[j];
+          }
+          // after the butterfly lane l holds the sum over the warp's 32 rows of column col0 + l
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float keep = up ? e[i + off] : e[i];
+              const float send = up ? e[i] : e[i + off];
+              e[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          p.colsum_part[((long long)z * (p.m_tiles * 4) + m_tile * 4 + q) * p.L.m_pad + col0 + lane] = e[0];
+        }
+        p.rowsum_part[((long long)z * (p.n_tiles * 2) + n_tile * 2 + grp) * p.L.n_pad + row] = rs;
+      } else if (EPI == EPI_SCORE_CONF) {
+        // ---- dual-softmax tail, pass 2: conf = (e / rowsum) * (e / colsum) recomputed from the accumulator (the cos matrix is
+        // never materialised), optional conf store, packed row / column arg-max (reference :218-220).  The 32-column chunk is
+        // staged once in shared memory: it feeds the TMA store of conf and the per-column scan of the arg-max.
+        const int Nz = p.L.n_of(z), M = p.L.M;
+        const int row = row0 + r_in_tile;
+        const bool row_ok = row < Nz;
+        const float ea = kProdInv * p.inv_scale * 1.4426950408889634f, eb = -p.inv_scale * 1.4426950408889634f;
+        const int t = t_in_grp, qq = t >> 5, cc = t & 31;          // column-scan role: (32-row quarter, column)
+        const float irs = row_ok ? __ldg(p.inv_rowsum + (long long)z * p.L.n_pad + row) : 0.f;
+        float* ics = extra + grp * kColsPerGroup;                   // this tile half's inverse column sums
+        epi_bar();                                                  // every thread of the group is done with the previous tile's values
+        ics[t] = __ldg(p.inv_colsum + (long long)z * p.L.m_pad + n_tile * BN + c_begin + t);
+        epi_bar();
+        unsigned long long rbest = 0ull;
+        const bool store_plain = p.conf != nullptr && !p.conf_tma;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sb = staging + grp * kStagingBytes;
+          float o[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 ic4 = *reinterpret_cast<const float4*>(ics + (c0 - c_begin) + 4 * j4);   // broadcast read
+            const float icv[4] = {ic4.x, ic4.y, ic4.z, ic4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * j4 + jj;
+              const bool ok = row_ok && (col0 + j) < M;
+              const float e = ok ? ex2_fast(fmaf(__uint_as_float(v[j]), ea, eb)) : 0.f;
+              const float c = (e * irs) * (e * icv[jj]);
               o[j] = c;
               if (ok) {
                 const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(col0 + j));
@@ -756,46 +643,40 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               }
             }
           }
+          if (p.conf_tma && leader) tma_store_wait_read<0>();       // the store that last read this group's buffer is done with it
+          epi_bar();                                                // ... and every thread has finished scanning the previous chunk
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(sb + stg_off(r_in_tile, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          if (EPI == EPI_SCORE_CONF && p.conf && !p.conf_tma && row_ok) {
-            float* dst = p.conf + ((long long)z * N + row) * M + col0;
-            for (int j = 0; j < 32 && col0 + j < M; ++j) dst[j] = o[j];
-          }
-          if (EPI == EPI_SCORE_CONF && p.conf_tma) fence_async_smem();
+          if (p.conf_tma) fence_async_smem();
           epi_bar();
-          if (EPI == EPI_SCORE_CONF && p.conf_tma && p.conf && leader) {
-            tma_store_3d(&maps.out_f32, sb, col0, row0, z);       // rows >= N and columns >= M are clipped by the tensor map
+          if (p.conf_tma && leader) {
+            tma_store_3d(&maps.out_f32, sb, col0, row0, z);         // rows >= N and columns >= M are clipped by the tensor map
             tma_store_commit();
           }
-          // column pass over the staged 128 x 32 chunk
+          // column scan over the staged 128 x 32 chunk: thread (qq, cc) = rows [32 qq, +32) of column col0 + cc
           const int col = col0 + cc;
           if (col < M) {
-            if (EPI == EPI_SCORE_SUMS) {
-              float sum = 0.f;
-#pragma unroll 8
-              for (int i = 0; i < 32; ++i) sum += *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
-              p.colsum_part[((long long)z * (p.m_tiles * 4) + m_tile * 4 + qq) * p.L.m_pad + col] = sum;
-            } else {
-              unsigned long long cbest = 0ull;
-              const int r_end = min(32, N - (row0 + qq * 32));
-              for (int i = 0; i < r_end; ++i) {
-                const float c = *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
-                const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row0 + qq * 32 + i));
-                cbest = pk > cbest ? pk : cbest;
-              }
-              if (cbest) atomicMax(p.colbest + (long long)z * M + col, cbest);
+            unsigned long long cbest = 0ull;
+            const int r_first = row0 + qq * 32;
+            const int r_end = min(32, Nz - r_first);
+            float* crow = store_plain ? p.conf + ((long long)z * p.L.N + r_first) * M + col : nullptr;
+            for (int i = 0; i < r_end; ++i) {
+              const float c = *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
+              if (store_plain) crow[(long long)i * M] = c;          // 32 consecutive columns of one row per warp instruction
+              const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(r_first + i));
+              cbest = pk > cbest ? pk : cbest;
             }
+            if (store_plain)                                        // ragged batch: rows [Nz, N) of the frame are defined as zero
+              for (int i = max(r_end, 0); i < 32 && r_first + i < p.L.N; ++i) crow[(long long)i * M] = 0.f;
+            if (cbest) atomicMax(p.colbest + (long long)z * M + col, cbest);
           }
         }
-        if (EPI == EPI_SCORE_SUMS) {
-          p.rowsum_part[((long long)z * p.n_tiles + n_tile) * p.L.n_pad + row] = rs;
-        } else if (row_ok && rbest) {
-          atomicMax(p.rowbest + (long long)z * N + row, rbest);
-        }
+        if (row_ok && rbest) atomicMax(p.rowbest + (long long)z * p.L.N + row, rbest);
       } else if (EPI == EPI_BIAS_PLANES) {
-        // ---- out planes = acc + bias, 32 columns per chunk (the residual already sits in the accumulator: identity K-block)
+        // ---- out planes = acc + bias, 32 columns per chunk (a residual, if any, already sits in the accumulator: identity
+        // K-block); rows past the segment's valid count are written as zero so that padding never accumulates state
+        const bool row_ok = r_in_tile < n_valid;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
@@ -808,14 +689,18 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           epi_bar();
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            }
             uint4 oh, ol;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {    // same rounding as split_f32, two elements per conversion instruction
-              const float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kPreInv, bb[2 * e] * kPre),
-                                            fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kPreInv, bb[2 * e + 1] * kPre));
+              float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kPreInv, bb[2 * e] * kPre),
+                                      fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kPreInv, bb[2 * e + 1] * kPre));
+              if (!row_ok) sc = make_float2(0.f, 0.f);
               const __half2 h2 = __float22half2_rn(sc);
               const float2 back = __half22float2(h2);
               reinterpret_cast<__half2*>(&oh)[e] = h2;
@@ -832,97 +717,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tma_store_commit();
           }
         }
-      } else if (EPI == EPI_RESID) {
-        // ---- x += delta (reference GATs_SuperGlue.py:59,64), in place on the fp16-split planes, 32 columns per chunk.
-        // The old x values come in with COALESCED loads (lane = (row 8i + lane/4, 16-byte piece lane%4): 8 rows x 64 B per
-        // instruction -- a thread-per-row load touches 32 lines per instruction and made this epilogue LSU-bound), are parked
-        // in the staging buffer at their final swizzled position, and each thread then reads / updates / rewrites its own row
-        // there.  A warp only touches the rows it owns, so __syncwarp is the only extra ordering.  Loads for the next chunk are
-        // issued before the current chunk is processed.
-        const int wrow = q * 32;                                    // first tile row of this warp
-        const int lrow = lane >> 2, lpiece = lane & 3;
-        const __half* xh_base = p.x_hi + (long long)(out_row0 + wrow + lrow) * kD + n_tile * BN + lpiece * 8;
-        const __half* xl_base = p.x_lo + (long long)(out_row0 + wrow + lrow) * kD + n_tile * BN + lpiece * 8;
-        if (u + unit_step < total_units) {
-          // This CTA's NEXT tile: pull the x rows into L2 now.  Every chunk ends with a proxy fence (MEMBAR) that waits for
-          // the thread's outstanding loads, so the register prefetch below can never hide more than one chunk of latency --
-          // it has to find its data in L2, not in HBM.
-          const int un = u + unit_step;
-          const int zn = un / units_per_batch, remn = un - zn * units_per_batch;
-          const long long rown = (long long)zn * p.c_batch_rows + ((remn / p.n_tiles) * CL + crank) * BM + r_in_tile;
-          const int coln = (remn % p.n_tiles) * BN + c_begin;
-#pragma unroll
-          for (int cb = 0; cb < kColsPerGroup * 2; cb += 128) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x_hi + rown * kD + coln) + cb));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x_lo + rown * kD + coln) + cb));
-          }
-        }
-        uint4 xh[4], xl[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xh[i] = *reinterpret_cast<const uint4*>(xh_base + (long long)(8 * i) * kD + c_begin);
-          xl[i] = *reinterpret_cast<const uint4*>(xl_base + (long long)(8 * i) * kD + c_begin);
-        }
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
-          const bool stamp = tl && threadIdx.x == 128 && tc == 1 && c0 == c_begin + 64;
-          if (stamp) tl[58] = clock64();
-          uint32_t v[32];
-          tmem_ld32(lane_base + c0, v);
-          const int col0 = n_tile * BN + c0;
-          uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
-          uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
-          stage_wait();
-          epi_bar();
-          if (stamp) tl[59] = clock64();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            *reinterpret_cast<uint4*>(sh + stg64_off(wrow + 8 * i + lrow, lpiece)) = xh[i];
-            *reinterpret_cast<uint4*>(sl + stg64_off(wrow + 8 * i + lrow, lpiece)) = xl[i];
-          }
-          if (c0 + 32 < c_end) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              xh[i] = *reinterpret_cast<const uint4*>(xh_base + (long long)(8 * i) * kD + c0 + 32);
-              xl[i] = *reinterpret_cast<const uint4*>(xl_base + (long long)(8 * i) * kD + c0 + 32);
-            }
-          }
-          tmem_ld_wait();
-          __syncwarp();
-          if (stamp) tl[60] = clock64();
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const uint4 oh_in = *reinterpret_cast<const uint4*>(sh + stg64_off(r_in_tile, j8));
-            const uint4 ol_in = *reinterpret_cast<const uint4*>(sl + stg64_off(r_in_tile, j8));
-            const __half* hh = reinterpret_cast<const __half*>(&oh_in);
-            const __half* hl = reinterpret_cast<const __half*>(&ol_in);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint4 oh, ol;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float xn = fmaf(__uint_as_float(v[j8 * 8 + e]), kProdInv, bb[e]) + join_f32(hh[e], hl[e]);
-              __half h, l;
-              split_f32(xn, h, l);
-              reinterpret_cast<__half*>(&oh)[e] = h;
-              reinterpret_cast<__half*>(&ol)[e] = l;
-            }
-            *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
-            *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
-          }
-          if (stamp) tl[61] = clock64();
-          fence_async_smem();
-          if (stamp) tl[62] = clock64();
-          epi_bar();
-          if (leader) {
-            tma_store_2d(&maps.out_hi, sh, col0, out_row0);
-            tma_store_2d(&maps.out_lo, sl, col0, out_row0);
-            tma_store_commit();
-          }
-        }
       } else {
-        // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_RESID / EPI_L2NORM / EPI_KV
+        // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_L2NORM
         float inv_norm = 1.f;
         if (EPI == EPI_L2NORM) {                    // F.normalize: first pass over the accumulator for the row norm
           float ss = 0.f;
@@ -964,24 +760,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const float zf = 1.f / (dot + eps_m);
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= zf;
-          } else if (EPI == EPI_RESID) {
-            const long long g = (long long)(out_row0 + r_in_tile) * kD + col0;
-#pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
-              const uint4 uh = *reinterpret_cast<const uint4*>(p.x_hi + g + j8 * 8);
-              const uint4 ul = *reinterpret_cast<const uint4*>(p.x_lo + g + j8 * 8);
-              const __half* hh = reinterpret_cast<const __half*>(&uh);
-              const __half* hl = reinterpret_cast<const __half*>(&ul);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[j8 * 8 + e] += join_f32(hh[e], hl[e]);
-            }
-          } else if (EPI == EPI_KV) {
-            const bool row_ok = r_in_tile < n_valid;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              if (col0 < p.elu_cols) x[j] = elu1(x[j]);
-              if (!row_ok) x[j] = 0.f;              // pad rows must not reach the K^T V reduction or the K mean
-            }
           } else {  // EPI_L2NORM
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= inv_norm;
@@ -1014,17 +792,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               tma_store_2d(&maps.out_lo, sl, col0 + sc * 32, out_row0);
               tma_store_commit();
             }
-            if (EPI == EPI_KV && col0 < p.elu_cols) {
-              // K mean of the linear attention: per-32-row column sums of elu1(K) from the staged planes
-              const int t = t_in_grp, qq = t >> 5, cc = t & 31;                // thread = (quarter, column)
-              float s0 = 0.f;
-#pragma unroll 8
-              for (int i = 0; i < 32; ++i) {
-                const uint32_t off = stg64_off(qq * 32 + i, cc >> 3) + (cc & 7) * 2;
-                s0 += join_f32(*reinterpret_cast<const __half*>(sh + off), *reinterpret_cast<const __half*>(sl + off));
-              }
-              p.statpart[(long long)(out_row0 / 32 + qq) * 256 + col0 + sc * 32 + cc] = s0;
-            }
           }
         }
       }
@@ -1032,7 +799,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (TWO && crank != 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // the leader's MMA warp waits for both CTAs
+        if (crank != 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tmem_empty_bar[buf]);
       }
       if (tl && threadIdx.x == 128 && tc < 8) tl[41 + 2 * tc] = clock64();
@@ -1040,12 +807,11 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     if (leader) tma_store_wait_all();
   }
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  cluster_sync_all();                  // no CTA leaves while its peer may still land loads in it / arrive on its barriers
   if (tl && threadIdx.x == 0) { tl[2] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[63] = sm; }
   if (warp == 2) {
     tc_fence_after();
-    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -1092,7 +858,8 @@ bool make_map(CUtensorMap* out, const void* ptr, long long rows, long long cols,
 }
 
 // conf [B][N][M] fp32 as a 3-D tensor (box 32 x 128 x 1, SWIZZLE_128B): a 128-row tile that hangs over the end of a
-// frame (rows >= N) or of a row (columns >= M) is clipped by the hardware.  Needs M % 4 == 0 (16-byte global strides).
+// frame (rows >= N) or of a row (columns >= M) is clipped by the hardware.  Needs M % 4 == 0 (16-byte global strides)
+// and a 16-byte aligned base.
 bool make_map3(CUtensorMap* out, const float* ptr, int M, int N, int B) {
   EncodeFn enc = get_encode();
   if (!enc) return false;
@@ -1114,17 +881,15 @@ int num_sms() {
   return n;
 }
 
-template <int CL, bool TWO, int EPI, int ACV = ACV_NONE, int BKV = 64>
-cudaError_t launch_variant(const cudaLaunchConfig_t& cfg0, const Maps& mp, const TcParams& tp) {
+template <int EPI, int ACV = ACV_NONE>
+cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const Maps& mp, const TcParams& tp) {
   static bool attr_done = false;
-  auto* kern = gemm_tc_kernel<BKV, CL, TWO, EPI, ACV>;
+  auto* kern = gemm_tc_kernel<EPI, ACV>;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BKV, TWO>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  cudaLaunchConfig_t cfg = cfg0;
-  cfg.dynamicSmemBytes = Cfg<BKV, TWO>::kSmemBytes;
   return cudaLaunchKernelEx(&cfg, kern, mp, tp);
 }
 
@@ -1134,60 +899,28 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
   return make_map(out, ptr, rows, cols, ld, box_cols, box_rows, f32);
 }
 
-static int g_cluster = 0;   // 0 = undecided; 1 = no cluster, 2 = multicast B (1-CTA MMA), 3 = 2-CTA MMA (default)
-
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
-  if (!g_cluster) {
-    const char* c = getenv("OPB_GEMM_CLUSTER");
-    g_cluster = c ? atoi(c) : 3;
-    if (g_cluster < 1 || g_cluster > 3) g_cluster = 3;
-  }
-  static int g_acv_bk = 0;
-  if (!g_acv_bk) {
-    const char* c = getenv("OPB_ACV_BK");
-    g_acv_bk = (c && atoi(c) == 32) ? 32 : 64;
-  }
-  // converter variants: a 32-wide K-block / 6-stage form exists (OPB_ACV_BK=32; the raw-tile round trip -- TMA flight, conversion,
-  // MMA -- is a latency chain per stage) but measured slightly slower end to end than 64-wide / 3 stages (3274 vs 3365 frames/s)
-  const int BK = (p.a_conv == ACV_NORM_RELU && p.epi == EPI_BIAS_PLANES) ? g_acv_bk : 64;
-  const bool even = (p.rows / BM) % 2 == 0;
-  const int CL = (g_cluster >= 2 && even) ? 2 : 1;
-  const bool TWO = g_cluster == 3 && even;
-  if (p.rows % BM || p.n_out % BN || p.K1 % 64 || p.K2 % 64 || p.K1 <= 0) return -1;
-  if (p.epi != EPI_F32 && !TWO) return -1;                       // fused epilogues exist for the 2-CTA form only
-  if ((p.epi == EPI_QSCALE || p.epi == EPI_RESID || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
-  if (p.mn_major && (!TWO || p.K2)) return -1;
-  if (p.a_conv && (!TWO || p.mn_major || p.batch != 1 || !p.a_raw)) return -1;
-  if (p.a_conv == ACV_NORM_RELU && ((p.epi != EPI_RESID && p.epi != EPI_BIAS_PLANES) || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
-  if (p.a_conv == ACV_QSCALE && (p.epi != EPI_F32_STATS || p.K2 != kD || !p.kmean)) return -1;
+  if (p.rows % (2 * BM) || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.batch <= 0) return -1;
+  if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
+  if (p.a_conv && (p.a_conv != ACV_NORM_RELU || p.batch != 1 || !p.a_raw || p.epi != EPI_BIAS_PLANES || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
-  if (p.epi == EPI_QKV && (p.q_tiles < 0 || p.q_tiles > 1 || p.n_out != (p.q_tiles + 2) * BN || p.batch != 1 || !p.out.hi || !p.bias ||
-                           (p.q_tiles && (p.ldc % 4 || !p.c)))) return -1;
+  if (p.epi == EPI_QKV && (p.n_out != 2 * BN || p.batch != 1 || !p.out.hi || !p.bias)) return -1;
+  if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM) && !p.bias) return -1;
   const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
   int conf_tma = 0;
-  if (f32_out && (p.ldc % 4 || (p.batch > 1 && p.c_batch_elems != (long long)p.rows * p.ldc))) return -1;
+  if (f32_out && (p.ldc % 4 || !p.c)) return -1;
   const long long a_rows = (long long)(p.batch - 1) * p.a_batch_rows + p.rows;
   const long long b1_rows = (long long)(p.batch - 1) * p.b_batch_rows + p.n_out;
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
-  const long long a_cols = (long long)(p.batch - 1) * p.a_batch_k + p.K1, b_cols = (long long)(p.batch - 1) * p.b_batch_k + p.K1;
   Maps mp;
-  bool ok;
-  if (p.mn_major) {
-    // row-major [reduction rows, channels] planes; box = 64 channels x 64 rows
-    const long long k_rows = (long long)(p.batch - 1) * p.a_batch_k + p.K1;
-    ok = make_map(&mp.a1h, p.a1.hi, k_rows, p.rows, p.a1.ld, 64, 64, false) && make_map(&mp.a1l, p.a1.lo, k_rows, p.rows, p.a1.ld, 64, 64, false) &&
-         make_map(&mp.b1h, p.b1.hi, k_rows, p.n_out, p.b1.ld, 64, 64, false) && make_map(&mp.b1l, p.b1.lo, k_rows, p.n_out, p.b1.ld, 64, 64, false);
-  } else {
-    ok = make_map(&mp.b1h, p.b1.hi, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, b_cols, p.b1.ld, BK, BN / CL, false);
-    if (p.a_conv == ACV_NORM_RELU) { mp.a1h = mp.b1h; mp.a1l = mp.b1l; }     // every A tile comes in raw: the plane maps are never used
-    else ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false);
-  }
-  if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.a_conv == ACV_NORM_RELU ? p.K1 : p.K2, p.a_raw_ld, 32, BM, true);
+  bool ok = make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, BN / 2, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, BN / 2, false);
+  if (p.a_conv) { mp.a1h = mp.b1h; mp.a1l = mp.b1l; }     // every A1 tile comes in raw: the plane maps are never used
+  else ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, p.K1, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, p.K1, p.a1.ld, BK, BM, false);
+  if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.K1, p.a_raw_ld, 32, BM, true);
   else mp.a_raw = mp.b1h;
   if (ok && p.K2) {
-    ok = make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / CL, false);
-    if (p.a_conv == ACV_QSCALE) { mp.a2h = mp.b2h; mp.a2l = mp.b2l; }
-    else ok = ok && make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false);
+    ok = make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / 2, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / 2, false) &&
+         make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false);
   } else if (ok) {
     mp.a2h = mp.a1h; mp.a2l = mp.a1l; mp.b2h = mp.b1h; mp.b2l = mp.b1l;
   }
@@ -1197,68 +930,59 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     mp.out_hi = mp.out_f32; mp.out_lo = mp.out_f32;
   } else if (p.epi == EPI_QKV) {
     ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, 2 * BN, p.out.ld, 64, BM, false);
-    if (p.q_tiles) ok = ok && make_map(&mp.out_f32, p.c, out_rows, BN, p.ldc, 32, BM, true);
-    else mp.out_f32 = mp.out_hi;
+    mp.out_f32 = mp.out_hi;
     mp.out_lo = mp.out_hi;
   } else if (score) {
-    mp.out_f32 = mp.a1h; mp.out_hi = mp.a1h; mp.out_lo = mp.a1h;
-    if (p.epi == EPI_SCORE_CONF && p.conf && p.L.M % 4 == 0) {
+    mp.out_f32 = mp.b1h; mp.out_hi = mp.b1h; mp.out_lo = mp.b1h;
+    if (p.epi == EPI_SCORE_CONF && p.conf && p.L.M % 4 == 0 && (reinterpret_cast<uintptr_t>(p.conf) & 15) == 0)
       conf_tma = make_map3(&mp.out_f32, p.conf, p.L.M, p.L.N, p.batch) ? 1 : 0;
-    }
   } else {
     ok = ok && make_map(&mp.out_hi, p.out.hi, out_rows, p.n_out, p.out.ld, 32, BM, false) && make_map(&mp.out_lo, p.out.lo, out_rows, p.n_out, p.out.ld, 32, BM, false);
     mp.out_f32 = mp.out_hi;
   }
   if (!ok) return -2;
   TcParams tp{};
-  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.n_out = p.n_out;
+  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
-  tp.a_batch_k = p.a_batch_k; tp.b_batch_k = p.b_batch_k;
-  tp.L = p.L; tp.bias = p.bias; tp.elu_cols = p.elu_cols; tp.tl = timeline;
+  tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;
+  tp.L = p.L; tp.bias = p.bias; tp.tl = timeline;
   tp.inv_scale = p.inv_scale; tp.rowsum_part = p.rowsum_part; tp.colsum_part = p.colsum_part; tp.inv_rowsum = p.inv_rowsum;
   tp.inv_colsum = p.inv_colsum; tp.conf = p.conf; tp.conf_tma = conf_tma; tp.rowbest = p.rowbest; tp.colbest = p.colbest;
-  tp.mn_major = p.mn_major; tp.q_tiles = p.q_tiles;
   tp.mu = p.mu; tp.rstd = p.rstd;
-  tp.kmean = p.kmean; tp.cross = p.cross; tp.x_hi = p.resid.hi; tp.x_lo = p.resid.lo; tp.statpart = p.statpart;
-  const int total_units = (tp.m_tiles / CL) * tp.n_tiles * tp.batch;
-  const int grid = total_units * CL < num_sms() ? total_units * CL : (num_sms() / CL) * CL;
+  tp.kmean = p.kmean; tp.cross = p.cross; tp.statpart = p.statpart;
+  if ((p.epi == EPI_QSCALE || p.b2_per_seg || p.epi == EPI_QKV || p.epi == EPI_F32_STATS || p.a_conv) && !tp.seg_rows) return -1;
+  const int total_units = (tp.m_tiles / 2) * tp.n_tiles * tp.batch;
+  const int grid = total_units * 2 < num_sms() ? total_units * 2 : (num_sms() / 2) * 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(threads_of(p.a_conv));
+  cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le;
-  if (TWO && p.a_conv == ACV_NORM_RELU) {
-    le = p.epi == EPI_RESID ? launch_variant<2, true, EPI_RESID, ACV_NORM_RELU>(cfg, mp, tp)
-         : BK == 32         ? launch_variant<2, true, EPI_BIAS_PLANES, ACV_NORM_RELU, 32>(cfg, mp, tp)
-                            : launch_variant<2, true, EPI_BIAS_PLANES, ACV_NORM_RELU>(cfg, mp, tp);
-  } else if (TWO && p.a_conv == ACV_QSCALE) {
-    le = launch_variant<2, true, EPI_F32_STATS, ACV_QSCALE>(cfg, mp, tp);
-  } else if (TWO) {
+  if (p.a_conv) {
+    le = launch_variant<EPI_BIAS_PLANES, ACV_NORM_RELU>(cfg, mp, tp);
+  } else {
     switch (p.epi) {
-      case EPI_F32: le = launch_variant<2, true, EPI_F32>(cfg, mp, tp); break;
-      case EPI_F32_STATS: le = launch_variant<2, true, EPI_F32_STATS>(cfg, mp, tp); break;
-      case EPI_QSCALE: le = launch_variant<2, true, EPI_QSCALE>(cfg, mp, tp); break;
-      case EPI_RESID: le = launch_variant<2, true, EPI_RESID>(cfg, mp, tp); break;
-      case EPI_L2NORM: le = launch_variant<2, true, EPI_L2NORM>(cfg, mp, tp); break;
-      case EPI_SCORE_SUMS: le = launch_variant<2, true, EPI_SCORE_SUMS>(cfg, mp, tp); break;
-      case EPI_SCORE_CONF: le = launch_variant<2, true, EPI_SCORE_CONF>(cfg, mp, tp); break;
-      case EPI_KV: le = launch_variant<2, true, EPI_KV>(cfg, mp, tp); break;
-      case EPI_QKV: le = launch_variant<2, true, EPI_QKV>(cfg, mp, tp); break;
-      case EPI_BIAS_PLANES: le = launch_variant<2, true, EPI_BIAS_PLANES>(cfg, mp, tp); break;
+      case EPI_F32: le = launch_variant<EPI_F32>(cfg, mp, tp); break;
+      case EPI_F32_STATS: le = launch_variant<EPI_F32_STATS>(cfg, mp, tp); break;
+      case EPI_QSCALE: le = launch_variant<EPI_QSCALE>(cfg, mp, tp); break;
+      case EPI_L2NORM: le = launch_variant<EPI_L2NORM>(cfg, mp, tp); break;
+      case EPI_SCORE_SUMS: le = launch_variant<EPI_SCORE_SUMS>(cfg, mp, tp); break;
+      case EPI_SCORE_CONF: le = launch_variant<EPI_SCORE_CONF>(cfg, mp, tp); break;
+      case EPI_QKV: le = launch_variant<EPI_QKV>(cfg, mp, tp); break;
+      case EPI_BIAS_PLANES: le = launch_variant<EPI_BIAS_PLANES>(cfg, mp, tp); break;
       default: return -1;
     }
-  } else if (CL == 2) {
-    le = launch_variant<2, false, EPI_F32>(cfg, mp, tp);
-  } else {
-    le = launch_variant<1, false, EPI_F32>(cfg, mp, tp);
   }
   if (le != cudaSuccess) return -2;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  return 0;
 }
 
 }  // namespace opb

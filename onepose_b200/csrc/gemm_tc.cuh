@@ -12,4 +12,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
 // 2-D row-major tensor map [rows, ld] (columns used: `cols`), box = box_cols x box_rows; swizzle follows the box row width
 // (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B).  Cached per (pointer, shape, box, dtype).
 bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32);
+// Programmatic dependent launch switch shared by every launch site (default on; opb_debug_set_pdl).
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
 }  // namespace opb

@@ -1,16 +1,13 @@
-// Linear-attention state on the 5th-gen tensor cores, straight from the fp32 [K | V] rows of the QKV GEMM.
+// Linear-attention state on the 5th-gen tensor cores.
 //
 //   per segment s, head h:   KV[h][d][q] = sum_rows elu1(K[r,h,d]) * V[r,h,q],   Ksum[h][d] = sum_rows elu1(K[r,h,d])
 //   (reference GATs_SuperGlue.py:71-78; the 1/m of :75 is applied by kv_state_reduce)
 //
-// One CTA per 256-row slab (slabs never straddle a segment: segments are padded to 256 rows).  256 threads:
-//   all threads : stream 16-row stages of fp32 K,V from global (register prefetch one stage ahead), apply elu+1 to K, zero
-//                 the pad rows, split to fp16 hi/lo and write them into shared memory in the UMMA MN-major SWIZZLE_128B
-//                 layout (what a TMA load of a row-major [rows, channels] box would produce);
-//   thread 0    : per stage 6 tcgen05.mma (2 head pairs x one k-step of 16 rows x 3 split passes, M = N = 128, both operands
-//                 MN-major: A = K^T, B = V, reduction index = row) accumulating in TMEM across the whole slab;
-//   warps 0-3   : epilogue -- the two diagonal 64x64 head blocks of each 128x128 accumulator -> partial[slab][h][64*64 + 64].
-// The conversion (SIMT) is the bound; the MMAs of stage i run under the conversion of stage i+1.
+// The k,v projection epilogue (EPI_QKV) leaves  kvh[rows, 512] = fp16(64 * [elu1(K) | V])  with pad rows zero, so the state
+// is ONE tensor-core pass over operands that TMA lands directly in the UMMA MN-major SWIZZLE_128B layout (reduction index =
+// row).  Rounding K and V to fp16 perturbs each product by <= 2^-11 relative with zero mean; the state is a MEAN over the
+// segment's rows, so the perturbation of the mean is ~2^-12/sqrt(rows) -- measured end to end in tools/kv_precision.py
+// (cosine error unchanged at 7e-7 down to 16-row segments).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -20,12 +17,6 @@
 namespace opb {
 namespace {
 
-constexpr int kRowsPerStage = 16;
-constexpr int kStagesInFlight = 2;
-constexpr int kPlaneBytes = kRowsPerStage * 256 * 2;          // one fp16 plane of one operand: 16 rows x 256 channels = 8 KB
-constexpr int kStageBytes = 4 * kPlaneBytes;                   // K_hi, K_lo, V_hi, V_lo = 32 KB (2 stages + slack = 66 KB: 2 CTAs per SM)
-constexpr int kSmemBytes = kStagesInFlight * kStageBytes + 1024 + 64;
-constexpr int kChanBlockBytes = kRowsPerStage * 128;           // LBO: 64-channel blocks are 16 rows x 128 B = 2 KB apart
 constexpr uint32_t kSpin = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,16 +36,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (ok) break;
     if (++spins > kSpin) __trap();
   }
-}
-// MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 rows per atom; LBO between 64-channel blocks, SBO = 1024 B between 8-row groups
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(kChanBlockBytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
 }
 // kind::f16, D = f32, A = B = f16, A and B MN-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -83,158 +64,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-
-// byte offset of channel c (0..255), row r (0..31) inside one MN-major SWIZZLE_128B plane of a stage
-__device__ __forceinline__ uint32_t plane_off(int r, int c) {
-  return (uint32_t)((c >> 6) * kChanBlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
-}
-
-__global__ void __launch_bounds__(256, 2) kv_state_tc_kernel(const float* __restrict__ kv, int ld, int k_off, int v_off, int k_activated, Layout L,
-                                                             float* __restrict__ partial) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* free_bar = reinterpret_cast<uint64_t*>(smem + kStagesInFlight * kStageBytes);   // [2] stage buffer free (its MMAs retired)
-  uint64_t* done_bar = free_bar + kStagesInFlight;                                          // accumulators complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slab = blockIdx.x;
-  const int row0 = slab * 256;
-  const int seg = L.seg_of_row(row0);
-  const int n_valid = min(256, L.seg_valid(seg) - (row0 - L.seg_start(seg)));   // <= 0: slab entirely in the padding
-  float* out = partial + (long long)slab * kHeads * (kDh * kDh + kDh);
-
-  if (n_valid <= 0) {                              // nothing to reduce: define the partial and leave
-    for (int i = tid; i < kHeads * (kDh * kDh + kDh); i += 256) out[i] = 0.f;
-    return;
-  }
-  if (tid == 0) {
-    mbar_init(&free_bar[0], 1); mbar_init(&free_bar[1], 1); mbar_init(done_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  // thread -> data: 4 consecutive channels (c4) of 8 rows (rsel, rsel+2, ...) of every stage
-  const int c4 = (tid & 127) * 4;                  // 0..508: < 256 -> K channel, else V channel c4-256
-  const int rsel = tid >> 7;
-  const bool is_k = c4 < 256;
-  const float* col_ptr = kv + (is_k ? k_off + c4 : v_off + c4 - 256);
-  float ks4[4] = {0.f, 0.f, 0.f, 0.f};
-  const int n_stages = (n_valid + kRowsPerStage - 1) / kRowsPerStage;
-
-  float4 pre[kRowsPerStage / 2];
-  auto prefetch = [&](int s) {
-#pragma unroll
-    for (int i = 0; i < kRowsPerStage / 2; ++i) {
-      const int r = s * kRowsPerStage + rsel + 2 * i;
-      pre[i] = r < n_valid ? *reinterpret_cast<const float4*>(col_ptr + (long long)(row0 + r) * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  prefetch(0);
-  for (int s = 0; s < n_stages; ++s) {
-    const int buf = s & 1;
-    uint8_t* st = smem + buf * kStageBytes;
-    if (s >= kStagesInFlight) mbar_wait(&free_bar[buf], ((s >> 1) - 1) & 1);   // MMAs of stage s-2 have retired
-    uint8_t* p_hi = st + (is_k ? 0 : 2 * kPlaneBytes);
-    uint8_t* p_lo = p_hi + kPlaneBytes;
-    const int cc = c4 & 255;
-#pragma unroll
-    for (int i = 0; i < kRowsPerStage / 2; ++i) {
-      const int rr = rsel + 2 * i;
-      float4 x = pre[i];
-      if (is_k) {
-        if (!k_activated && s * kRowsPerStage + rr < n_valid) { x.x = elu1_fast(x.x); x.y = elu1_fast(x.y); x.z = elu1_fast(x.z); x.w = elu1_fast(x.w); }
-        ks4[0] += x.x; ks4[1] += x.y; ks4[2] += x.z; ks4[3] += x.w;
-      }
-      const float2 a = make_float2(x.x * kPre, x.y * kPre), b = make_float2(x.z * kPre, x.w * kPre);
-      const __half2 ha = __float22half2_rn(a), hb = __float22half2_rn(b);
-      const float2 fa = __half22float2(ha), fb = __half22float2(hb);
-      const __half2 la = __float22half2_rn(make_float2(a.x - fa.x, a.y - fa.y)), lb = __float22half2_rn(make_float2(b.x - fb.x, b.y - fb.y));
-      __half2 hv[2] = {ha, hb}, lv[2] = {la, lb};
-      const uint32_t off = plane_off(rr, cc);
-      *reinterpret_cast<uint2*>(p_hi + off) = *reinterpret_cast<uint2*>(hv);
-      *reinterpret_cast<uint2*>(p_lo + off) = *reinterpret_cast<uint2*>(lv);
-    }
-    if (s + 1 < n_stages) prefetch(s + 1);         // next stage's global loads fly during the barrier + MMA issue
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t kh = smem_u32(st), kl = kh + kPlaneBytes, vh = kh + 2 * kPlaneBytes, vl = kh + 3 * kPlaneBytes;
-#pragma unroll
-      for (int pair = 0; pair < 2; ++pair) {       // head pair (2 x 64 channels = one M=128 / N=128 operand)
-        const uint32_t d = tmem_base + pair * 128;
-        const uint32_t po = pair * 2 * kChanBlockBytes;
-#pragma unroll
-        for (int k = 0; k < kRowsPerStage / 16; ++k) {
-          const uint32_t ko = k * 2048;            // 16 rows = two 8-row atoms
-          const uint64_t ah = make_desc_mn(kh + po + ko), al = make_desc_mn(kl + po + ko);
-          const uint64_t bh = make_desc_mn(vh + po + ko), bl = make_desc_mn(vl + po + ko);
-          mma(d, ah, bh, (uint32_t)((s | k) != 0));
-          mma(d, ah, bl, 1u);
-          mma(d, al, bh, 1u);
-        }
-      }
-      commit(&free_bar[buf]);
-      if (s == n_stages - 1) commit(done_bar);
-    }
-  }
-  // ---- epilogue: diagonal head blocks of the two accumulators
-  mbar_wait(done_bar, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp < 4) {
-    const int lane_row = warp * 32 + lane;         // accumulator row = K channel within the head pair
-    const int hl = lane_row >> 6, d = lane_row & 63;
-#pragma unroll 1
-    for (int pair = 0; pair < 2; ++pair) {
-      const int h = pair * 2 + hl;
-      float* o = out + (long long)h * (kDh * kDh + kDh) + d * kDh;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + pair * 128 + hl * 64 + half * 32 + ((uint32_t)(warp * 32) << 16), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(o + half * 32 + j) = make_float4(__uint_as_float(v[j]) * kProdInv, __uint_as_float(v[j + 1]) * kProdInv,
-                                                                      __uint_as_float(v[j + 2]) * kProdInv, __uint_as_float(v[j + 3]) * kProdInv);
-      }
-    }
-  }
-  // K column sums: threads t and t+128 hold the even / odd rows of the same 4 K channels
-  float* red = reinterpret_cast<float*>(smem);     // stage buffers are idle now (all MMAs retired: done_bar)
-  __syncthreads();
-  if (is_k) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) red[rsel * 256 + c4 + e] = ks4[e];
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  out[(long long)(tid >> 6) * (kDh * kDh + kDh) + kDh * kDh + (tid & 63)] = red[tid] + red[256 + tid];
-  if (warp == 0) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// fp16 variant: the QKV GEMM epilogue (EPI_QKV) already wrote  kvh[rows, 512] = fp16(64 * [elu1(K) | V])  (pad rows zero), so
-// the state is ONE tensor-core pass over operands that TMA lands directly in the UMMA MN-major SWIZZLE_128B layout -- no SIMT
-// conversion, half the bytes.  Rounding K and V to fp16 perturbs each product by <= 2^-11 relative with zero mean; the state is
-// a MEAN over the segment's rows, so the perturbation of the mean is ~2^-12/sqrt(rows) -- measured end to end in
-// tools/kv_precision.py (cosine error unchanged at 7e-7 down to 16-row segments).
-//
-// One CTA per 256-row slab, 192 threads, 2 CTAs per SM:
+// One CTA per ROW GROUP = `slabs_per_group` consecutive 256-row slabs of one segment (groups never straddle a segment; the
+// host picks the group size so that the grid is about two CTAs per SM -- fewer, larger groups mean fewer partial states to
+// write and re-read).  192 threads, 2 CTAs per SM:
 //   warp 0     TMA producer: 32-row stages = 8 boxes of 64 channels x 32 rows (4 K blocks, 4 V blocks), 3-stage ring
-//   warp 1     TMEM owner + MMA issuer: per stage 2 head pairs x 2 k-steps of 16 rows, M = N = 128, accumulating over the slab
+//   warp 1     TMEM owner + MMA issuer: per stage 2 head pairs x 2 k-steps of 16 rows, M = N = 128, accumulating over the group
 //   warps 2-5  K column sums from the staged tile (the K mean of the attention normaliser), then the epilogue
 constexpr int kHRows = 32;                                 // rows per stage
 constexpr int kHStages = 3;
@@ -264,7 +98,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
-__global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constant__ CUtensorMap kv_map, Layout L, float* __restrict__ partial) {
+__global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constant__ CUtensorMap kv_map, Layout L, KvGroups G, float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kHStages * kHStageBytes);   // [3] stage landed
@@ -273,12 +107,17 @@ __global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slab = blockIdx.x;
-  const int row0 = slab * 256;
-  const int seg = L.seg_of_row(row0);
-  const int n_valid = min(256, L.seg_valid(seg) - (row0 - L.seg_start(seg)));
-  float* out = partial + (long long)slab * kHeads * (kDh * kDh + kDh);
-  if (n_valid <= 0) {
+  // row group -> (frame, side, group index inside the segment)
+  const int per_frame = G.gq + G.gd;
+  const int b = blockIdx.x / per_frame, g = blockIdx.x - b * per_frame;
+  const int side = g >= G.gq ? 1 : 0, gi = side ? g - G.gq : g;
+  const int seg = 2 * b + side;
+  const int group_rows = G.slabs * 256;
+  const int row0 = L.seg_start(seg) + gi * group_rows;
+  float* out = partial + (long long)blockIdx.x * kHeads * (kDh * kDh + kDh);
+  griddep_sync();                                          // kvh of the preceding GEMM is visible from here on
+  const int n_valid = min(group_rows, L.seg_valid(seg) - gi * group_rows);
+  if (n_valid <= 0) {                                      // group entirely in the padding: never read by the reduction, defined anyway
     for (int i = tid; i < kHeads * (kDh * kDh + kDh); i += 192) out[i] = 0.f;
     return;
   }
@@ -398,21 +237,21 @@ __global__ void __launch_bounds__(192, 2) kv_state_h_kernel(const __grid_constan
 
 }  // namespace
 
-int launch_kv_state_tc(const float* kv, int ld, int k_off, int v_off, int k_activated, const Layout& L, float* partial, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kv_state_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -2;
-    attr_done = true;
-  }
-  const int slabs = L.rows() / 256;
-  kv_state_tc_kernel<<<slabs, 256, kSmemBytes, stream>>>(kv, ld, k_off, v_off, k_activated, L, partial);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-
 }  // namespace opb
 
 namespace opb {
-int launch_kv_state_h(const __half* kvh, const Layout& L, float* partial, cudaStream_t stream) {
+KvGroups kv_groups_for(const Layout& L, int num_sms) {
+  const int total_slabs = L.rows() / 256;
+  int slabs = total_slabs / (2 * num_sms);                 // about two CTAs per SM (the kernel's occupancy)
+  slabs = slabs < 1 ? 1 : (slabs > 8 ? 8 : slabs);
+  KvGroups G;
+  G.slabs = slabs;
+  G.gq = (L.n_pad / 256 + slabs - 1) / slabs;
+  G.gd = (L.m_pad / 256 + slabs - 1) / slabs;
+  return G;
+}
+
+int launch_kv_state_h(const __half* kvh, const Layout& L, const KvGroups& G, float* partial, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kv_state_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBytes) != cudaSuccess) return -2;
@@ -420,8 +259,15 @@ int launch_kv_state_h(const __half* kvh, const Layout& L, float* partial, cudaSt
   }
   CUtensorMap map;
   if (!make_tensor_map_2d(&map, kvh, L.rows(), 512, 512, 64, kHRows, false)) return -2;
-  const int slabs = L.rows() / 256;
-  kv_state_h_kernel<<<slabs, 192, kHSmemBytes, stream>>>(map, L, partial);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(L.B * (G.gq + G.gd)));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = kHSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kv_state_h_kernel, map, L, G, partial) == cudaSuccess ? 0 : -2;
 }
 }  // namespace opb

@@ -22,7 +22,6 @@ import torch.nn as nn
 from . import _lib
 
 GNN_LAYERS = ["GATs", "self", "cross"] * 4          # GATs_SuperGlue.py:162
-_BACKENDS = {"tcgen05": 0, "simt": 1, "tcgen05_unfused": 2}   # 1, 2: cross-check paths used by the tests
 
 
 class _GATsParams(nn.Module):
@@ -79,7 +78,7 @@ class _GnnParams(nn.Module):
 
 
 class GATsSuperGlue(nn.Module):
-    def __init__(self, hparams, gemm_backend: str = "tcgen05"):
+    def __init__(self, hparams):
         super().__init__()
         self.hparams = hparams
         self.match_type = hparams["match_type"]
@@ -89,17 +88,16 @@ class GATsSuperGlue(nn.Module):
         self.gnn = _GnnParams(d)
         self.final_proj = nn.Conv1d(d, d, kernel_size=1, bias=True)
         self.register_parameter("bin_score", nn.Parameter(torch.tensor(1.0)))
-        if gemm_backend not in _BACKENDS:
-            raise ValueError(f"gemm_backend must be one of {sorted(_BACKENDS)}")
-        self._backend = gemm_backend
         self._lib = _lib.load()        # raises if the CUDA library is not built
         self._handle = None
         self._handle_device = None
         self._weights_key = None
-        self._object_key = None
+        self._M = None
+        self._obj_key = None           # (data_ptr, _version, shape) of the caller tensors the current object was packed from
+        self._obj_ref = None           # strong reference to those tensors: their storage cannot be recycled under the key
+        self._obj_copy = None          # private copy of the packed object (exact comparison on a key miss)
         self._chunk_frames = 0
         self._hoist = True
-        self._fuse = None
         self.last_batched = None       # batched outputs of the last forward (all B frames)
 
     # ------------------------------------------------------------------ handle / weights
@@ -119,17 +117,15 @@ class GATsSuperGlue(nn.Module):
         hp = self.hparams
         cfg = _lib.OpbConfig(int(hp["descriptor_dim"]), 4, float(hp["scale_factor"]), float(hp["match_threshold"]),
                              int(bool(hp["include_self"])), int(bool(hp["additional"])),
-                             int(bool(hp["with_linear_transform"])), device.index or 0, _BACKENDS[self._backend])
+                             int(bool(hp["with_linear_transform"])), device.index or 0)
         h = C.c_void_p()
         _lib.check(self._lib.opb_create(C.byref(cfg), C.byref(h)))
         self._handle, self._handle_device = h, device
-        self._weights_key = self._object_key = None
+        self._weights_key = self._obj_key = self._obj_ref = self._obj_copy = self._M = None
         if self._chunk_frames:
             _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
         if not self._hoist:
             _lib.check(self._lib.opb_set_hoist(self._handle, 0), self._handle)
-        if self._fuse is not None:
-            _lib.check(self._lib.opb_set_fuse_level(self._handle, self._fuse), self._handle)
 
     def _sync_weights(self):
         key = tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
@@ -140,13 +136,7 @@ class GATsSuperGlue(nn.Module):
             _lib.check(self._lib.opb_load_weight(self._handle, name.encode(), w.data_ptr(), w.numel()), self._handle)
         _lib.check(self._lib.opb_finalize_weights(self._handle), self._handle)
         self._weights_key = key
-        self._object_key = None
-
-    def set_fuse_level(self, level: int):
-        """0 / 1 / 2: how much element-wise work rides in the GEMM epilogues (see opb_set_fuse_level)."""
-        self._fuse = int(level)
-        if self._handle is not None:
-            _lib.check(self._lib.opb_set_fuse_level(self._handle, self._fuse), self._handle)
+        self._obj_key = self._obj_ref = self._obj_copy = self._M = None
 
     def set_hoist(self, enable: bool):
         """Evaluate the frame-invariant GNN layers once per call (default) or per frame like the reference."""
@@ -155,15 +145,16 @@ class GATsSuperGlue(nn.Module):
             _lib.check(self._lib.opb_set_hoist(self._handle, int(self._hoist)), self._handle)
 
     def set_chunk_frames(self, frames: int):
-        """Frames pushed through the GNN together (L2-residency knob of the C ABI)."""
+        """Frames pushed through the GNN together (workspace-size knob of the C ABI)."""
         self._chunk_frames = int(frames)
         if self._handle is not None:
             _lib.check(self._lib.opb_set_chunk_frames(self._handle, self._chunk_frames), self._handle)
 
     # ------------------------------------------------------------------ fast API
-    def set_object(self, descriptors3d_db: torch.Tensor, descriptors2d_db: torch.Tensor):
+    def set_object(self, descriptors3d_db: torch.Tensor, descriptors2d_db: torch.Tensor, reserve=None):
         """Upload per-object constants once (what inference.py:113-130 builds per sequence).
-        descriptors3d_db [256, M], descriptors2d_db [256, M*L], CUDA fp32."""
+        descriptors3d_db [256, M], descriptors2d_db [256, M*L], CUDA fp32.  reserve = (frames, N): size the
+        workspace now instead of on the first call."""
         d3 = descriptors3d_db.float().contiguous()
         d2 = descriptors2d_db.float().contiguous()
         if not d3.is_cuda:
@@ -177,11 +168,20 @@ class GATsSuperGlue(nn.Module):
         _lib.check(self._lib.opb_set_object(self._handle, d3.data_ptr(), d2.data_ptr(), M, d2.shape[1] // M, st),
                    self._handle)
         self._M = M
-        self._object_key = None
+        self._obj_key = self._obj_ref = self._obj_copy = None
+        if reserve is not None:
+            _lib.check(self._lib.opb_reserve_workspace(self._handle, int(reserve[0]), int(reserve[1])), self._handle)
 
-    def match_frames(self, descriptors2d_query: torch.Tensor, return_conf: bool = True):
-        """B frames of the current object.  descriptors2d_query [B, 256, N] CUDA fp32.
-        Returns dict of batched tensors (matches0 [B,N] int64, ..., conf_matrix [B,N,M] or None)."""
+    def _require_object(self):
+        if self._handle is None or self._M is None:
+            raise RuntimeError("no object set: call set_object(descriptors3d_db, descriptors2d_db) first (or use forward(data))")
+
+    def match_frames(self, descriptors2d_query: torch.Tensor, return_conf: bool = True, lengths: torch.Tensor | None = None):
+        """B frames of the current object.  descriptors2d_query [B, 256, N] CUDA fp32; lengths (optional) CUDA int32 [B] =
+        valid query points per frame (ragged batch: SuperPoint yields a different count per frame).
+        Returns dict of batched tensors (matches0 [B,N] int64, ..., conf_matrix [B,N,M] or None).  Asynchronous: no host
+        synchronisation; a range violation (see check_range) turns the call's matches into -1."""
+        self._require_object()
         q = descriptors2d_query.float().contiguous()
         B, _, N = q.shape
         M = self._M
@@ -191,15 +191,22 @@ class GATsSuperGlue(nn.Module):
         s0 = torch.empty(B, N, dtype=torch.float32, device=dev)
         s1 = torch.empty(B, M, dtype=torch.float32, device=dev)
         conf = torch.empty(B, N, M, dtype=torch.float32, device=dev) if return_conf else None
+        if lengths is not None:
+            lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+            if lengths.numel() != B:
+                raise ValueError("lengths must have one entry per frame")
         st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self._lib.opb_forward(self._handle, q.data_ptr(), B, N, m0.data_ptr(), m1.data_ptr(), s0.data_ptr(),
-                                         s1.data_ptr(), conf.data_ptr() if conf is not None else None, st), self._handle)
+        _lib.check(self._lib.opb_forward(self._handle, q.data_ptr(), lengths.data_ptr() if lengths is not None else None, B, N,
+                                         m0.data_ptr(), m1.data_ptr(), s0.data_ptr(), s1.data_ptr(),
+                                         conf.data_ptr() if conf is not None else None, st), self._handle)
         return {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1, "conf_matrix": conf}
 
-    def match_frames_host(self, q_host: torch.Tensor, out: dict | None = None):
+    def match_frames_host(self, q_host: torch.Tensor, out: dict | None = None, lengths: torch.Tensor | None = None,
+                          materialize_conf: bool = True):
         """End-to-end call on HOST buffers (bench.py e2e leg): pinned fp32 [B,256,N] in; matches /
         scores copied back to pinned host tensors.  conf_matrix is computed on the device and stays
-        there (the reference caller discards it: inference.py:146)."""
+        there (the reference caller discards it: inference.py:146); materialize_conf=False skips it."""
+        self._require_object()
         B, _, N = q_host.shape
         M = self._M
         if out is None:
@@ -207,11 +214,19 @@ class GATsSuperGlue(nn.Module):
             out = {"matches0": torch.empty(B, N, dtype=torch.int64, **pin), "matches1": torch.empty(B, M, dtype=torch.int64, **pin),
                    "matching_scores0": torch.empty(B, N, dtype=torch.float32, **pin),
                    "matching_scores1": torch.empty(B, M, dtype=torch.float32, **pin)}
+        if lengths is not None:
+            lengths = lengths.to(device="cpu", dtype=torch.int32).contiguous()
         st = torch.cuda.current_stream(self._handle_device).cuda_stream
-        _lib.check(self._lib.opb_forward_host(self._handle, q_host.data_ptr(), B, N, out["matches0"].data_ptr(),
-                                              out["matches1"].data_ptr(), out["matching_scores0"].data_ptr(),
-                                              out["matching_scores1"].data_ptr(), None, st), self._handle)
+        _lib.check(self._lib.opb_forward_host(self._handle, q_host.data_ptr(), lengths.data_ptr() if lengths is not None else None, B, N,
+                                              out["matches0"].data_ptr(), out["matches1"].data_ptr(), out["matching_scores0"].data_ptr(),
+                                              out["matching_scores1"].data_ptr(), None, int(bool(materialize_conf)), st), self._handle)
         return out
+
+    def check_range(self):
+        """Wait for the last call and raise OpbError(OPB_E_RANGE) if it left the fp16-split operand range (its matches were
+        reported as -1).  forward() / match_frames() never block for this: they deliver the error of an EARLIER call."""
+        if self._handle is not None:
+            _lib.check(self._lib.opb_check_range(self._handle, None), self._handle)
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.opb_set_profiling(self._handle, int(enable)), self._handle)
@@ -233,13 +248,32 @@ class GATsSuperGlue(nn.Module):
 
     # ------------------------------------------------------------------ reference contract
     @staticmethod
-    def _fingerprint(t: torch.Tensor):
-        v = t.reshape(t.shape[0], -1).view(torch.int32)
-        return torch.stack([v.sum(dim=1, dtype=torch.int64), (v[:, ::97].to(torch.int64) * 31).sum(dim=1)], 1)
+    def _tensor_key(t: torch.Tensor):
+        return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+
+    def _use_object(self, d3: torch.Tensor, d2: torch.Tensor, base3: torch.Tensor, base2: torch.Tensor):
+        """Make (d3 [256,M], d2 [256,M*L]) the current object.  The reference caller re-sends the per-object tensors with every
+        frame (inference.py:80-94); they are packed once:
+          * same tensors as last time (data_ptr, _version, shape; a strong reference keeps their storage from being recycled)
+            -> nothing to do, no device work, no synchronisation;
+          * different tensors -> exact comparison with a private copy of the packed object (one device reduction + one
+            4-byte read-back); only a real change re-packs (opb_set_object)."""
+        key = (self._tensor_key(d3), self._tensor_key(d2))
+        if key == self._obj_key:
+            return
+        same = (self._obj_copy is not None and self._obj_copy[0].shape == d3.shape and self._obj_copy[1].shape == d2.shape
+                and self._obj_copy[0].device == d3.device
+                and bool(torch.equal(self._obj_copy[0], d3)) and bool(torch.equal(self._obj_copy[1], d2)))
+        if not same:
+            self.set_object(d3, d2)
+            self._obj_copy = (d3.clone(), d2.clone())
+        self._obj_key = key
+        self._obj_ref = (base3, base2)
 
     @torch.no_grad()
     def forward(self, data):
-        """Same keys / shapes as the reference (GATs_SuperGlue.py:180-190)."""
+        """Same keys / shapes as the reference (GATs_SuperGlue.py:180-190).  No host synchronisation on the common path
+        (same object tensors as the previous call); a range violation of an earlier call is raised here."""
         kpts2d, kpts3d = data["keypoints2d"].float(), data["keypoints3d"].float()
         desc2d_query = data["descriptors2d_query"].float()
         desc3d_db, desc2d_db = data["descriptors3d_db"].float(), data["descriptors2d_db"].float()
@@ -261,24 +295,22 @@ class GATsSuperGlue(nn.Module):
         B = desc2d_query.shape[0]
         self._ensure_handle(desc2d_query.device)
         self._sync_weights()
-        # per-object constants are re-sent by the caller every frame (inference.py:80-94); detect
-        # "same object as last call" by content so that they are packed once.
-        fp = torch.cat([self._fingerprint(desc3d_db), self._fingerprint(desc2d_db)], 1).cpu()
-        groups = []                                                       # runs of frames sharing an object
-        for b in range(B):
-            if groups and torch.equal(fp[b], fp[groups[-1][0]]):
-                groups[-1].append(b)
-            else:
-                groups.append([b])
+        _lib.check(self._lib.opb_poll_range(self._handle), self._handle)  # deferred report of an earlier call (never blocks)
+        # runs of frames that share an object (the reference accepts per-element 3D descriptors; its callers use B = 1)
+        if B == 1 or (desc3d_db.stride(0) == 0 and desc2d_db.stride(0) == 0):
+            groups = [list(range(B))]
+        else:
+            same = ((desc3d_db[1:] == desc3d_db[:-1]).flatten(1).all(1) & (desc2d_db[1:] == desc2d_db[:-1]).flatten(1).all(1)).cpu()
+            groups = [[0]]
+            for b in range(1, B):
+                if bool(same[b - 1]):
+                    groups[-1].append(b)
+                else:
+                    groups.append([b])
         outs = []
         for g in groups:
-            key = (tuple(fp[g[0]].tolist()), tuple(desc3d_db.shape[1:]), tuple(desc2d_db.shape[1:]))
-            if key != self._object_key:
-                self.set_object(desc3d_db[g[0]], desc2d_db[g[0]])
-                self._object_key = key
+            self._use_object(desc3d_db[g[0]], desc2d_db[g[0]], desc3d_db, desc2d_db)
             outs.append(self.match_frames(desc2d_query[g[0]:g[-1] + 1]))
-        # range guard of the fp16-split operand format (one 4-byte read-back; the reference caller syncs right after anyway)
-        _lib.check(self._lib.opb_check_range(self._handle, torch.cuda.current_stream(desc2d_query.device).cuda_stream), self._handle)
         out = outs[0] if len(outs) == 1 else {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
         self.last_batched = out
         pred = {

@@ -61,8 +61,10 @@ def _kenc(rs, sd, prefix, inp_dim, layers, feature_dim):
             idx += 2  # InstanceNorm1d (no params) + ReLU
 
 
-def make_state_dict(seed: int = 0, damped: bool = True, hparams: dict | None = None):
-    """Reference-keyed state dict (numpy fp32 arrays)."""
+def make_state_dict(seed: int = 0, damped: bool = True, hparams: dict | None = None, mlp3_scale: float | None = None):
+    """Reference-keyed state dict (numpy fp32 arrays).  ``mlp3_scale`` overrides the 0.02 damping of the layers' last
+    convolution (1.0 = the reference initialisation) while keeping the near-identity final projection: the knob of the
+    precision sweep (tools/damping_sweep.py) -- the larger it is, the larger the residual updates every GEMM error rides on."""
     hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
     d = hp["descriptor_dim"]
     rs = np.random.RandomState(seed)
@@ -86,11 +88,13 @@ def make_state_dict(seed: int = 0, damped: bool = True, hparams: dict | None = N
             sd[f"{p}.mlp.0.weight"], sd[f"{p}.mlp.0.bias"] = w, b
             w, b = _conv(rs, d, 2 * d)
             b[:] = 0.0  # reference GATs_SuperGlue.py:109
-            if damped:
+            if mlp3_scale is not None:
+                w *= mlp3_scale
+            elif damped:
                 w *= 0.02
             sd[f"{p}.mlp.3.weight"], sd[f"{p}.mlp.3.bias"] = w, b
     w, b = _conv(rs, d, d)
-    if damped:
+    if damped or mlp3_scale is not None:
         w = (np.eye(d, dtype=np.float32)[:, :, None] + 0.02 * w).astype(np.float32)
     sd["final_proj.weight"], sd["final_proj.bias"] = w, b
     sd["bin_score"] = np.array(1.0, dtype=np.float32)
@@ -142,3 +146,27 @@ def make_tracks(seed: int, M: int, d: int = D, max_len: int = 12):
     idxs = rs.randint(1, max_len + 1, size=M).astype(np.int64)
     desc = rs.randn(int(idxs.sum()), d)
     return desc, idxs
+
+
+def make_track_scores(seed: int, idxs: np.ndarray):
+    """Per-observation detection scores [sum_len, 1] f64 for ``mean_scores`` (reference feature_process.py:308-317);
+    wide dynamic range so that the summation order matters."""
+    rs = np.random.RandomState(seed + 7919)
+    n = int(np.sum(idxs))
+    return rs.rand(n, 1) * np.exp(3.0 * rs.randn(n, 1))
+
+
+def make_sfm_features(seed: int, n_points: int, d: int = D, max_len: int = 14):
+    """Stand-in for the per-object SfM feature files (reference feature_process.py:191-194, :357-363): unit-norm fp32
+    observation descriptors [d, sum_len], scores [sum_len, 1], track lengths idxs [n_points], and the per-point averages
+    (descriptors3d [d, n_points], scores3d [n_points, 1]) -- inputs of pad_features3d_random / build_features3d_leaves."""
+    rs = np.random.RandomState(seed)
+    idxs = rs.randint(1, max_len + 1, size=n_points).astype(np.int64)
+    centers = _unit_cols(rs.randn(d, n_points))
+    obs = _unit_cols(np.repeat(centers, idxs, axis=1) + 0.02 * rs.randn(d, int(idxs.sum())))
+    obs_scores = rs.rand(int(idxs.sum()), 1).astype(np.float32)
+    ends = np.cumsum(idxs)
+    starts = ends - idxs
+    avg = np.stack([obs[:, s:e].mean(axis=1) for s, e in zip(starts, ends)], 1).astype(np.float32)
+    avg_scores = np.stack([obs_scores[s:e].mean(axis=0) for s, e in zip(starts, ends)], 0).astype(np.float32)
+    return obs, obs_scores, idxs, avg, avg_scores

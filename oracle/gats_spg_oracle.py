@@ -186,3 +186,56 @@ def mean_descriptors(descriptors, idxs):
     ends = np.cumsum(idxs)
     starts = ends - idxs
     return np.stack([descriptors[s:e].mean(axis=0) for s, e in zip(starts, ends)], 0)
+
+
+def mean_scores(scores, idxs):
+    """scores: [sum(idxs), 1] float64 numpy -> [M, 1] (reference feature_process.py:308-317)."""
+    import numpy as np
+    ends = np.cumsum(idxs)
+    starts = ends - idxs
+    return np.stack([scores[s:e].mean(axis=0) for s, e in zip(starts, ends)], 0)
+
+
+# --------------------------------------------------------------------------
+# Per-object feature construction -- reference src/utils/data_utils.py:143-205
+# --------------------------------------------------------------------------
+def pad_features3d_random(descriptors, scores, n_target):
+    """descriptors [dim, n] f32, scores [n, 1] f32 -> padded (ones / zeros) or truncated to n_target (:143-160)."""
+    import numpy as np
+    descriptors = np.asarray(descriptors, np.float32)
+    scores = np.asarray(scores, np.float32)
+    dim, n = descriptors.shape
+    if n >= n_target:                                                     # :153-155
+        return descriptors[:, :n_target].copy(), scores[:n_target].copy()
+    pad = n_target - n                                                    # :157-158
+    return (np.concatenate([descriptors, np.ones((dim, pad), np.float32)], 1),
+            np.concatenate([scores, np.zeros((pad, 1), np.float32)], 0))
+
+
+def build_features3d_leaves(descriptors, scores, idxs, n_target, num_leaf):
+    """Leaf selection with the dustbin column and numpy's GLOBAL RNG, one permutation per 3D point (:163-205).
+    Consumes np.random exactly like the reference: seed it the same way to get the same tensors."""
+    import numpy as np
+    descriptors = np.asarray(descriptors, np.float32)
+    scores = np.asarray(scores, np.float32)
+    dim = descriptors.shape[0]
+    n_points = idxs.shape[0]
+    d_ext = np.concatenate([descriptors, np.ones((dim, 1), np.float32)], 1)   # :175 dustbin = all ones
+    s_ext = np.concatenate([scores, np.zeros((1, 1), np.float32)], 0)        # :176
+    dustbin = d_ext.shape[1] - 1
+    ends = np.cumsum(idxs, axis=0)
+    starts = np.insert(ends[:-1], 0, 0)
+    chosen = []
+    for lo, hi in zip(starts, ends):                                      # :182-192
+        if num_leaf > hi - lo:
+            cand = np.arange(lo, hi).tolist() + [dustbin] * (num_leaf - (hi - lo))
+            chosen.append(np.random.permutation(np.array(cand)))
+        else:
+            chosen.append(np.random.permutation(np.arange(lo, hi))[:num_leaf])
+    sel = np.concatenate(chosen, 0)
+    d_out, s_out = d_ext[:, sel], s_ext[sel, :]                           # :196-197
+    n_pad = n_target - n_points
+    if n_pad < 0:                                                         # :199-201
+        return d_out[:, :num_leaf * n_target], s_out[:num_leaf * n_target]
+    return (np.concatenate([d_out, np.ones((dim, n_pad * num_leaf), np.float32)], 1),   # :203-204
+            np.concatenate([s_out, np.zeros((n_pad * num_leaf, 1), np.float32)], 0))

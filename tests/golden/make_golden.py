@@ -11,9 +11,11 @@ the seeded synthetic inputs of ``onepose_b200.synthetic.make_batch`` and stores
 what the reference returns.  Inputs are NOT stored: they are regenerated from
 the seeds recorded in each file (numpy RandomState is platform-stable).
 
-Also stores the offline producer ``mean_descriptors``
-(reference ``src/sfm/postprocess/feature_process.py:297-305``) -- restated here
-rather than imported because that module pulls in h5py at import time.
+Also stores the adjacent producers: ``mean_descriptors`` / ``mean_scores``
+(reference ``src/sfm/postprocess/feature_process.py:297-317``; the module needs h5py at import
+time, so the two functions are exec'd from its SOURCE TEXT, unmodified) and
+``pad_features3d_random`` / ``build_features3d_leaves`` (``src/utils/data_utils.py:143-205``,
+imported) under a fixed ``np.random.seed``.
 """
 import os
 import sys
@@ -105,14 +107,74 @@ def empty_case():
     print("empty:", {k: (tuple(v.shape), v.dtype) if hasattr(v, "shape") else v for k, v in ret.items()})
 
 
-def mean_desc_case():
-    desc, idxs = synthetic.make_tracks(7, 300)
-    # reference feature_process.py:297-305 semantics: np.mean over rows [start:end) of each track
-    ends = np.cumsum(idxs)
-    starts = np.insert(ends[:-1], 0, 0)
-    avg = np.concatenate([np.mean(desc[s:e], axis=0).reshape(1, -1) for s, e in zip(starts, ends)], 0)
-    np.savez_compressed(os.path.join(HERE, "mean_descriptors_m300.npz"), seed=7, M=300, avg=avg)
-    print("mean_descriptors:", avg.shape, avg.dtype)
+def _reference_functions(path, names):
+    """Source text of top-level functions of a reference module that cannot be imported here (feature_process.py needs
+    h5py at import time), exec'd with numpy in scope: the functions run UNMODIFIED."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, missing
+    return [ns[n] for n in names]
+
+
+def mean_cases():
+    """mean_descriptors / mean_scores run from the reference's own source text (feature_process.py:297-317)."""
+    mean_descriptors, mean_scores = _reference_functions(
+        "/root/reference/src/sfm/postprocess/feature_process.py", ["mean_descriptors", "mean_scores"])
+    for name, seed, M, max_len in [("mean_descriptors_m300", 7, 300, 12), ("mean_tracks_long_m48", 11, 48, 400)]:
+        desc, idxs = synthetic.make_tracks(seed, M, max_len=max_len)
+        scores = synthetic.make_track_scores(seed, idxs)
+        avg = mean_descriptors(desc, idxs)
+        avg_s = mean_scores(scores, idxs)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=seed, M=M, max_len=max_len, avg=avg, avg_scores=avg_s)
+        print(name, avg.shape, avg.dtype, avg_s.shape, int(idxs.max()))
+
+
+def features3d_cases():
+    """pad_features3d_random / build_features3d_leaves of the imported reference (src/utils/data_utils.py:143-205) under a fixed
+    np.random.seed, and the reference forward on an object built by them (all-ones dustbin leaves, duplicate all-ones padded 3D
+    points -> exactly tied confidences)."""
+    from src.utils import data_utils
+    n_points, L = 40, 8
+    obs, obs_scores, idxs, avg, avg_scores = synthetic.make_sfm_features(21, n_points)
+    out = {"seed": 21, "n_points": n_points, "num_leaf": L, "np_seed": 123}
+    for tag, n_target in [("same", n_points), ("pad", n_points + 8), ("trunc", n_points - 6)]:
+        d3, s3 = data_utils.pad_features3d_random(avg, avg_scores, n_target)
+        np.random.seed(123)
+        d2, s2 = data_utils.build_features3d_leaves(obs, obs_scores, idxs, n_target, L)
+        out[f"{tag}_n_target"] = n_target
+        out[f"{tag}_desc3d"], out[f"{tag}_scores3d"] = d3.numpy(), s3.numpy()
+        out[f"{tag}_desc2d"], out[f"{tag}_scores2d"] = d2.numpy(), s2.numpy()
+        print("features3d", tag, tuple(d3.shape), tuple(d2.shape), d3.dtype)
+    np.savez_compressed(os.path.join(HERE, "features3d_n40_l8.npz"), **out)
+
+    # forward on a padded object: 88 real points padded to 96 (8 identical all-ones columns), dustbin leaves
+    n_real, n_target, N = 88, 96, 64
+    obs, obs_scores, idxs, avg, avg_scores = synthetic.make_sfm_features(33, n_real, max_len=11)
+    d3, _ = data_utils.pad_features3d_random(avg, avg_scores, n_target)
+    np.random.seed(5)
+    d2, _ = data_utils.build_features3d_leaves(obs, obs_scores, idxs, n_target, L)
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0, damped=True, hparams=hp)
+    model = GATsSuperGlue(hp).eval()
+    model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    q, _ = synthetic.make_frame(77, avg, N)
+    inp = {"keypoints2d": torch.zeros(1, N, 2), "keypoints3d": torch.zeros(1, n_target, 3),
+           "descriptors2d_query": torch.from_numpy(q)[None], "descriptors3d_db": d3[None], "descriptors2d_db": d2[None]}
+    with torch.no_grad():
+        pred, conf = model(inp)
+    conf = conf.numpy()
+    np.savez_compressed(os.path.join(HERE, "dustbin_n64_m96.npz"), desc3d=d3.numpy(), desc2d=d2.numpy(), query=q, n_real=n_real,
+                        matches0=pred["matches0"].numpy(), matches1=pred["matches1"].numpy(),
+                        matching_scores0=pred["matching_scores0"].numpy(), matching_scores1=pred["matching_scores1"].numpy(),
+                        conf_matrix=conf, raw_indices0=conf.argmax(2), raw_indices1=conf.argmax(1))
+    print("dustbin forward: matches", int((pred["matches0"] > -1).sum()), "conf.max", float(conf.max()),
+          "tied padded columns identical:", bool((conf[0][:, n_real:] == conf[0][:, n_real:n_real + 1]).all()))
 
 
 def state_dict_spec():
@@ -131,4 +193,5 @@ if __name__ == "__main__":
     for c in CASES:
         run_case(c)
     empty_case()
-    mean_desc_case()
+    mean_cases()
+    features3d_cases()

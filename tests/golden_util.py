@@ -9,7 +9,7 @@ from onepose_b200 import synthetic
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FORWARD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                       if not os.path.basename(p).startswith(("empty", "mean_desc")))
+                       if not os.path.basename(p).startswith(("empty", "mean_", "features3d", "dustbin")))
 RELEASED_CASES = [c for c in FORWARD_CASES if not c.startswith(("noself", "lintrans", "additional"))]
 
 
@@ -29,3 +29,15 @@ def conf_reference_view(g, conf):
     if "conf_matrix" in g:
         return g["conf_matrix"], conf
     return g["conf_sample"], conf[:, ::7, ::5]
+
+
+def load_dustbin_case():
+    """Forward on an object built by the reference's pad_features3d_random / build_features3d_leaves (all-ones dustbin leaves,
+    duplicate all-ones padded 3D points): inputs are stored in the fixture (they come from the reference functions)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "dustbin_n64_m96.npz"), allow_pickle=False))
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(0, damped=True, hparams=hp)
+    N, M = g["query"].shape[1], g["desc3d"].shape[1]
+    data = {"keypoints2d": np.zeros((1, N, 2), np.float32), "keypoints3d": np.zeros((1, M, 3), np.float32),
+            "descriptors2d_query": g["query"][None], "descriptors3d_db": g["desc3d"][None], "descriptors2d_db": g["desc2d"][None]}
+    return g, hp, sd, data

@@ -48,7 +48,7 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     import ctypes as C
     lib = _lib.load()
-    cfg = _lib.OpbConfig(256, 4, 0.07, 0.2, 1, 0, 0, 0, 0)
+    cfg = _lib.OpbConfig(256, 4, 0.07, 0.2, 1, 0, 0, 0)
     h = C.c_void_p()
     rc = lib.opb_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and b"no CPU path" in lib.opb_last_error(None)
@@ -102,3 +102,25 @@ def test_lightning_checkpoint_standin(tmp_path):
     model = LitModelGATsSPG.load_from_checkpoint(str(path)).eval().freeze()
     assert torch.equal(model.matcher.final_proj.weight, torch.from_numpy(syn["final_proj.weight"]))
     assert not any(p.requires_grad for p in model.parameters())
+
+
+def test_forward_signature_and_module_surface_match_reference():
+    """Same constructor argument, same forward(data) entry, same attribute names the reference callers touch."""
+    import inspect
+    sig = inspect.signature(GATsSuperGlue.__init__)
+    assert list(sig.parameters) == ["self", "hparams"]                      # GATs_SuperGlue.py:145
+    assert list(inspect.signature(GATsSuperGlue.forward).parameters) == ["self", "data"]   # :179
+    m = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS))
+    assert m.match_type == "softmax" and hasattr(m, "gnn") and hasattr(m, "final_proj") and hasattr(m, "bin_score")
+
+
+def test_features3d_module_mirrors_reference_names():
+    from onepose_b200 import features3d
+    import inspect
+    assert list(inspect.signature(features3d.pad_features3d_random).parameters)[:3] == ["descriptors", "scores", "n_target_shape"]
+    assert list(inspect.signature(features3d.build_features3d_leaves).parameters)[:5] == [
+        "descriptors", "scores", "idxs", "n_target_shape", "num_leaf"]                # data_utils.py:143, :163
+    assert list(inspect.signature(features3d.mean_descriptors).parameters)[:2] == ["descriptors", "idxs"]   # feature_process.py:297
+    assert list(inspect.signature(features3d.mean_scores).parameters)[:2] == ["scores", "idxs"]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        features3d.pad_features3d_random(np.ones((4, 3), np.float32), np.ones((3, 1), np.float32), 5, device="cpu")

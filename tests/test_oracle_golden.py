@@ -52,7 +52,36 @@ def test_oracle_rejects_other_match_types():
         oracle.forward({}, synthetic.make_batch(1, [1], 8, 8, 2), hp)
 
 
-def test_oracle_mean_descriptors():
-    g = np.load(f"{GOLDEN_DIR}/mean_descriptors_m300.npz")
-    desc, idxs = synthetic.make_tracks(int(g["seed"]), int(g["M"]))
-    np.testing.assert_allclose(oracle.mean_descriptors(desc, idxs), g["avg"], rtol=0, atol=1e-15)
+@pytest.mark.parametrize("name", ["mean_descriptors_m300", "mean_tracks_long_m48"])
+def test_oracle_segmented_means_match_reference_source(name):
+    """mean_descriptors / mean_scores: the goldens are outputs of the reference's own source text (make_golden.mean_cases)."""
+    g = np.load(f"{GOLDEN_DIR}/{name}.npz")
+    desc, idxs = synthetic.make_tracks(int(g["seed"]), int(g["M"]), max_len=int(g["max_len"]))
+    scores = synthetic.make_track_scores(int(g["seed"]), idxs)
+    np.testing.assert_array_equal(oracle.mean_descriptors(desc, idxs), g["avg"])
+    np.testing.assert_array_equal(oracle.mean_scores(scores, idxs), g["avg_scores"])
+
+
+def test_oracle_features3d_match_reference():
+    """pad_features3d_random / build_features3d_leaves: byte-identical to the imported reference under the same np.random.seed."""
+    g = np.load(f"{GOLDEN_DIR}/features3d_n40_l8.npz")
+    obs, obs_scores, idxs, avg, avg_scores = synthetic.make_sfm_features(int(g["seed"]), int(g["n_points"]))
+    for tag in ("same", "pad", "trunc"):
+        nt = int(g[f"{tag}_n_target"])
+        d3, s3 = oracle.pad_features3d_random(avg, avg_scores, nt)
+        np.random.seed(int(g["np_seed"]))
+        d2, s2 = oracle.build_features3d_leaves(obs, obs_scores, idxs, nt, int(g["num_leaf"]))
+        for mine, key in ((d3, "desc3d"), (s3, "scores3d"), (d2, "desc2d"), (s2, "scores2d")):
+            assert mine.dtype == np.float32 and mine.tobytes() == g[f"{tag}_{key}"].tobytes(), (tag, key)
+
+
+def test_oracle_dustbin_object_matches_reference():
+    """Reference-built object with all-ones dustbin leaves and duplicate padded 3D points: exactly tied confidences."""
+    from tests.golden_util import load_dustbin_case
+    g, hp, sd, data = load_dustbin_case()
+    out = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+    assert np.abs(out["conf_matrix"].numpy() - g["conf_matrix"]).max() < 2e-5
+    np.testing.assert_array_equal(out["matches0"][0].numpy(), g["matches0"])
+    np.testing.assert_array_equal(out["matches1"][0].numpy(), g["matches1"])
+    n_real = int(g["n_real"])
+    assert (g["conf_matrix"][0][:, n_real:] == g["conf_matrix"][0][:, n_real:n_real + 1]).all()     # the tie is exact in the reference
