@@ -11,9 +11,15 @@ of frames (object-sharded, weak scaling, no collective on the data path; one NCC
 all_gather of per-rank records at the end -- SURVEY 8e).
 
 Printed JSON line (rank 0): see the contract in the task description; extra objects
-``roofline`` (dominant kernel = the tensor-core GEMM core, measured live with CUDA
-events around its launches through the library's profiling hook) and ``cpu_baseline``
-(the oracle port of the reference's CPU forward, timed on this box's host cores).
+  roofline      dominant kernel = the mlp.0 tensor-core GEMM, measured live with CUDA events after every launch
+                (the library's profiling hook); `hbm_kernels` = the HBM-bound kernels the same way
+  cpu_baseline  the oracle port of the reference's CPU forward, timed on this box's host cores (rank 0, N=1)
+  parity_check  one frame of the last timed step compared with that CPU forward (conf, match indices)
+  value_no_conf the same step without materialising the confidence matrix (inference.py:146 discards it)
+  latency_b1    the reference's own calling convention: B=1 per frame through forward(data) (inference.py:80-94,146)
+  config4       BASELINE configs[3]: B=16, N2D=2000, N3D=15000 (full step and tail only)
+  config5       BASELINE configs[4] substitute: 80 heterogeneous synthetic objects, LPT-sharded over the ranks, set_object and
+                workspace growth inside the timed region, STRONG scaling (fixed total work) -- whole-job frames/s
 """
 from __future__ import annotations
 
@@ -45,7 +51,7 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return {"tflops": j["bf16_tflops_sustained"], "hbm_gbs": j["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+        return {"tflops": j["bf16_tflops_sustained"], "hbm_gbs": j["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)"}
     return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
@@ -105,34 +111,43 @@ def cpu_model():
     return "unknown"
 
 
-def time_cpu_port(frames_budget_s, max_frames, n_warm=1):
-    """The oracle port of the reference CPU forward, B=1 per call (the reference's own calling
-    convention, inference.py:85-92), all host threads.  Returns (frames/s, per-frame seconds list)."""
+def _oracle_setup():
     from onepose_b200 import synthetic
     from oracle import gats_spg_oracle as oracle
     torch.set_num_threads(cpu_threads())
     sd = synthetic.make_state_dict(0)
-    P = oracle.params_from_numpy(sd)
-    hp = synthetic.DEFAULT_HPARAMS
-    db, leaves = synthetic.make_object(0, N3D, NLEAF)
+    return synthetic, oracle, oracle.params_from_numpy(sd), synthetic.DEFAULT_HPARAMS
+
+
+def _oracle_one(oracle, P, hp, q, db, leaves):
+    data = {"keypoints2d": np.zeros((1, q.shape[1], 2), np.float32), "keypoints3d": np.zeros((1, db.shape[1], 3), np.float32),
+            "descriptors2d_query": q[None], "descriptors3d_db": db[None], "descriptors2d_db": leaves[None]}
+    data = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in data.items()}
+    t0 = time.perf_counter()
+    out = oracle.forward(P, data, hp)
+    return time.perf_counter() - t0, out
+
+
+def time_cpu_port(first_q, db, leaves, frames_budget_s, max_frames, n_warm=1):
+    """The oracle port of the reference CPU forward, B=1 per call (the reference's own calling convention,
+    inference.py:85-92), all host threads.  The first forward runs on `first_q` (a frame the GPU just processed) and its
+    result is returned for the parity check.  Returns (frames/s, per-frame seconds list, first result)."""
+    synthetic, oracle, P, hp = _oracle_setup()
     times = []
     t_begin = time.time()
+    first = None
     f = 0
     while True:
-        q, _ = synthetic.make_frame(f, db, N2D)
-        data = {"keypoints2d": np.zeros((1, N2D, 2), np.float32), "keypoints3d": np.zeros((1, N3D, 3), np.float32),
-                "descriptors2d_query": q[None], "descriptors3d_db": db[None], "descriptors2d_db": leaves[None]}
-        data = {k: torch.from_numpy(v) for k, v in data.items()}
-        t0 = time.perf_counter()
-        oracle.forward(P, data, hp)
-        dt = time.perf_counter() - t0
+        q = first_q if f == 0 else synthetic.make_frame(7000 + f, db, N2D)[0]
+        dt, out = _oracle_one(oracle, P, hp, q, db, leaves)
+        if f == 0:
+            first = out
         if f >= n_warm:
             times.append(dt)
         f += 1
         if len(times) >= max_frames or (times and time.time() - t_begin > frames_budget_s):
             break
-    med = statistics.median(times)
-    return 1.0 / med, times
+    return 1.0 / statistics.median(times), times, first
 
 
 def run_reference(args, rank, world):
@@ -140,28 +155,13 @@ def run_reference(args, rank, world):
     reference cannot travel to the GPU box) on this box's host cores."""
     if rank != 0:
         return
-    per_step = []
-    from onepose_b200 import synthetic
-    from oracle import gats_spg_oracle as oracle
-    torch.set_num_threads(cpu_threads())
-    sd = synthetic.make_state_dict(0)
-    P = oracle.params_from_numpy(sd)
-    hp = synthetic.DEFAULT_HPARAMS
+    synthetic, oracle, P, hp = _oracle_setup()
     db, leaves = synthetic.make_object(0, N3D, NLEAF)
-
-    def one(fid):
-        q, _ = synthetic.make_frame(fid, db, N2D)
-        data = {"keypoints2d": np.zeros((1, N2D, 2), np.float32), "keypoints3d": np.zeros((1, N3D, 3), np.float32),
-                "descriptors2d_query": q[None], "descriptors3d_db": db[None], "descriptors2d_db": leaves[None]}
-        data = {k: torch.from_numpy(v) for k, v in data.items()}
-        t0 = time.perf_counter()
-        oracle.forward(P, data, hp)
-        return time.perf_counter() - t0
-
+    per_step = []
     for w in range(args.warmup):
-        one(w)
+        _oracle_one(oracle, P, hp, synthetic.make_frame(w, db, N2D)[0], db, leaves)
     for s in range(args.steps):
-        per_step.append(one(1000 + s))
+        per_step.append(_oracle_one(oracle, P, hp, synthetic.make_frame(1000 + s, db, N2D)[0], db, leaves)[0])
     total = sum(per_step)
     fps = args.steps / total
     line = {
@@ -178,6 +178,126 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------- extra legs (each bounded, best effort)
+def leg_latency_b1(model, dev, db, leaves, q_host, n_frames=40):
+    """B=1 per frame through forward(data), the object tensors re-passed with every frame like pack_data does
+    (inference.py:80-94).  device: inputs resident, CUDA events around each call (L2 not flushed: consecutive frames of a
+    sequence are what the caller sends).  e2e: per frame pinned-host query -> .cuda() -> forward -> matches0/scores0 .cpu()."""
+    d3 = torch.from_numpy(db)[None].to(dev)
+    d2 = torch.from_numpy(leaves)[None].to(dev)
+    k2 = torch.zeros(1, N2D, 2, device=dev)
+    k3 = torch.zeros(1, N3D, 3, device=dev)
+    qd = [q_host[0][f:f + 1].to(dev) for f in range(8)]
+    mk = lambda q: {"keypoints2d": k2, "keypoints3d": k3, "descriptors2d_query": q, "descriptors3d_db": d3, "descriptors2d_db": d2}   # noqa: E731
+    for f in range(5):
+        model(mk(qd[f % 8]))
+    launches = model.launch_count()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_frames)]
+    t0 = time.perf_counter()
+    for f in range(n_frames):
+        ev[f][0].record()
+        model(mk(qd[f % 8]))
+        ev[f][1].record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    dev_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    # end to end per frame, host in / host out, one frame in flight (what inference.py:140-151 does)
+    qh = [q_host[0][f:f + 1].clone().pin_memory() for f in range(8)]
+    for f in range(3):
+        pred, _ = model(mk(qh[f % 8].to(dev, non_blocking=True)))
+        pred["matches0"].cpu()
+    t0 = time.perf_counter()
+    for f in range(n_frames):
+        pred, _ = model(mk(qh[f % 8].to(dev, non_blocking=True)))
+        pred["matches0"].cpu()
+        pred["matching_scores0"].cpu()
+    e2e = (time.perf_counter() - t0) / n_frames
+    return {"device_ms_median": dev_ms[len(dev_ms) // 2], "device_ms_min": dev_ms[0], "back_to_back_ms": 1e3 * wall / n_frames,
+            "e2e_ms": 1e3 * e2e, "frames": n_frames, "launches_per_frame": launches,
+            "note": "B=1 forward(data) with the per-object tensors re-passed every frame (inference.py:80-94,146); conf matrix materialised; "
+                    "device_ms = CUDA events around one call, back_to_back = wall clock of the loop / frames (launch-bound if > device_ms)"}
+
+
+def leg_config4(model, dev, synthetic, steps=3):
+    """BASELINE configs[3]: dense-SfM stress, B=16, N2D=2000, N3D=15000 -- full step and the dual-softmax + mutual-NN tail alone."""
+    B, N, M = 16, 2000, 15000
+    db, leaves = synthetic.make_object(4, M, NLEAF)
+    q = torch.from_numpy(np.stack([synthetic.make_frame(9000 + f, db, N)[0] for f in range(B)], 0)).to(dev)
+    model.set_object(torch.from_numpy(db).to(dev), torch.from_numpy(leaves).to(dev), reserve=(B, N))
+    for _ in range(2):
+        out = model.match_frames(q)
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        ev[s][0].record()
+        out = model.match_frames(q)
+        ev[s][1].record()
+    torch.cuda.synchronize(dev)
+    ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+    model.set_profiling(True)
+    model.match_frames(q)
+    tail = 0.0
+    for name in ("gemm epi5 ", "gemm epi6 ", "gemm epi7 ", "score_sums_finalize", "mutual_match"):
+        tail += model.get_profile_entry(name)["ms"]
+    model.set_profiling(False)
+    conf_bytes = B * N * M * 4
+    return {"workload": f"B={B} N2D={N} N3D={M} L={NLEAF}", "ms_per_step": ms, "frames_per_s": B / (ms * 1e-3),
+            "tail_ms": tail, "tail_conf_write_floor_ms": conf_bytes / (peaks()["hbm_gbs"] * 1e9) * 1e3,
+            "matches_per_batch": int((out["matches0"] > -1).sum()),
+            "whole_step_tflops": algorithmic_flops_per_frame(N, M) * B / (ms * 1e-3) / 1e12,
+            "note": "tail = final_proj + two score-GEMM passes (sums, conf + arg-max) + finalize + mutual-NN, in-stream events"}
+
+
+def leg_config5(model, dev, rank, world, dist, seed=5):
+    """BASELINE configs[4] substitute: 80 heterogeneous synthetic objects, statically LPT-partitioned over the
+    ranks by frames x (N2D + N3D); per object set_object + batches of <= 32 frames; workspace growth and per-object constants
+    inside the timed region; no data-path collective.  Strong scaling: the job is the same at every world size."""
+    from onepose_b200 import sharding
+    jobs = sharding.hetero_job(seed)
+    plan = sharding.partition_lpt([j["cost"] for j in jobs], world)
+    mine = [jobs[i] for i in plan[rank]]
+    g = torch.Generator(device=dev)
+    data = []
+    for j in mine:                                            # synthetic descriptors generated on the device, outside the timed region
+        g.manual_seed(1000 + j["id"])
+        db = torch.nn.functional.normalize(torch.randn(DIM, j["M"], device=dev, generator=g), dim=0)
+        leaves = torch.nn.functional.normalize(db.repeat_interleave(NLEAF, dim=1) + 0.02 * torch.randn(DIM, j["M"] * NLEAF, device=dev, generator=g), dim=0)
+        q = torch.randn(j["frames"], DIM, j["N"], device=dev, generator=g)
+        n_plant = min(j["N"] // 2, j["M"])
+        q[:, :, :n_plant] = db[:, :n_plant][None] + 0.03 * q[:, :, :n_plant]
+        data.append((db, leaves, torch.nn.functional.normalize(q, dim=1)))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_match = torch.zeros((), dtype=torch.int64, device=dev)
+    t0 = time.perf_counter()
+    e0.record()
+    for (db, leaves, q) in data:
+        model.set_object(db, leaves)
+        for f0 in range(0, q.shape[0], 32):
+            out = model.match_frames(q[f0:f0 + 32])
+            n_match += (out["matches0"] > -1).sum()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    busy_ms = e0.elapsed_time(e1)
+    rec = torch.tensor([float(sum(j["frames"] for j in mine)), busy_ms, float(len(mine)), float(sum(j["cost"] for j in mine)), float(n_match.item()),
+                        1e3 * wall], dtype=torch.float64, device=dev)
+    allrec = sharding.gather_records(rec)
+    frames = float(allrec[:, 0].sum())
+    busy = allrec[:, 1]
+    return {"workload": "80 synthetic objects, M~U[800,2500], N~U[300,2000], frames~U[50,400], 17593 frames (sharding.hetero_job seed 5)",
+            "scaling": "strong", "frames": frames, "job_ms": float(busy.max()), "frames_per_s": frames / (float(busy.max()) * 1e-3),
+            "per_rank_busy_ms": [round(float(x), 2) for x in busy], "per_rank_objects": [int(x) for x in allrec[:, 2]],
+            "imbalance_max_over_mean": float(busy.max() / busy.mean()), "lpt_cost_imbalance": float(allrec[:, 3].max() / allrec[:, 3].mean()),
+            "matches": float(allrec[:, 4].sum()), "host_wall_ms_max": float(allrec[:, 5].max()),
+            "note": "set_object, ragged shapes and workspace growth inside the timed region; conf matrix materialised; "
+                    "device time per rank by CUDA events, job time = max over ranks"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +307,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="frames per step (batch of one object)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per GNN chunk (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (latency_b1, config4, config5)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -205,7 +326,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from onepose_b200 import GATsSuperGlue, synthetic
+    from onepose_b200 import GATsSuperGlue, sharding, synthetic
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(0)
     model = GATsSuperGlue(hp).eval()
@@ -223,7 +344,7 @@ def main():
         qs = np.stack([synthetic.make_frame(100000 * rank + 1000 * s + f, db, N2D)[0] for f in range(B)], 0)
         q_host.append(torch.from_numpy(qs).pin_memory())
     q_dev = [q.to(dev) for q in q_host]
-    model.set_object(torch.from_numpy(db).to(dev), torch.from_numpy(leaves).to(dev))
+    model.set_object(torch.from_numpy(db).to(dev), torch.from_numpy(leaves).to(dev), reserve=(B, N2D))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -231,6 +352,18 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        """`steps` calls of fn(slot), CUDA events around each (L2 flushed in between, outside the event pair); returns summed ms."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        out = None
+        for s in range(steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record()
+            out = fn(s % n_slots)
+            ev[s][1].record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), out
 
     # ---------------- device-resident throughput ("value") ----------------
     for w in range(args.warmup):
@@ -241,22 +374,31 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.fill_(s & 0xFF)                       # L2 flush between timed iterations (outside the event pair)
-        ev[s][0].record()
-        out = model.match_frames(q_dev[s % n_slots])
-        ev[s][1].record()
-    barrier()
+    my_ms, out = timed(lambda s: model.match_frames(q_dev[s]), args.steps)
     wall = time.perf_counter() - wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    my_ms = sum(step_ms)
+    last_slot = (args.steps - 1) % n_slots
     t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    model.check_range()
+    check_frame = 0
+    check_conf = out["conf_matrix"][check_frame].cpu()
+    check_m0 = out["matches0"][check_frame].cpu()
+    check_m1 = out["matches1"][check_frame].cpu()
+    del out
+
+    # ---------------- the same step without the confidence matrix (inference.py:146 discards it) ----------------
+    for w in range(2):
+        model.match_frames(q_dev[w % n_slots], return_conf=False)
+    barrier()
+    nc_ms, _ = timed(lambda s: model.match_frames(q_dev[s], return_conf=False), args.steps)
+    t1 = torch.tensor([nc_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    nc_total_ms = float(t1.item())
 
     # ---------------- end to end through the public host-buffer call ("e2e") ----------------
     host_out = None
@@ -266,7 +408,7 @@ def main():
     e2e_t0 = time.perf_counter()
     e2e_steps = args.steps
     for s in range(e2e_steps):
-        host_out = model.match_frames_host(q_host[s % n_slots], host_out)   # H2D + forward + D2H + sync inside
+        host_out = model.match_frames_host(q_host[s % n_slots], host_out)   # H2D + forward (conf materialised) + D2H + sync inside
     barrier()
     e2e_s = time.perf_counter() - e2e_t0
     t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -275,34 +417,68 @@ def main():
     e2e_s = float(t2.item())
     assert int((host_out["matches0"] > -1).sum()) > 0
 
-    # ---------------- roofline of the dominant kernel (GEMM core), measured live ----------------
+    # ---------------- roofline of the dominant kernel (mlp.0 GEMM) and of the HBM-bound kernels, measured live ----------------
     model.set_profiling(True)
     prof_runs = []
     for s in range(3):
         model.match_frames(q_dev[s % n_slots])
         prof_runs.append(model.get_profile())
-    dom = model.get_profile_entry("gemm epi1 ")      # (trailing blank: not "epi10") dominant kernel: the mlp.0 GEMM variant (largest single kernel of the step)
+    dom = model.get_profile_entry("gemm epi1 ")      # (trailing blank: not "epi10") the mlp.0 GEMM: largest single kernel of the step
+    entries = {k: model.get_profile_entry(k) for k in ("gats_aggregate", "kv_state_h", "gemm epi7 ", "gemm epi6 ")}
     model.set_profiling(False)
     prof = prof_runs[-1]
     pk = peaks()
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     dom_tflops = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
-    ncu_path = os.path.join(ROOT, "profiles", "r1_v5_ncu_summary.json")
+    n_pad, m_pad = (N2D + 255) // 256 * 256, (N3D + 255) // 256 * 256
+    rows = B * (n_pad + m_pad)
+
+    def hbm(entry, bytes_per_step, what):
+        e = entries[entry]
+        if e["launches"] == 0 or e["ms"] <= 0:
+            return None
+        gbs = bytes_per_step / (e["ms"] * 1e-3) / 1e9
+        return {"kernel": what, "launches_per_step": e["launches"], "ms_per_step": e["ms"],
+                "algorithmic_MB_per_step": bytes_per_step / 1e6, "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
+
+    hbm_kernels = [x for x in (
+        # per step: the object prologue runs layer 0 on one copy of the object, layers 3, 6, 9 on all B frames: leaves once per launch
+        # + one read and one write of every 3D row it touches
+        hbm("gats_aggregate", 4 * (4.0 * N3D * NLEAF * DIM) + 2.0 * 1024 * N3D * (1 + 3 * B), "gats_aggregate_frames8 (fp32 leaf rows + x planes r/w)"),
+        # 9 launches per step: 7 on the full layout, 1 on the query-only rows, 1 on the object rows
+        hbm("kv_state_h", 1024.0 * (7 * rows + B * n_pad + m_pad), "kv_state_h_kernel (fp16 [K|V] plane read)"),
+        hbm("gemm epi7 ", 4.0 * B * N2D * N3D, "score GEMM pass 2 (EPI_SCORE_CONF): mandatory conf write"),
+    ) if x]
+    ncu_path = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
     traffic = None
-    if os.path.exists(ncu_path):                     # DRAM bytes of one launch of that variant from the committed ncu --set full capture
-        for k in json.load(open(ncu_path))["launches"]:
-            if "gemm_tc_kernel<64, 2, 1, 1, 0>" in k["kernel"] and k["dram_read_MB"] is not None:   # <BK, cluster, 2-CTA, EPI_F32_STATS, no converter>
+    if os.path.exists(ncu_path):                     # DRAM bytes of one full-chunk launch of that variant from the committed ncu --set full capture
+        for k in json.load(open(ncu_path)).get("launches", []):
+            if "gemm_tc_kernel<1, 0>" in k["kernel"] and k.get("dram_read_MB") is not None:
                 traffic = (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
+
+    # ---------------- extra legs (bounded; a failure is reported, not fatal) ----------------
+    extra = {}
+    if not args.no_extra:
+        for name, fn in (("latency_b1", lambda: leg_latency_b1(model, dev, db, leaves, q_host)),
+                         ("config4", lambda: leg_config4(model, dev, synthetic)),
+                         ("config5", lambda: leg_config5(model, dev, rank, world, dist))):
+            try:
+                extra[name] = fn()
+            except Exception as e:            # noqa: BLE001
+                extra[name] = {"error": f"{type(e).__name__}: {e}"}
+                if name == "config5" and world > 1:
+                    raise
+        # the legs above changed the object: nothing below uses the model
 
     # ---------------- per-rank records over NCCL (the path's only collective) ----------------
     rec = torch.tensor([float(B * args.steps), my_ms, float(n_match)], dtype=torch.float64, device=dev)
-    from onepose_b200 import sharding
     allrec = sharding.gather_records(rec)           # the path's only collective: one all_gather of a 3-double record
     frames_total = float(allrec[:, 0].sum())
 
     if rank == 0:
         fps = frames_total / (total_ms * 1e-3)
         e2e_fps = (B * e2e_steps * world) / e2e_s
+        whole = algorithmic_flops_per_frame(N2D, N3D) * B / (total_ms / args.steps * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,10 +493,13 @@ def main():
                     "note": "opb_forward_host: pinned H2D of query descriptors, forward incl. conf matrix on device, D2H of matches+scores, sync"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
+            "value_no_conf": frames_total / (nc_total_ms * 1e-3),
             "roofline": {"bound": "tensor",
                          "kernel": "gemm_tc_kernel<EPI_F32_STATS>: mlp.0 GEMM [x|Q'].[W0a|G]^T, N=512 K=512 (largest single kernel of the step)",
                          "achieved": dom_tflops, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": dom_tflops / pk["tflops"],
-                         "traffic": traffic, "peak_source": pk["source"],
+                         "traffic": traffic,
+                         "traffic_source": "profiles/r2_ncu_summary.json (ncu --set full of the same launch; regenerated by tools/final_round.sh)" if traffic else None,
+                         "peak_source": pk["source"],
                          "note": "algorithmic FLOPs (each logical MMA counted once); the kernel executes 3 fp16 passes per logical product, "
                                  "so frac <= 1/3 by construction and executed tensor throughput = 3 x achieved",
                          "executed_tflops": 3 * dom_tflops, "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
@@ -329,14 +508,21 @@ def main():
                          "gemm_ms_per_step": prof["gemm_ms"], "step_ms_profiled": prof["total_ms"], "gemm_share_of_step": prof["gemm_ms"] / prof["total_ms"],
                          "gemm_launches_per_step": prof["gemm_launches"],
                          "algorithmic_gflop_per_frame": algorithmic_flops_per_frame(N2D, N3D) / 1e9,
-                         "whole_step_tflops": algorithmic_flops_per_frame(N2D, N3D) * B / (total_ms / args.steps * 1e-3) / 1e12},
+                         "whole_step_tflops": whole, "whole_step_frac": whole / pk["tflops"],
+                         "hbm_kernels": hbm_kernels},
             "matches_per_batch": n_match, "wall_s_timed_region": wall,
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
-            cpu_fps, times = time_cpu_port(frames_budget_s=20.0, max_frames=8)
+            cpu_fps, times, first = time_cpu_port(q_host[last_slot][check_frame].numpy(), db, leaves, frames_budget_s=20.0, max_frames=8)
             line["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                                     "sample": f"{len(times)} single-frame forwards (B=1) of the oracle port at the same shape, torch CPU fp32, "
                                               f"{cpu_threads()} threads of {os.cpu_count()} logical CPUs, median; cpu={cpu_model()}"}
+            dconf = float((check_conf - first["conf_matrix"][0]).abs().max())
+            eq0, eq1 = bool(torch.equal(check_m0, first["matches0"][0])), bool(torch.equal(check_m1, first["matches1"][0]))
+            line["parity_check"] = {"frame": f"slot {last_slot} frame {check_frame} of the last timed step (B={B})",
+                                    "max_abs_dconf": dconf, "matches0_equal": eq0, "matches1_equal": eq1,
+                                    "n_matches": int((check_m0 > -1).sum()), "tolerance": 1e-4, "ok": bool(dconf <= 1e-4 and eq0 and eq1)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -105,11 +105,13 @@ struct opb_matcher {
   DevBuf leaves;          // fp32 [M*Lf, 256] point-major
   PlaneBuf db;            // [m_pad, 256]
   DevBuf s2;              // [4][M*Lf]
+  PlaneBuf xo;            // [m_pad, 256]: 3D-point state entering layer 2 (object prologue), valid while prologue_ready
+  bool prologue_ready = false;
   // workspace (chunk)
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
   bool hoist = true;      // evaluate the frame-invariant layers once per call (object_prologue)
-  PlaneBuf x, qp, pn, g, xo, xq, bd, lin_a, lin_b;
+  PlaneBuf x, qp, pn, g, xq, bd, lin_a, lin_b;
   DevBuf kvt;             // fp16 [rows, 512]
   DevBuf hid, kvpart, kmean, statpart, mu, rstd, rowsum_part, colsum_part, rowsum, colsum, rowbest, colbest;
   DevBuf range_flag;
@@ -239,7 +241,6 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->pn.ensure(rows * kD, true));
   CK(m, m->g.ensure(S * 512 * kD));
   CK(m, m->bd.ensure(S * kD * kD, true));          // block-diagonal state operand: off-diagonal blocks stay zero for the buffer's lifetime
-  CK(m, m->xo.ensure((size_t)m->m_pad * kD, true));
   CK(m, m->xq.ensure((size_t)frames * n_pad * kD, true));
   CK(m, m->kvt.ensure(rows * 512 * sizeof(__half), true));
   CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
@@ -344,7 +345,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p2.epi = EPI_F32_STATS; p2.statpart = m->statpart.as<float>();
   if (int rc = run_gemm(m, p2, st, 2.0 * valid_rows * 512 * 512, "mlp0")) return rc;
   // (6) InstanceNorm statistics per segment (:126)
-  LAUNCH(m, st, "in_stats_final", in_stats_final, dim3(S, 16), dim3(32, 8), 0, st, (const float*)m->statpart.as<float>(), L, m->mu.as<float>(),
+  LAUNCH(m, st, "in_stats_final", in_stats_final, dim3(S, 16), dim3(32, kStatSlices), 0, st, (const float*)m->statpart.as<float>(), L, m->mu.as<float>(),
          m->rstd.as<float>());
   // (7) x <- x + mlp.3(ReLU(IN(hidden)))  (:122, :59/:64): the converters form hn inside the GEMM, the residual is an identity K-block
   GemmProblem p3{};
@@ -358,8 +359,9 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
 
 // Object prologue: GNN layers 0 (GATs) and the 3D side of layer 1 (self-attention) depend only on the per-object
 // constants (reference GATs_SuperGlue.py:50-54 and :60-64 with src1 = desc3d_db), not on the query frame.  They are
-// evaluated ONCE per opb_forward call -- on a single copy of the object's rows -- and shared by all frames of the
-// call instead of once per frame.  Result: m->xo = 3D-point state entering layer 2.
+// evaluated ONCE PER OBJECT -- on a single copy of the object's rows, by the first opb_forward after opb_set_object /
+// opb_finalize_weights (it needs the chunk workspace) -- and shared by every frame of every later call, like the leaf
+// logits s2.  Result: m->xo = 3D-point state entering layer 2.
 static int object_prologue(opb_matcher* m, cudaStream_t st) {
   Layout Lo{};
   Lo.B = 1; Lo.N = 0; Lo.M = m->M; Lo.n_pad = 0; Lo.m_pad = m->m_pad; Lo.R = m->m_pad;
@@ -494,7 +496,7 @@ void opb_destroy(opb_matcher* m) {
                     &m->mu, &m->rstd, &m->rowsum_part, &m->colsum_part, &m->rowsum, &m->colsum, &m->rowbest, &m->colbest, &m->range_flag,
                     &m->st_q, &m->st_m0, &m->st_m1, &m->st_s0, &m->st_s1, &m->st_conf, &m->st_len};
   for (auto* b : bufs) b->release();
-  PlaneBuf* pb[] = {&m->wf, &m->wlin, &m->db, &m->x, &m->qp, &m->pn, &m->g, &m->xo, &m->xq, &m->bd, &m->lin_a, &m->lin_b, &m->eye};
+  PlaneBuf* pb[] = {&m->wf, &m->wlin, &m->db, &m->xo, &m->x, &m->qp, &m->pn, &m->g, &m->xq, &m->bd, &m->lin_a, &m->lin_b, &m->eye};
   for (auto* b : pb) b->release();
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   for (auto e : m->h2d_ev) cudaEventDestroy(e);
@@ -602,7 +604,8 @@ int opb_finalize_weights(opb_matcher* m) {
   if (int rc = upload_f32(m, m->wa3, wa3)) return rc;
   CK(m, cudaDeviceSynchronize());
   m->weights_ready = true;
-  m->object_ready = false;  // s2 depends on the weights
+  m->object_ready = false;  // s2 and the prologue depend on the weights
+  m->prologue_ready = false;
   return OPB_OK;
 }
 
@@ -617,11 +620,13 @@ int opb_set_object(opb_matcher* m, const float* desc3d_db, const float* desc2d_d
   if (m_pad != m->m_pad) { m->ws_frames = 0; m->ws_N = 0; }  // workspace depends on m_pad
   m->M = M; m->Lf = Lf; m->m_pad = m_pad;
   const long long n_leaf_rows = (long long)M * Lf;
-  m->leaves.grew = m->db.hi.grew = m->db.lo.grew = m->s2.grew = false;
+  m->leaves.grew = m->db.hi.grew = m->db.lo.grew = m->s2.grew = m->xo.hi.grew = false;
+  m->prologue_ready = false;
   CK(m, m->leaves.ensure((size_t)n_leaf_rows * kD * sizeof(float)));
   CK(m, m->db.ensure((size_t)m_pad * kD));
   CK(m, m->s2.ensure((size_t)4 * n_leaf_rows * sizeof(float)));
-  if (m->leaves.grew || m->db.hi.grew || m->s2.grew) CK(m, cudaDeviceSynchronize());   // frees of the old buffers vs work in flight
+  CK(m, m->xo.ensure((size_t)m_pad * kD));
+  if (m->leaves.grew || m->db.hi.grew || m->s2.grew || m->xo.hi.grew) CK(m, cudaDeviceSynchronize());   // frees of the old buffers vs work in flight
   launch_k(transpose_cf_to_rows<1>, dim3((unsigned)((n_leaf_rows + 31) / 32), 1), dim3(32, 8), 0, st, desc2d_db, (int)n_leaf_rows, (int)n_leaf_rows, 0ll,
            (const int*)nullptr, (int)n_leaf_rows, (__half*)nullptr, (__half*)nullptr, m->leaves.as<float>(), 0ll, 0);
   // rows [M, m_pad) of the object planes are written as zero by the transpose (MODE 0 pads to rows_out)
@@ -670,8 +675,9 @@ int opb_forward(opb_matcher* m, const float* q, const int32_t* n2d_lengths, int3
     if (!m->ev_fwd0) { cudaEventCreate(&m->ev_fwd0); cudaEventCreate(&m->ev_fwd1); }
     cudaEventRecord(m->ev_fwd0, st);
   }
-  if (m->hoist) {
+  if (m->hoist && !m->prologue_ready) {
     if (int rc = object_prologue(m, st)) return rc;
+    m->prologue_ready = true;
   }
   // granularity of the query-side layer-1 pass: the host-copy pieces when the queries stream in from the host, else the chunk
   const int piece = m->h2d_pending > 0 ? std::min(chunk, kQPassFrames) : chunk;

@@ -236,7 +236,7 @@ __global__ void gats_aggregate(const __half* x_hi, const __half* x_lo, Layout L,
 // Same layer, warp per (POINT, group of 8 frames): the point's 8 leaf rows and leaf logits are read once into registers and
 // reused for every frame of the group (the leaves are per-object constants; reference GATs.py:46 reshapes the same tensor for
 // every batch element).  Fast path for num_leaf == 8 (the released configuration, test_GATsSPG.yaml:5).
-constexpr int kGatsFramesPerWarp = 8;
+constexpr int kGatsFramesPerWarp = 16;   // leaf rows re-read once per 16 frames (8: 229 MB of leaf traffic per layer at B = 32, 16: 115 MB)
 __global__ void __launch_bounds__(256) gats_aggregate_frames8(const __half* x_hi, const __half* x_lo, Layout L,
                                                               const float* __restrict__ leaves, const float* __restrict__ s2,
                                                               const float* __restrict__ wa3, int include_self, int additional, float alpha,
@@ -372,10 +372,12 @@ __global__ void kv_state_reduce(const float* __restrict__ partial, Layout L, KvG
 // (reference GATs_SuperGlue.py:126: no affine, biased variance, eps 1e-5).
 // Stage 1: per 32-row quarter and channel: sum, sum of squares (fp32) -- written by the mlp.0 GEMM epilogue (EPI_F32_STATS).
 // Stage 2, here: per (segment, channel): fixed-order fp64 combine -> mean, rstd.
-// grid (S, 16), block (32 channels, 8 slices)
+// grid (S, 16), block (32 channels, kStatSlices slices): the slices keep enough independent loads in flight that the kernel is
+// not a chain of dependent L2 round trips (8 slices: 17 us per launch at 224 quarters per segment)
 // ---------------------------------------------------------------------------------------
-__global__ void in_stats_final(const float* __restrict__ part, Layout L, float* __restrict__ mu, float* __restrict__ rstd) {
-  __shared__ double sh[8][32][2];
+constexpr int kStatSlices = 32;
+__global__ void __launch_bounds__(32 * kStatSlices) in_stats_final(const float* __restrict__ part, Layout L, float* __restrict__ mu, float* __restrict__ rstd) {
+  __shared__ double sh[kStatSlices][32][2];
   griddep_sync();
   const int seg = blockIdx.x;
   const int c = blockIdx.y * 32 + threadIdx.x;
@@ -384,7 +386,7 @@ __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* 
   const int valid = L.seg_valid(seg);
   const int nq = (valid + 31) / 32;
   double s = 0.0, s2 = 0.0;
-  for (int t = slice; t < nq; t += 8) {
+  for (int t = slice; t < nq; t += kStatSlices) {
     const float2 v = reinterpret_cast<const float2*>(part)[(long long)(q0 + t) * 512 + c];
     s += (double)v.x;
     s2 += (double)v.y;
@@ -395,7 +397,7 @@ __global__ void in_stats_final(const float* __restrict__ part, Layout L, float* 
   if (slice == 0) {
     s = 0.0; s2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s += sh[k][threadIdx.x][0]; s2 += sh[k][threadIdx.x][1]; }
+    for (int k = 0; k < kStatSlices; ++k) { s += sh[k][threadIdx.x][0]; s2 += sh[k][threadIdx.x][1]; }
     const double n = (double)(valid > 0 ? valid : 1);
     const double mean = s / n;
     double var = s2 / n - mean * mean;

@@ -46,3 +46,17 @@ def gather_records(record: torch.Tensor, group=None) -> torch.Tensor:
     parts = [torch.empty_like(record) for _ in range(world)]
     dist.all_gather(parts, record.contiguous(), group=group)
     return torch.stack(parts, 0)
+
+
+def hetero_job(seed: int = 5, n_objects: int = 80):
+    """Stand-in for the reference's evaluation set (configs/experiment/test_GATsSPG.yaml:27-106: 80 (object, sequence) pairs looped
+    by inference.py:185-198) when the data is not mounted -- SURVEY 8d: per object M ~ U[800, 2500] 3D points, N ~ U[300, 2000]
+    query points, U[50, 400] frames.  Deterministic in `seed`; every rank computes the same list.
+    Returns a list of dicts {id, M, N, frames, cost}."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    jobs = []
+    for i in range(n_objects):
+        M, N, F = int(rs.randint(800, 2501)), int(rs.randint(300, 2001)), int(rs.randint(50, 401))
+        jobs.append({"id": i, "M": M, "N": N, "frames": F, "cost": object_cost(F, N, M)})
+    return jobs

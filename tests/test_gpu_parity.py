@@ -475,6 +475,7 @@ def test_object_cache_follows_tensor_identity_and_content():
     assert len(packs) == 1
     dA2["descriptors3d_db"].copy_(torch.from_numpy(dB["descriptors3d_db"]).cuda())      # same tensor, new content
     dA2["descriptors2d_db"].copy_(torch.from_numpy(dB["descriptors2d_db"]).cuda())
+    dA2["descriptors2d_query"] = torch.from_numpy(dB["descriptors2d_query"]).cuda()
     m(dA2)
     assert len(packs) == 2
     _check_against(m.last_batched, refB, "object B in A's storage")
