@@ -353,6 +353,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    step_log = []
+
     def timed(fn, steps):
         """`steps` calls of fn(slot), CUDA events around each (L2 flushed in between, outside the event pair); returns summed ms."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -363,7 +365,9 @@ def main():
             out = fn(s % n_slots)
             ev[s][1].record()
         barrier()
-        return sum(a.elapsed_time(b) for a, b in ev), out
+        per_step = [a.elapsed_time(b) for a, b in ev]
+        step_log.append([round(x, 3) for x in per_step])
+        return sum(per_step), out
 
     # ---------------- device-resident throughput ("value") ----------------
     for w in range(args.warmup):
@@ -511,6 +515,7 @@ def main():
                          "whole_step_tflops": whole, "whole_step_frac": whole / pk["tflops"],
                          "hbm_kernels": hbm_kernels},
             "matches_per_batch": n_match, "wall_s_timed_region": wall,
+            "step_ms": {"value": step_log[0], "value_no_conf": step_log[1]},
         }
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:

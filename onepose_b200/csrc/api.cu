@@ -26,6 +26,9 @@ static thread_local std::string g_create_error;
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
+static bool g_l2_prefetch = true;
+bool l2_prefetch_enabled() { return g_l2_prefetch; }
+void set_l2_prefetch_enabled(bool on) { g_l2_prefetch = on; }
 
 struct DevBuf {
   void* p = nullptr;
@@ -110,7 +113,8 @@ struct opb_matcher {
   // workspace (chunk)
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
-  bool hoist = true;      // evaluate the frame-invariant layers once per call (object_prologue)
+  bool hoist = true;      // evaluate the frame-invariant layers once per object (object_prologue)
+  int kv_two_pass = 1;    // k,v projection as A_hi.(B_hi + B_lo): its output is one fp16 plane, the A_lo term is below that rounding
   PlaneBuf x, qp, pn, g, xq, bd, lin_a, lin_b;
   DevBuf kvt;             // fp16 [rows, 512]
   DevBuf hid, kvpart, kmean, statpart, mu, rstd, rowsum_part, colsum_part, rowsum, colsum, rowbest, colbest;
@@ -312,6 +316,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   pk.a1 = x.c(kD); pk.K1 = kD; pk.b1 = W.wqkv.c(kD, (size_t)256 * kD); pk.n_out = 512;
   pk.bias = W.bqkv.as<float>() + 256;
   pk.epi = EPI_QKV; pk.out = Planes{m->kvt.as<__half>(), m->kvt.as<__half>(), 512};
+  pk.a_hi_only = m->kv_two_pass;
   if (int rc = run_gemm(m, pk, st, 2.0 * valid_rows * 512 * kD, "kv_proj")) return rc;
   // (2) linear-attention state of every segment (:71-78): per-row-group partial states on the tensor cores ...
   const KvGroups G = kv_groups_for(L, m->num_sms);
@@ -881,6 +886,18 @@ int opb_gather_features3d(const float* desc, const float* scores, int32_t dim, i
 }
 
 // ---- test hooks ---------------------------------------------------------------------------
+int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes) {
+  if (!m || (passes != 2 && passes != 3)) return OPB_E_INVALID;
+  m->kv_two_pass = passes == 2 ? 1 : 0;
+  m->prologue_ready = false;
+  return OPB_OK;
+}
+
+int opb_debug_set_l2_prefetch(int32_t enable) {
+  set_l2_prefetch_enabled(enable != 0);
+  return OPB_OK;
+}
+
 int opb_debug_set_pdl(int32_t enable) {
   set_pdl_enabled(enable != 0);
   return OPB_OK;

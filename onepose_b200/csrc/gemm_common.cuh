@@ -36,6 +36,9 @@ struct GemmProblem {
   int K1, K2;
   int b2_per_seg;
   int b2_lo_zero;        // the lo plane of b2 is identically zero (identity K-block): its A_hi.B_lo pass is skipped (bit-identical)
+  int a_hi_only;         // use only the hi plane of A (A_lo neither loaded nor multiplied): for a product whose OUTPUT is rounded to one
+                         // fp16 plane anyway (k,v projection: the dropped term is below the output rounding, zero-mean per row, and the
+                         // consumer averages over the segment's rows)
   int rows, n_out;       // per batch; rows % 256 == 0 (a CTA pair works on two adjacent row tiles), n_out % 256 == 0
   int batch;
   long long a_batch_rows, b_batch_rows, c_batch_elems;

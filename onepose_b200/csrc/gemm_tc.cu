@@ -134,6 +134,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -192,6 +195,9 @@ struct TcParams {
   int K1, K2;            // reduction split (multiples of BK)
   int b2_per_seg;
   int b2_lo_zero;        // skip the A_hi . B_lo pass of the K2 block (identity K-block: B_lo == 0)
+  int a_hi_only;         // the A operand enters with its hi plane only: no A_lo load, no A_lo . B_hi pass (k,v projection)
+  int l2_prefetch;       // producer pulls the NEXT unit's A tiles into L2 while this unit's k-blocks stream (hides the HBM latency that
+                         // a 3-stage ring cannot cover: ~4k cycles per stage turn-around measured against 1.5k cycles of MMA per k-block)
   int n_out;
   int m_tiles, n_tiles, batch;
   long long a_batch_rows, b_batch_rows;
@@ -300,13 +306,22 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
         const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // the pair's row tiles share a segment (segments are 256-row aligned)
         const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN + crank * kBRowsLoad;
+        // next unit of this CTA: its A tiles are prefetched into L2 k-block by k-block (skipped when it re-uses this row tile)
+        int pf_row = -1;
+        if (p.l2_prefetch && u + unit_step < total_units) {
+          const int un = u + unit_step;
+          const int zn = un / units_per_batch, remn = un - zn * units_per_batch;
+          const int mn = (remn / p.n_tiles) * 2 + crank;
+          if (zn != z || mn != m_tile) pf_row = (int)(zn * p.a_batch_rows) + mn * BM;
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           const bool first = kb < nkb1;
           const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
-          if (crank == 0) mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);   // leader arms for both CTAs' loads
+          if (crank == 0)                                               // leader arms for both CTAs' loads
+            mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : (p.a_hi_only ? 2 * (kStageBytes - kABytes) : 2 * kStageBytes));
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
           const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
@@ -320,10 +335,19 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
           } else {
             tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
-            tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
+            if (!p.a_hi_only) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
           }
           tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
           tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
+          if (pf_row >= 0) {
+            if (conv) {
+              tma_prefetch_2d(&maps.a_raw, kc, pf_row);
+              tma_prefetch_2d(&maps.a_raw, kc + 32, pf_row);
+            } else {
+              tma_prefetch_2d(mah, kc, pf_row);
+              if (!p.a_hi_only) tma_prefetch_2d(mal, kc, pf_row);
+            }
+          }
         }
       }
     }
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
             tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
             if (!skip_lo) tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
-            tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
+            if (!p.a_hi_only) tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
           }
           tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);              // frees the stage in both CTAs
         }
@@ -728,9 +752,14 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tmem_ld32(lane_base + c0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = fmaf(__uint_as_float(v[j]), kProdInv, __ldg(p.bias + c0 + j));
-              ss = fmaf(x, x, ss);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j4);
+              const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = fmaf(__uint_as_float(v[4 * j4 + e]), kProdInv, bv[e]);
+                ss = fmaf(x, x, ss);
+              }
             }
           }
           inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
@@ -749,14 +778,33 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           tmem_ld_wait();
           const int col0 = n_tile * BN + c0;
           float x[64];
+          // warp-uniform parameter reads as 16-byte loads: 16 instead of 64 load instructions per chunk and thread
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) x[j] = fmaf(__uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]), kProdInv, __ldg(p.bias + col0 + j));
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 bb = __ldg(bias4 + j4);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;
+              x[j] = fmaf(__uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]), kProdInv, bv[e]);
+            }
+          }
           if (EPI == EPI_QSCALE) {
             // one 64-column chunk = one head (head-contiguous channels); the row's head dot product is thread-local
-            const float* km = p.kmean + (long long)src * kD + col0;
+            const float4* km4 = reinterpret_cast<const float4*>(p.kmean + (long long)src * kD + col0);
             float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { x[j] = elu1_fast(x[j]); dot = fmaf(x[j], __ldg(km + j), dot); }
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 kk = __ldg(km4 + j4);
+              const float kv4[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                x[j] = elu1_fast(x[j]);
+                dot = fmaf(x[j], kv4[e], dot);
+              }
+            }
             const float zf = 1.f / (dot + eps_m);
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= zf;
@@ -902,6 +950,7 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
   if (p.rows % (2 * BM) || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.batch <= 0) return -1;
   if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
+  if (p.a_hi_only && (p.a_conv || p.K2)) return -1;
   if (p.a_conv && (p.a_conv != ACV_NORM_RELU || p.batch != 1 || !p.a_raw || p.epi != EPI_BIAS_PLANES || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
   if (p.epi == EPI_QKV && (p.n_out != 2 * BN || p.batch != 1 || !p.out.hi || !p.bias)) return -1;
@@ -942,7 +991,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   }
   if (!ok) return -2;
   TcParams tp{};
-  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.n_out = p.n_out;
+  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.a_hi_only = p.a_hi_only; tp.l2_prefetch = l2_prefetch_enabled() ? 1 : 0; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;

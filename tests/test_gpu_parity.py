@@ -435,6 +435,30 @@ def test_programmatic_dependent_launch_is_transparent():
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
+def test_kv_projection_two_vs_three_passes():
+    """The k,v projection runs as A_hi.(B_hi + B_lo) (its output is one fp16 plane; the dropped A_lo term is below that rounding
+    and averages out over the segment's rows).  Against the full three-pass product: same matches, conf within 2e-6; both
+    meet the oracle -- with the damped fixtures and with undamped weights (O(1) residual updates)."""
+    lib = _lib.load()
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    for damped, shape in ((True, (2, 300, 900)), (False, (2, 200, 500))):
+        sd = synthetic.make_state_dict(3, damped=damped)
+        B, N, M = shape
+        data = synthetic.make_batch(21, list(range(B)), N, M, 8)
+        ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+        outs = []
+        for passes in (2, 3):
+            m = _module(sd, hp)
+            m._ensure_handle(torch.device("cuda", 0))
+            assert lib.opb_debug_set_kv_passes(m._handle, passes) == 0
+            m(_cuda(data))
+            _check_against(m.last_batched, ref, f"kv passes {passes} damped={damped}")
+            outs.append(m.last_batched)
+        assert torch.equal(outs[0]["matches0"], outs[1]["matches0"])
+        scale = float(outs[1]["conf_matrix"].max())
+        assert float((outs[0]["conf_matrix"] - outs[1]["conf_matrix"]).abs().max()) <= 4e-6 * max(scale, 1e-3)
+
+
 def test_host_buffer_call_equals_device_call():
     """opb_forward_host (pinned host in / host out, chunked H2D on a side stream) == opb_forward on device tensors."""
     hp = dict(synthetic.DEFAULT_HPARAMS)
