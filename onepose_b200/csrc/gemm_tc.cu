@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         // ---- planes out (row-major, 64 columns per chunk): EPI_QSCALE / EPI_L2NORM
         float inv_norm = 1.f;
         if (EPI == EPI_L2NORM) {                    // F.normalize: first pass over the accumulator for the row norm
-          float ss = 0.f;
+          float ssp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -758,11 +758,11 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float x = fmaf(__uint_as_float(v[4 * j4 + e]), kProdInv, bv[e]);
-                ss = fmaf(x, x, ss);
+                ssp[e] = fmaf(x, x, ssp[e]);
               }
             }
           }
-          inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          inv_norm = 1.f / fmaxf(sqrtf((ssp[0] + ssp[1]) + (ssp[2] + ssp[3])), 1e-12f);
         }
         int src = 0;
         float eps_m = 0.f;
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           if (EPI == EPI_QSCALE) {
             // one 64-column chunk = one head (head-contiguous channels); the row's head dot product is thread-local
             const float4* km4 = reinterpret_cast<const float4*>(p.kmean + (long long)src * kD + col0);
-            float dot = 0.f;
+            float dotp[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains instead of one 64-long dependent FFMA chain
 #pragma unroll
             for (int j4 = 0; j4 < 16; ++j4) {
               const float4 kk = __ldg(km4 + j4);
@@ -802,9 +802,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               for (int e = 0; e < 4; ++e) {
                 const int j = 4 * j4 + e;
                 x[j] = elu1_fast(x[j]);
-                dot = fmaf(x[j], kv4[e], dot);
+                dotp[e] = fmaf(x[j], kv4[e], dotp[e]);
               }
             }
+            const float dot = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
             const float zf = 1.f / (dot + eps_m);
 #pragma unroll
             for (int j = 0; j < 64; ++j) x[j] *= zf;
@@ -824,11 +825,12 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             for (int j8 = 0; j8 < 4; ++j8) {
               uint4 oh, ol;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                __half h, l;
-                split_f32(x[sc * 32 + j8 * 8 + e], h, l);
-                reinterpret_cast<__half*>(&oh)[e] = h;
-                reinterpret_cast<__half*>(&ol)[e] = l;
+              for (int e = 0; e < 4; ++e) {    // same rounding as split_f32, two elements per conversion instruction
+                const float2 sc2 = make_float2(x[sc * 32 + j8 * 8 + 2 * e] * kPre, x[sc * 32 + j8 * 8 + 2 * e + 1] * kPre);
+                const __half2 h2 = __float22half2_rn(sc2);
+                const float2 back = __half22float2(h2);
+                reinterpret_cast<__half2*>(&oh)[e] = h2;
+                reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc2.x - back.x, sc2.y - back.y));
               }
               *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
               *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;

@@ -237,7 +237,7 @@ __global__ void gats_aggregate(const __half* x_hi, const __half* x_lo, Layout L,
 // reused for every frame of the group (the leaves are per-object constants; reference GATs.py:46 reshapes the same tensor for
 // every batch element).  Fast path for num_leaf == 8 (the released configuration, test_GATsSPG.yaml:5).
 constexpr int kGatsFramesPerWarp = 16;   // leaf rows re-read once per 16 frames (8: 229 MB of leaf traffic per layer at B = 32, 16: 115 MB)
-__global__ void __launch_bounds__(256) gats_aggregate_frames8(const __half* x_hi, const __half* x_lo, Layout L,
+__global__ void __launch_bounds__(256, 2) gats_aggregate_frames8(const __half* x_hi, const __half* x_lo, Layout L,
                                                               const float* __restrict__ leaves, const float* __restrict__ s2,
                                                               const float* __restrict__ wa3, int include_self, int additional, float alpha,
                                                               GatsOut out) {
@@ -260,39 +260,62 @@ __global__ void __launch_bounds__(256) gats_aggregate_frames8(const __half* x_hi
 #pragma unroll
   for (int j = 0; j < 8; ++j) w3[j] = wa3[(j >> 2) * 128 + lane * 4 + (j & 3)];
   auto lrelu = [alpha](float v) { return v > 0.f ? v : alpha * v; };
-#pragma unroll 2
-  for (int b = b_begin; b < b_end; ++b) {
-    const long long row = (long long)b * L.R + L.n_pad + i;
-    float h3[8];
-    gats_read_h3(x_hi, x_lo, row, lane, h3);
-    float s3 = 0.f;
+  // frames in batches of kGatsBatch: all their row loads are issued before the first is consumed (the kernel is bound by bytes
+  // in flight: one frame at a time keeps ~2 KB per warp outstanding, far below what the HBM latency needs)
+  constexpr int kGatsBatch = 4;
+  for (int b0 = b_begin; b0 < b_end; b0 += kGatsBatch) {
+    uint2 rh[kGatsBatch][2], rl[kGatsBatch][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s3 = fmaf(h3[j], w3[j], s3);
-    s3 = warp_sum(s3);
-    float e = lane < 8 ? lrelu(s3 + s2l) : -INFINITY;
-    const float e_self = include_self ? lrelu(2.f * s3) : -INFINITY;
-    float mx = e;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // lanes 0..7 hold the leaf logits
-    mx = fmaxf(__shfl_sync(0xffffffffu, mx, 0), e_self);
-    const float p = lane < 8 ? exp_fast(e - mx) : 0.f;
-    const float p_self = include_self ? exp_fast(e_self - mx) : 0.f;
-    float ps = p;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-    const float inv = 1.f / (__shfl_sync(0xffffffffu, ps, 0) + p_self);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = include_self ? (p_self * inv) * h3[j] : 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float a = __shfl_sync(0xffffffffu, p, c) * inv;
-      acc[0] = fmaf(a, lu[c].x, acc[0]); acc[1] = fmaf(a, lu[c].y, acc[1]);
-      acc[2] = fmaf(a, lu[c].z, acc[2]); acc[3] = fmaf(a, lu[c].w, acc[3]);
-      acc[4] = fmaf(a, lv[c].x, acc[4]); acc[5] = fmaf(a, lv[c].y, acc[5]);
-      acc[6] = fmaf(a, lv[c].z, acc[6]); acc[7] = fmaf(a, lv[c].w, acc[7]);
+    for (int k = 0; k < kGatsBatch; ++k) {
+      const int b = min(b0 + k, b_end - 1);
+      const long long row = (long long)b * L.R + L.n_pad + i;
+      const uint2* ph = reinterpret_cast<const uint2*>(x_hi + row * kD);
+      const uint2* pl = reinterpret_cast<const uint2*>(x_lo + row * kD);
+      rh[k][0] = ph[lane]; rh[k][1] = ph[32 + lane];
+      rl[k][0] = pl[lane]; rl[k][1] = pl[32 + lane];
     }
-    gats_write_row(out, out.lin ? (long long)b * L.m_pad + i : row, lane, acc, h3, include_self, additional);
+#pragma unroll
+    for (int k = 0; k < kGatsBatch; ++k) {
+      const int b = b0 + k;
+      if (b >= b_end) break;
+      const long long row = (long long)b * L.R + L.n_pad + i;
+      float h3[8];
+#pragma unroll
+      for (int half_i = 0; half_i < 2; ++half_i) {
+        const __half* hh = reinterpret_cast<const __half*>(&rh[k][half_i]);
+        const __half* hl = reinterpret_cast<const __half*>(&rl[k][half_i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h3[half_i * 4 + j] = join_f32(hh[j], hl[j]);
+      }
+      float s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s3 = fmaf(h3[j], w3[j], s3);
+      s3 = warp_sum(s3);
+      float e = lane < 8 ? lrelu(s3 + s2l) : -INFINITY;
+      const float e_self = include_self ? lrelu(2.f * s3) : -INFINITY;
+      float mx = e;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // lanes 0..7 hold the leaf logits
+      mx = fmaxf(__shfl_sync(0xffffffffu, mx, 0), e_self);
+      const float p = lane < 8 ? exp_fast(e - mx) : 0.f;
+      const float p_self = include_self ? exp_fast(e_self - mx) : 0.f;
+      float ps = p;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      const float inv = 1.f / (__shfl_sync(0xffffffffu, ps, 0) + p_self);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = include_self ? (p_self * inv) * h3[j] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float a = __shfl_sync(0xffffffffu, p, c) * inv;
+        acc[0] = fmaf(a, lu[c].x, acc[0]); acc[1] = fmaf(a, lu[c].y, acc[1]);
+        acc[2] = fmaf(a, lu[c].z, acc[2]); acc[3] = fmaf(a, lu[c].w, acc[3]);
+        acc[4] = fmaf(a, lv[c].x, acc[4]); acc[5] = fmaf(a, lv[c].y, acc[5]);
+        acc[6] = fmaf(a, lv[c].z, acc[6]); acc[7] = fmaf(a, lv[c].w, acc[7]);
+      }
+      gats_write_row(out, out.lin ? (long long)b * L.m_pad + i : row, lane, acc, h3, include_self, additional);
+    }
   }
 }
 
