@@ -136,8 +136,6 @@ int opb_gather_features3d(const float* desc, const float* scores, int32_t dim, i
 /* ---- test hooks (used by tests/ and tools/ only; stable but not part of the drop-in surface) ---- */
 /* Programmatic dependent launch on (default) / off for every launch of the library (A/B measurements). */
 int opb_debug_set_pdl(int32_t enable);
-/* Producer-side L2 prefetch of the next tile's A operand in the GEMM core on (default) / off (A/B measurements). */
-int opb_debug_set_l2_prefetch(int32_t enable);
 /* Tensor-core passes of the k,v projection: 2 (default: A_hi.(B_hi + B_lo); its output is rounded to one fp16 plane anyway) or
  * 3 (the full split product), for the precision A/B in tests/ and tools/. */
 int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes);

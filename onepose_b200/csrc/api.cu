@@ -26,9 +26,6 @@ static thread_local std::string g_create_error;
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
-static bool g_l2_prefetch = true;
-bool l2_prefetch_enabled() { return g_l2_prefetch; }
-void set_l2_prefetch_enabled(bool on) { g_l2_prefetch = on; }
 
 struct DevBuf {
   void* p = nullptr;
@@ -890,11 +887,6 @@ int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes) {
   if (!m || (passes != 2 && passes != 3)) return OPB_E_INVALID;
   m->kv_two_pass = passes == 2 ? 1 : 0;
   m->prologue_ready = false;
-  return OPB_OK;
-}
-
-int opb_debug_set_l2_prefetch(int32_t enable) {
-  set_l2_prefetch_enabled(enable != 0);
   return OPB_OK;
 }
 

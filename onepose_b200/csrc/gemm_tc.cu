@@ -134,9 +134,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c_inner, int c_outer) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -196,8 +193,6 @@ struct TcParams {
   int b2_per_seg;
   int b2_lo_zero;        // skip the A_hi . B_lo pass of the K2 block (identity K-block: B_lo == 0)
   int a_hi_only;         // the A operand enters with its hi plane only: no A_lo load, no A_lo . B_hi pass (k,v projection)
-  int l2_prefetch;       // producer pulls the NEXT unit's A tiles into L2 while this unit's k-blocks stream (hides the HBM latency that
-                         // a 3-stage ring cannot cover: ~4k cycles per stage turn-around measured against 1.5k cycles of MMA per k-block)
   int n_out;
   int m_tiles, n_tiles, batch;
   long long a_batch_rows, b_batch_rows;
@@ -306,14 +301,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
         const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // the pair's row tiles share a segment (segments are 256-row aligned)
         const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN + crank * kBRowsLoad;
-        // next unit of this CTA: its A tiles are prefetched into L2 k-block by k-block (skipped when it re-uses this row tile)
-        int pf_row = -1;
-        if (p.l2_prefetch && u + unit_step < total_units) {
-          const int un = u + unit_step;
-          const int zn = un / units_per_batch, remn = un - zn * units_per_batch;
-          const int mn = (remn / p.n_tiles) * 2 + crank;
-          if (zn != z || mn != m_tile) pf_row = (int)(zn * p.a_batch_rows) + mn * BM;
-        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
@@ -339,15 +326,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           }
           tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
           tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
-          if (pf_row >= 0) {
-            if (conv) {
-              tma_prefetch_2d(&maps.a_raw, kc, pf_row);
-              tma_prefetch_2d(&maps.a_raw, kc + 32, pf_row);
-            } else {
-              tma_prefetch_2d(mah, kc, pf_row);
-              if (!p.a_hi_only) tma_prefetch_2d(mal, kc, pf_row);
-            }
-          }
         }
       }
     }
@@ -993,7 +971,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   }
   if (!ok) return -2;
   TcParams tp{};
-  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.a_hi_only = p.a_hi_only; tp.l2_prefetch = l2_prefetch_enabled() ? 1 : 0; tp.n_out = p.n_out;
+  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.a_hi_only = p.a_hi_only; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;

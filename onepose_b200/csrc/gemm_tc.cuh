@@ -15,7 +15,4 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
 // Programmatic dependent launch switch shared by every launch site (default on; opb_debug_set_pdl).
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
-// Producer-side L2 prefetch of the next unit's A tiles in the GEMM core (opb_debug_set_l2_prefetch).
-bool l2_prefetch_enabled();
-void set_l2_prefetch_enabled(bool on);
 }  // namespace opb

@@ -37,7 +37,6 @@ def step(i):
 
 SWITCHES = {
     "pdl": lambda v: lib.opb_debug_set_pdl(v),
-    "l2_prefetch": lambda v: lib.opb_debug_set_l2_prefetch(v),
     "kv_2pass": lambda v: lib.opb_debug_set_kv_passes(model._handle, 2 if v else 3),
 }
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 12

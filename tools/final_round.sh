@@ -12,7 +12,7 @@ timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 OPB_PROFILE_DUMP=1 timeout 300 python bench.py --no-cpu-baseline --no-extra --steps 3 --warmup 3 > /dev/null 2> gpurun_out/${tag}_instream_profile.txt; tail -24 gpurun_out/${tag}_instream_profile.txt
 # one step = 75 launches once the object prologue is cached (first step: 85); list the second and third step
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 85 -c 150 --csv --log-file gpurun_out/${tag}_launches_ncu.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_ncu_list.log 2>&1
-# matching kernels per step: 69 (79 in the first); take the last 20 of the third step: GATs layer 9, self layer 10, cross layer 11, tail
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel|kv_state_h|gats_aggregate|kv_state_reduce|in_stats_final" -s 197 -c 20 -o gpurun_out/${tag}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_ncu_full.log 2>&1; tail -2 gpurun_out/${tag}_ncu_full.log
+# matching kernels per step: 69 (79 in the first); take the last ~27 of the third step (and the first of the next): GATs layer 9, self layer 10, cross layer 11, tail
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel|kv_state_h|gats_aggregate|kv_state_reduce|in_stats_final" -s 190 -c 30 -o gpurun_out/${tag}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_ncu_full.log 2>&1; tail -2 gpurun_out/${tag}_ncu_full.log
 timeout 900 python tools/damping_sweep.py --out gpurun_out/${tag}_damping_sweep.json > gpurun_out/${tag}_damping_sweep.log 2>&1; tail -12 gpurun_out/${tag}_damping_sweep.log
 ls -la gpurun_out | tail -12

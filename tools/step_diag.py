@@ -31,7 +31,7 @@ for rep in range(2):
     run("match_frames no conf", lambda i: model.match_frames(q[i], return_conf=False))
     run("opb_forward fixed conf buffer", lambda i: fixed(i))
     run("opb_forward fixed, no flush", lambda i: fixed(i), do_flush=False)
-for name, setter in (("pdl off", lambda v: lib.opb_debug_set_pdl(v)), ("l2 prefetch off", lambda v: lib.opb_debug_set_l2_prefetch(v))):
+for name, setter in (("pdl off", lambda v: lib.opb_debug_set_pdl(v)),):
     setter(0); run(name, lambda i: fixed(i)); setter(1); run(name.replace("off", "on"), lambda i: fixed(i))
 lib.opb_debug_set_kv_passes(model._handle, 3); run("kv 3 passes", lambda i: fixed(i)); lib.opb_debug_set_kv_passes(model._handle, 2); run("kv 2 passes", lambda i: fixed(i))
 import os
