@@ -133,6 +133,22 @@ int opb_segmented_mean_scores_f64(const double* scores, const int64_t* seg_len, 
 int opb_gather_features3d(const float* desc, const float* scores, int32_t dim, int64_t n_src, const int64_t* idx, int64_t n_idx,
                           float* desc_out, float* scores_out, int64_t n_out, void* stream);
 
+/* ---- adjacent consumer: object pose from the matched correspondences ----
+ * Replaces the per-frame cv2.solvePnPRansac(..., reprojectionError=5, iterationsCount=10000, flags=SOLVEPNP_EPNP) of
+ * ransac_PnP (reference src/utils/eval_utils.py:18-42) for B frames in one call, on the device:
+ *   K          device f64 [B, 9]   row-major camera matrices
+ *   pts2d      device f64 [total, 2], pts3d device f64 [total, 3]  matched key points of all frames, concatenated
+ *   offsets    device int32 [B+1]  frame b owns correspondences [offsets[b], offsets[b+1])
+ *   hypotheses minimal samples per frame (P3P), reproj_error in pixels, seed of the sample generator (results are a
+ *              deterministic function of it)
+ *   workspace  device f64 [B * hypotheses * 13]
+ * Outputs (device): pose f64 [B, 12] = row-major [R | t] (world -> camera), inlier_mask int32 [total], n_inliers int32 [B].
+ * A frame with fewer than 4 correspondences or no model gets the identity pose and no inliers (the reference's cv2.error
+ * branch).  Parity with the reference is on the pose (cm / degree), not on bits: OpenCV draws its own samples. */
+int opb_ransac_pnp(const double* K, const double* pts2d, const double* pts3d, const int32_t* offsets, int32_t B, int32_t hypotheses,
+                   double reproj_error, uint64_t seed, double* workspace, double* pose_out, int32_t* inlier_mask, int32_t* n_inliers,
+                   void* stream);
+
 /* ---- test hooks (used by tests/ and tools/ only; stable but not part of the drop-in surface) ---- */
 /* Programmatic dependent launch on (default) / off for every launch of the library (A/B measurements). */
 int opb_debug_set_pdl(int32_t enable);

@@ -2,6 +2,6 @@
 ``GATsSuperGlue`` forward.  The CUDA library is loaded lazily by the matcher; importing this
 package on a machine without the built library works, constructing a matcher does not."""
 from .matcher import GATsSuperGlue, LitModelGATsSPG  # noqa: F401
-from . import features3d, synthetic  # noqa: F401
+from . import features3d, pnp, synthetic  # noqa: F401
 
-__all__ = ["GATsSuperGlue", "LitModelGATsSPG", "features3d", "synthetic"]
+__all__ = ["GATsSuperGlue", "LitModelGATsSPG", "features3d", "pnp", "synthetic"]

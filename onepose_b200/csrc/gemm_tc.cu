@@ -34,14 +34,14 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;
+constexpr int kStagesFull = 3;
 constexpr int kABytes = BM * BK * 2;             // one plane of this CTA's A tile (16 KB)
 constexpr int kBBytes = (BN / 2) * BK * 2;       // one plane of this CTA's HALF of the B tile (16 KB)
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+constexpr int kStageBytesFull = 2 * kABytes + 2 * kBBytes;
 constexpr int kStagingBytes = 16384;             // one 128-row x 128-B swizzled epilogue buffer
 constexpr int kNumStaging = 2;
 constexpr int kExtraBytes = 1024;                // per-tile scratch of the score epilogue (inverse column sums of the tile)
-constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + kExtraBytes;
+constexpr int kSmemBytes = kStagesFull * kStageBytesFull + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + kExtraBytes;
 constexpr uint32_t kSBO = 8 * BK * 2;            // bytes between 8-row groups of a K-major SWIZZLE_128B operand
 constexpr int kTmemCols = 512;
 // warps 0-3: TMA / MMA / TMEM / spare.  Plain variants: warps 4-11 = two epilogue groups of 4 warps (384 threads).
@@ -192,7 +192,6 @@ struct TcParams {
   int K1, K2;            // reduction split (multiples of BK)
   int b2_per_seg;
   int b2_lo_zero;        // skip the A_hi . B_lo pass of the K2 block (identity K-block: B_lo == 0)
-  int a_hi_only;         // the A operand enters with its hi plane only: no A_lo load, no A_lo . B_hi pass (k,v projection)
   int n_out;
   int m_tiles, n_tiles, batch;
   long long a_batch_rows, b_batch_rows;
@@ -234,8 +233,15 @@ struct Maps {
 //   ACV_NORM_RELU  A  = ReLU((hid - mu_seg) * rstd_seg)          mlp.3 reads mlp.0's fp32 output (GATs_SuperGlue.py:126-127)
 enum { ACV_NONE = 0, ACV_NORM_RELU = 1 };
 
-template <int EPI, int ACV = ACV_NONE>
+// HI: the A operand enters with its hi plane only (k,v projection, GemmProblem::a_hi_only): the stage shrinks to A_hi + B_hi + B_lo =
+// 48 KB and the ring deepens to FOUR stages in the same 192 KB -- with two passes a k-block is only ~1k cycles of MMA, and three
+// stages cannot cover the ~4k-cycle turn-around of a stage (load issue -> data landed) any more.
+template <int EPI, int ACV = ACV_NONE, bool HI = false>
 __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
+  constexpr int kStages = HI ? 4 : kStagesFull;
+  constexpr int kStageBytes = HI ? kABytes + 2 * kBBytes : kStageBytesFull;
+  constexpr int kBOff = HI ? kABytes : 2 * kABytes;      // offset of the B planes inside a stage
+  static_assert(!HI || ACV == ACV_NONE, "converters need the full stage");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + kStages * kStageBytes;
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           const bool first = kb < nkb1;
           const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
           if (crank == 0)                                               // leader arms for both CTAs' loads
-            mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : (p.a_hi_only ? 2 * (kStageBytes - kABytes) : 2 * kStageBytes));
+            mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
           const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
@@ -322,10 +328,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
           } else {
             tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
-            if (!p.a_hi_only) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
+            if (!HI) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
           }
-          tma_load_2d_2sm(st + 2 * kABytes, mbh, &full_bar[s], kc, brow);
-          tma_load_2d_2sm(st + 2 * kABytes + kBBytes, mbl, &full_bar[s], kc, brow);
+          tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kc, brow);
+          tma_load_2d_2sm(st + kBOff + kBBytes, mbl, &full_bar[s], kc, brow);
         }
       }
     }
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           if (tl && tc == 1 && kb < 16) tl[20 + kb] = clock64();
           tc_fence_after();
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
-          const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + 2 * kABytes, sb_l = sb_h + kBBytes;
+          const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + kBOff, sb_l = sb_h + kBBytes;
           const bool skip_lo = p.b2_lo_zero && kb >= nkb1;          // B_lo == 0: the A_hi.B_lo pass adds exact zeros
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
             tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
             if (!skip_lo) tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
-            if (!p.a_hi_only) tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
+            if (!HI) tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
           }
           tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);              // frees the stage in both CTAs
         }
@@ -618,7 +624,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         epi_bar();                                                  // every thread of the group is done with the previous tile's values
         ics[t] = __ldg(p.inv_colsum + (long long)z * p.L.m_pad + n_tile * BN + c_begin + t);
         epi_bar();
-        unsigned long long rbest = 0ull;
+        // running row arg-max as (value, column): columns are visited in ascending order and only a STRICTLY larger value
+        // replaces the best, so the first maximum wins like torch.max; packed once per tile for the 64-bit atomicMax
+        float rbest_v = 0.f;
+        int rbest_c = -1;
         const bool store_plain = p.conf != nullptr && !p.conf_tma;
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
@@ -639,10 +648,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
               const float e = ok ? ex2_fast(fmaf(__uint_as_float(v[j]), ea, eb)) : 0.f;
               const float c = (e * irs) * (e * icv[jj]);
               o[j] = c;
-              if (ok) {
-                const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(col0 + j));
-                rbest = pk > rbest ? pk : rbest;
-              }
+              if (c > rbest_v) { rbest_v = c; rbest_c = col0 + j; }
             }
           }
           if (p.conf_tma && leader) tma_store_wait_read<0>();       // the store that last read this group's buffer is done with it
@@ -656,25 +662,33 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tma_store_3d(&maps.out_f32, sb, col0, row0, z);         // rows >= N and columns >= M are clipped by the tensor map
             tma_store_commit();
           }
-          // column scan over the staged 128 x 32 chunk: thread (qq, cc) = rows [32 qq, +32) of column col0 + cc
+          // column scan over the staged 128 x 32 chunk: thread (qq, cc) = rows [32 qq, +32) of column col0 + cc.  Fully unrolled
+          // (invalid rows hold 0 and can never win): 32 independent shared-memory loads in flight instead of a latency chain.
           const int col = col0 + cc;
           if (col < M) {
-            unsigned long long cbest = 0ull;
             const int r_first = row0 + qq * 32;
-            const int r_end = min(32, Nz - r_first);
-            float* crow = store_plain ? p.conf + ((long long)z * p.L.N + r_first) * M + col : nullptr;
-            for (int i = 0; i < r_end; ++i) {
-              const float c = *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
-              if (store_plain) crow[(long long)i * M] = c;          // 32 consecutive columns of one row per warp instruction
-              const unsigned long long pk = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(r_first + i));
-              cbest = pk > cbest ? pk : cbest;
+            float cbest_v = 0.f;
+            int cbest_r = -1;
+            float cv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cv[i] = *reinterpret_cast<const float*>(sb + stg_off(qq * 32 + i, cc >> 2) + (cc & 3) * 4);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cv[i] > cbest_v) { cbest_v = cv[i]; cbest_r = r_first + i; }
+            if (store_plain) {                                      // 32 consecutive columns of one row per warp instruction; rows
+              float* crow = p.conf + ((long long)z * p.L.N + r_first) * M + col;       // [Nz, N) of a ragged frame are written as 0
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (r_first + i < p.L.N) crow[(long long)i * M] = cv[i];
             }
-            if (store_plain)                                        // ragged batch: rows [Nz, N) of the frame are defined as zero
-              for (int i = max(r_end, 0); i < 32 && r_first + i < p.L.N; ++i) crow[(long long)i * M] = 0.f;
-            if (cbest) atomicMax(p.colbest + (long long)z * M + col, cbest);
+            if (cbest_r >= 0)
+              atomicMax(p.colbest + (long long)z * M + col,
+                        ((unsigned long long)__float_as_uint(cbest_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cbest_r));
           }
         }
-        if (row_ok && rbest) atomicMax(p.rowbest + (long long)z * p.L.N + row, rbest);
+        if (rbest_c >= 0)
+          atomicMax(p.rowbest + (long long)z * p.L.N + row,
+                    ((unsigned long long)__float_as_uint(rbest_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)rbest_c));
       } else if (EPI == EPI_BIAS_PLANES) {
         // ---- out planes = acc + bias, 32 columns per chunk (a residual, if any, already sits in the accumulator: identity
         // K-block); rows past the segment's valid count are written as zero so that padding never accumulates state
@@ -909,10 +923,10 @@ int num_sms() {
   return n;
 }
 
-template <int EPI, int ACV = ACV_NONE>
+template <int EPI, int ACV = ACV_NONE, bool HI = false>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const Maps& mp, const TcParams& tp) {
   static bool attr_done = false;
-  auto* kern = gemm_tc_kernel<EPI, ACV>;
+  auto* kern = gemm_tc_kernel<EPI, ACV, HI>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -930,7 +944,7 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
   if (p.rows % (2 * BM) || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.batch <= 0) return -1;
   if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
-  if (p.a_hi_only && (p.a_conv || p.K2)) return -1;
+  if (p.a_hi_only && (p.a_conv || p.K2 || p.epi != EPI_QKV)) return -1;
   if (p.a_conv && (p.a_conv != ACV_NORM_RELU || p.batch != 1 || !p.a_raw || p.epi != EPI_BIAS_PLANES || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
   if (p.epi == EPI_QKV && (p.n_out != 2 * BN || p.batch != 1 || !p.out.hi || !p.bias)) return -1;
@@ -971,7 +985,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   }
   if (!ok) return -2;
   TcParams tp{};
-  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.a_hi_only = p.a_hi_only; tp.n_out = p.n_out;
+  tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.n_out = p.n_out;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;
@@ -1005,7 +1019,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
       case EPI_L2NORM: le = launch_variant<EPI_L2NORM>(cfg, mp, tp); break;
       case EPI_SCORE_SUMS: le = launch_variant<EPI_SCORE_SUMS>(cfg, mp, tp); break;
       case EPI_SCORE_CONF: le = launch_variant<EPI_SCORE_CONF>(cfg, mp, tp); break;
-      case EPI_QKV: le = launch_variant<EPI_QKV>(cfg, mp, tp); break;
+      case EPI_QKV: le = p.a_hi_only ? launch_variant<EPI_QKV, ACV_NONE, true>(cfg, mp, tp) : launch_variant<EPI_QKV>(cfg, mp, tp); break;
       case EPI_BIAS_PLANES: le = launch_variant<EPI_BIAS_PLANES>(cfg, mp, tp); break;
       default: return -1;
     }

@@ -505,8 +505,8 @@ __global__ void mutual_match(const unsigned long long* __restrict__ rowbest, con
     long long mm = -1ll;
     float ms = 0.f;
     if (!poisoned && n < Nb) {
-      const int i0 = idx_of(rb[n]);
-      const bool mutual = idx_of(cb[i0]) == n;
+      const int i0 = idx_of(rb[n]);                       // -1: the row never saw a positive confidence (cannot happen for finite inputs)
+      const bool mutual = i0 >= 0 && idx_of(cb[i0]) == n;
       ms = mutual ? val_of(rb[n]) : 0.f;
       if (mutual && ms > thr) mm = i0;
     }
@@ -518,10 +518,10 @@ __global__ void mutual_match(const unsigned long long* __restrict__ rowbest, con
     float ms1 = 0.f;
     if (!poisoned) {
       const int i1 = idx_of(cb[m]);
-      const int i0 = idx_of(rb[i1]);
+      const int i0 = i1 >= 0 ? idx_of(rb[i1]) : -1;
       const bool mutual1 = i0 == m;
       // mscores0[i1], valid0[i1] recomputed (cheap) instead of read-after-write across threads
-      const bool mutual0_i1 = idx_of(cb[i0]) == i1;
+      const bool mutual0_i1 = i0 >= 0 && idx_of(cb[i0]) == i1;
       const float ms0_i1 = mutual0_i1 ? val_of(rb[i1]) : 0.f;
       const bool valid0_i1 = mutual0_i1 && ms0_i1 > thr;
       ms1 = mutual1 ? ms0_i1 : 0.f;

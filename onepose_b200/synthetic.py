@@ -170,3 +170,24 @@ def make_sfm_features(seed: int, n_points: int, d: int = D, max_len: int = 14):
     avg = np.stack([obs[:, s:e].mean(axis=1) for s, e in zip(starts, ends)], 1).astype(np.float32)
     avg_scores = np.stack([obs_scores[s:e].mean(axis=0) for s, e in zip(starts, ends)], 0).astype(np.float32)
     return obs, obs_scores, idxs, avg, avg_scores
+
+
+def make_pnp_scene(seed: int, n: int, outlier_frac: float = 0.4, noise_px: float = 0.5, size: int = 512):
+    """Matched 2D-3D correspondences of one frame for the pose solver (reference eval_utils.py:18-42): an object of ~10 cm
+    about 50-80 cm in front of a 512 x 512 crop camera, pixel noise on the inliers, uniformly random 2D positions for the
+    outliers.  Returns (K [3,3], pts2d [n,2], pts3d [n,3], pose_gt [3,4]) as float64 (3D points in metres)."""
+    rs = np.random.RandomState(seed)
+    K = np.array([[600.0 + 50 * rs.rand(), 0, size / 2 + 5 * rs.randn()], [0, 600.0 + 50 * rs.rand(), size / 2 + 5 * rs.randn()], [0, 0, 1.0]])
+    w = rs.randn(3)
+    th = np.linalg.norm(w)
+    k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    t = np.array([0.03 * rs.randn(), 0.03 * rs.randn(), 0.5 + 0.3 * rs.rand()])
+    P = 0.05 * rs.randn(n, 3)
+    X = P @ R.T + t
+    uv = X[:, :2] / X[:, 2:3] * np.array([K[0, 0], K[1, 1]]) + np.array([K[0, 2], K[1, 2]])
+    uv += noise_px * rs.randn(n, 2)
+    out = rs.rand(n) < outlier_frac
+    uv[out] = rs.rand(int(out.sum()), 2) * size
+    return K, uv, P, np.concatenate([R, t[:, None]], 1)

@@ -177,6 +177,26 @@ def features3d_cases():
           "tied padded columns identical:", bool((conf[0][:, n_real:] == conf[0][:, n_real:n_real + 1]).all()))
 
 
+PNP_SCENES = [  # seed, n correspondences, outlier fraction
+    (1, 300, 0.3), (2, 500, 0.5), (3, 120, 0.6), (4, 60, 0.2), (5, 800, 0.4), (6, 30, 0.5), (7, 6, 0.0), (8, 3, 0.0)]
+
+
+def pnp_cases():
+    """ransac_PnP of the imported, unmodified reference (src/utils/eval_utils.py:18-42; cv2 of THIS image) on seeded scenes."""
+    from src.utils import eval_utils
+    import cv2
+    out = {"cv2_version": cv2.__version__, "scenes": np.array(PNP_SCENES)}
+    for seed, n, frac in PNP_SCENES:
+        K, uv, P, gt = synthetic.make_pnp_scene(seed, n, frac)
+        pose, pose_homo, inliers = eval_utils.ransac_PnP(K, uv, P.copy(), scale=1000)
+        out[f"pose_{seed}"] = pose
+        out[f"n_inliers_{seed}"] = len(inliers)
+        out[f"gt_{seed}"] = gt
+        r = np.rad2deg(np.arccos(np.clip((np.trace(pose[:, :3] @ gt[:, :3].T) - 1) / 2, -1, 1)))
+        print(f"pnp scene {seed}: n={n} outliers={frac}: reference inliers {len(inliers)}, err vs gt {r:.3f} deg {np.linalg.norm(pose[:, 3] - gt[:, 3]) * 100:.3f} cm")
+    np.savez_compressed(os.path.join(HERE, "pnp_scenes.npz"), **out)
+
+
 def state_dict_spec():
     """Key names / shapes of the reference module's state dict (load_state_dict compatibility)."""
     import json
@@ -195,3 +215,4 @@ if __name__ == "__main__":
     empty_case()
     mean_cases()
     features3d_cases()
+    pnp_cases()

@@ -9,7 +9,7 @@ from onepose_b200 import synthetic
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FORWARD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                       if not os.path.basename(p).startswith(("empty", "mean_", "features3d", "dustbin")))
+                       if not os.path.basename(p).startswith(("empty", "mean_", "features3d", "dustbin", "pnp_")))
 RELEASED_CASES = [c for c in FORWARD_CASES if not c.startswith(("noself", "lintrans", "additional"))]
 
 

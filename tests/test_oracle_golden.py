@@ -85,3 +85,18 @@ def test_oracle_dustbin_object_matches_reference():
     np.testing.assert_array_equal(out["matches1"][0].numpy(), g["matches1"])
     n_real = int(g["n_real"])
     assert (g["conf_matrix"][0][:, n_real:] == g["conf_matrix"][0][:, n_real:n_real + 1]).all()     # the tie is exact in the reference
+
+
+def test_oracle_pnp_matches_reference_function():
+    """ransac_PnP restated (oracle/pnp_oracle.py) vs the imported reference function's outputs (same cv2, fixed-seed RNG)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import pnp_oracle
+    g = np.load(f"{GOLDEN_DIR}/pnp_scenes.npz")
+    if str(g["cv2_version"]) != cv2.__version__:
+        pytest.skip("golden made with another OpenCV build")
+    for seed, n, frac in g["scenes"]:
+        K, uv, P, gt = synthetic.make_pnp_scene(int(seed), int(n), float(frac))
+        pose, homo, inliers = pnp_oracle.ransac_PnP(K, uv, P, scale=1000)
+        np.testing.assert_allclose(pose, g[f"pose_{int(seed)}"], atol=1e-12)
+        assert len(inliers) == int(g[f"n_inliers_{int(seed)}"])
+        assert homo.shape == (4, 4)
