@@ -272,18 +272,26 @@ def leg_config5(model, dev, rank, world, dist, seed=5):
         dist.barrier()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    obj_ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(data) + 1)]
     n_match = torch.zeros((), dtype=torch.int64, device=dev)
     t0 = time.perf_counter()
     e0.record()
-    for (db, leaves, q) in data:
+    obj_ev[0].record()
+    for oi, (db, leaves, q) in enumerate(data):
         model.set_object(db, leaves)
         for f0 in range(0, q.shape[0], 32):
             out = model.match_frames(q[f0:f0 + 32])
             n_match += (out["matches0"] > -1).sum()
+        obj_ev[oi + 1].record()
     e1.record()
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - t0
     busy_ms = e0.elapsed_time(e1)
+    per_obj = torch.zeros(len(jobs), dtype=torch.float64, device=dev)       # measured device ms of every object (0 = not mine)
+    for oi, j in enumerate(mine):
+        per_obj[j["id"]] = obj_ev[oi].elapsed_time(obj_ev[oi + 1])
+    if world > 1:
+        dist.all_reduce(per_obj)
     rec = torch.tensor([float(sum(j["frames"] for j in mine)), busy_ms, float(len(mine)), float(sum(j["cost"] for j in mine)), float(n_match.item()),
                         1e3 * wall], dtype=torch.float64, device=dev)
     allrec = sharding.gather_records(rec)
@@ -294,6 +302,7 @@ def leg_config5(model, dev, rank, world, dist, seed=5):
             "per_rank_busy_ms": [round(float(x), 2) for x in busy], "per_rank_objects": [int(x) for x in allrec[:, 2]],
             "imbalance_max_over_mean": float(busy.max() / busy.mean()), "lpt_cost_imbalance": float(allrec[:, 3].max() / allrec[:, 3].mean()),
             "matches": float(allrec[:, 4].sum()), "host_wall_ms_max": float(allrec[:, 5].max()),
+            "per_object": [[j["M"], j["N"], j["frames"], round(float(per_obj[j["id"]]), 2)] for j in jobs],
             "note": "set_object, ragged shapes and workspace growth inside the timed region; conf matrix materialised; "
                     "device time per rank by CUDA events, job time = max over ranks"}
 

@@ -152,6 +152,9 @@ int opb_ransac_pnp(const double* K, const double* pts2d, const double* pts3d, co
 /* ---- test hooks (used by tests/ and tools/ only; stable but not part of the drop-in surface) ---- */
 /* Programmatic dependent launch on (default) / off for every launch of the library (A/B measurements). */
 int opb_debug_set_pdl(int32_t enable);
+/* byte >= 0: every workspace / object buffer allocated from now on is filled with `byte` (0xFF = NaN patterns) unless the
+ * algorithm requires it to start as zero; -1: off.  Proves that no result depends on uninitialised memory. */
+int opb_debug_set_ws_fill(int32_t byte);
 /* Tensor-core passes of the k,v projection: 2 (default: A_hi.(B_hi + B_lo); its output is rounded to one fp16 plane anyway) or
  * 3 (the full split product), for the precision A/B in tests/ and tools/. */
 int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes);

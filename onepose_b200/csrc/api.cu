@@ -24,6 +24,7 @@ constexpr int kQPassFrames = 16;    // granularity of the query-side layer-1 pas
 
 static thread_local std::string g_create_error;
 static bool g_pdl = true;
+static int g_ws_fill = -1;     // >= 0: byte value written into every fresh allocation that the algorithm does not require to be zero
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
 
@@ -40,7 +41,8 @@ struct DevBuf {
     if (e != cudaSuccess) return e;
     bytes = need;
     grew = true;
-    if (zero) e = cudaMemset(p, 0, need);
+    if (zero) e = cudaMemset(p, 0, need);                       // buffers whose untouched parts are read as zero (bd, flags)
+    else if (g_ws_fill >= 0) e = cudaMemset(p, g_ws_fill, need);   // test hook: poison everything else (opb_debug_set_ws_fill)
     return e;
   }
   void release() {
@@ -237,13 +239,13 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   const size_t R = (size_t)n_pad + m->m_pad;
   const size_t rows = R * frames;
   const size_t S = 2 * (size_t)frames;
-  CK(m, m->x.ensure(rows * kD, true));
-  CK(m, m->qp.ensure(rows * kD, true));
-  CK(m, m->pn.ensure(rows * kD, true));
+  CK(m, m->x.ensure(rows * kD));
+  CK(m, m->qp.ensure(rows * kD));
+  CK(m, m->pn.ensure(rows * kD));
   CK(m, m->g.ensure(S * 512 * kD));
   CK(m, m->bd.ensure(S * kD * kD, true));          // block-diagonal state operand: off-diagonal blocks stay zero for the buffer's lifetime
-  CK(m, m->xq.ensure((size_t)frames * n_pad * kD, true));
-  CK(m, m->kvt.ensure(rows * 512 * sizeof(__half), true));
+  CK(m, m->xq.ensure((size_t)frames * n_pad * kD));
+  CK(m, m->kvt.ensure(rows * 512 * sizeof(__half)));
   CK(m, m->hid.ensure(rows * 512 * sizeof(float)));
   CK(m, m->kvpart.ensure(rows / 256 * kHeads * kKVPartial * sizeof(float)));
   CK(m, m->kmean.ensure(S * kD * sizeof(float)));
@@ -258,8 +260,8 @@ static int ensure_workspace(opb_matcher* m, int frames, int N) {
   CK(m, m->colbest.ensure((size_t)frames * m->m_pad * sizeof(unsigned long long)));
   CK(m, m->range_flag.ensure(sizeof(int), true));
   if (m->cfg.with_linear_transform) {
-    CK(m, m->lin_a.ensure((size_t)frames * m->m_pad * kD, true));
-    CK(m, m->lin_b.ensure((size_t)frames * m->m_pad * kD, true));
+    CK(m, m->lin_a.ensure((size_t)frames * m->m_pad * kD));
+    CK(m, m->lin_b.ensure((size_t)frames * m->m_pad * kD));
   }
   // (re)allocation fills ran on the legacy stream: order them against the caller's (possibly non-blocking) stream once
   CK(m, cudaDeviceSynchronize());
@@ -887,6 +889,11 @@ int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes) {
   if (!m || (passes != 2 && passes != 3)) return OPB_E_INVALID;
   m->kv_two_pass = passes == 2 ? 1 : 0;
   m->prologue_ready = false;
+  return OPB_OK;
+}
+
+int opb_debug_set_ws_fill(int32_t byte) {
+  g_ws_fill = byte < 0 ? -1 : (byte & 0xFF);
   return OPB_OK;
 }
 

@@ -461,6 +461,25 @@ def test_object_prologue_hoisting_matches_per_frame_evaluation():
     assert torch.equal(outs[0]["matches0"], outs[1]["matches0"])
 
 
+def test_results_do_not_depend_on_uninitialised_workspace():
+    """Every workspace / object buffer poisoned with 0xFF bytes (NaN patterns) at allocation: same results as the oracle, for
+    ragged sizes, growing workspaces and both GATs code paths (only the block-diagonal state operand is required to start zero)."""
+    lib = _lib.load()
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    sd = synthetic.make_state_dict(1)
+    try:
+        assert lib.opb_debug_set_ws_fill(0xFF) == 0
+        m = _module(sd, hp)
+        for obj, (B, N, M, L) in enumerate([(2, 100, 300, 8), (3, 333, 700, 8), (1, 50, 129, 5), (2, 260, 513, 8)]):
+            data = synthetic.make_batch(30 + obj, list(range(B)), N, M, L)
+            ref = oracle.forward(oracle.params_from_numpy(sd), data, hp)
+            m(_cuda(data))
+            _check_against(m.last_batched, ref, f"poisoned workspace, object {obj}")
+        m.check_range()
+    finally:
+        lib.opb_debug_set_ws_fill(-1)
+
+
 def test_programmatic_dependent_launch_is_transparent():
     """PDL on (default) and off give bit-identical results (it only overlaps kernel prologues with the previous kernel's tail)."""
     lib = _lib.load()
