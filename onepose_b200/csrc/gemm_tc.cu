@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
   static_assert(!kSplit || kBRingOff + kBStages * kBStageBytes == kStagesFull * kStageBytesFull, "split rings fill the same 192 KB");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + kStages * kStageBytes;
+  uint8_t* staging = smem + kStagesFull * kStageBytesFull;   // every ring layout fills the same 192 KB
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumStaging * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
