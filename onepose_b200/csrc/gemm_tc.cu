@@ -238,30 +238,19 @@ enum { ACV_NONE = 0, ACV_NORM_RELU = 1 };
 // stages cannot cover the ~4k-cycle turn-around of a stage (load issue -> data landed) any more.
 template <int EPI, int ACV = ACV_NONE, bool HI = false>
 __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
-  // Converter variant: SPLIT rings.  The raw fp32 A tile has the longest turn-around of all operands (HBM load -> conversion ->
-  // MMA), and three 64 KB stages cannot cover it (the kernel ran at ~2.3k cycles per k-block against 1.5k of MMA).  The same
-  // 192 KB hold FOUR 32 KB A stages plus TWO 32 KB B stages: the weights come out of L2 and need less run-ahead.  The B ring
-  // has its own producer (warp 3) and barriers.
-  constexpr bool kSplit = ACV != ACV_NONE;
-  constexpr int kStages = (HI || kSplit) ? 4 : kStagesFull;                                    // stages of the A (or unified) ring
-  constexpr int kStageBytes = kSplit ? 2 * kABytes : (HI ? kABytes + 2 * kBBytes : kStageBytesFull);
-  constexpr int kBOff = HI ? kABytes : 2 * kABytes;      // unified ring: offset of the B planes inside a stage
-  constexpr int kBStages = kSplit ? 2 : kStages;
-  constexpr int kBRingOff = kStages * kStageBytes;       // split rings: the B ring follows the A ring
-  constexpr int kBStageBytes = 2 * kBBytes;
+  constexpr int kStages = HI ? 4 : kStagesFull;
+  constexpr int kStageBytes = HI ? kABytes + 2 * kBBytes : kStageBytesFull;
+  constexpr int kBOff = HI ? kABytes : 2 * kABytes;      // offset of the B planes inside a stage
   static_assert(!HI || ACV == ACV_NONE, "converters need the full stage");
-  static_assert(!kSplit || kBRingOff + kBStages * kBStageBytes == kStagesFull * kStageBytesFull, "split rings fill the same 192 KB");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + kStagesFull * kStageBytesFull;   // every ring layout fills the same 192 KB
+  uint8_t* staging = smem + kStages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumStaging * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint64_t* raw_bar = tmem_empty_bar + 2;            // [kStages] raw fp32 A tile has landed (ACV)
-  uint64_t* fullb_bar = raw_bar + kStages;           // [kBStages] split rings only
-  uint64_t* emptyb_bar = fullb_bar + 2;              // [kBStages]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(emptyb_bar + 2);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(raw_bar + kStages);
   float* extra = reinterpret_cast<float*>(staging + kNumStaging * kStagingBytes + 256);   // kExtraBytes of per-tile scratch
 
   // Epilogue groups: the TMEM -> registers -> staging -> TMA-store chain of one 32-column chunk is a serial latency chain
@@ -284,8 +273,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     // full: the TMA transaction arrive (+ with converters: one arrive per converter warp of BOTH CTAs, on the leader)
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], ACV ? 1 + 2 * kConvWarps : 1); mbar_init(&empty_bar[s], 1); mbar_init(&raw_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * kEpiGroups); }
-    if (kSplit)
-      for (int b = 0; b < kBStages; ++b) { mbar_init(&fullb_bar[b], 1); mbar_init(&emptyb_bar[b], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -326,7 +313,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           uint8_t* st = smem + s * kStageBytes;
           const bool first = kb < nkb1;
           const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
-          if (!kSplit && crank == 0)                                    // leader arms for both CTAs' loads
+          if (crank == 0)                                               // leader arms for both CTAs' loads
             mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);
           const int kc = (first ? kb * BK : (kb - nkb1) * BK);
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
@@ -334,21 +321,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
-          if (kSplit) {
-            // A ring only (the B tiles travel through their own ring, warp 3).  full barrier = 16 converter-warp arrivals + ONE
-            // arrival from the leader's producer: a plain arrive for a raw k-block, the arrive.expect_tx of the plane loads otherwise
-            if (conv) {
-              mbar_expect_tx(&raw_bar[s], 2 * kABytes);
-              tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
-              tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
-              if (crank == 0) mbar_arrive(&full_bar[s]);
-            } else {
-              if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * 2 * kABytes);
-              tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
-              tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
-            }
-            continue;
-          }
           if (conv) {
             // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
             mbar_expect_tx(&raw_bar[s], 2 * kABytes);
@@ -360,28 +332,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           }
           tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kc, brow);
           tma_load_2d_2sm(st + kBOff + kBBytes, mbl, &full_bar[s], kc, brow);
-        }
-      }
-    }
-  } else if (kSplit && warp == 3) {
-    // ===================== B producer of the split rings: this CTA's half of the weight tile, two stages =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      constexpr int kBRowsLoad = BN / 2;
-      for (int u = unit0; u < total_units; u += unit_step) {
-        const int z = u / units_per_batch, rem = u - z * units_per_batch;
-        const int n_tile = rem % p.n_tiles;
-        const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
-        const int b_row2 = n_tile * BN + crank * kBRowsLoad;       // converter GEMMs have no per-segment B2
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kBStages;
-          mbar_wait(&emptyb_bar[s], ((it / kBStages) & 1) ^ 1);
-          uint8_t* st = smem + kBRingOff + s * kBStageBytes;
-          const bool first = kb < nkb1;
-          const int kc = (first ? kb * BK : (kb - nkb1) * BK);
-          if (crank == 0) mbar_expect_tx(&fullb_bar[s], 2 * kBStageBytes);     // both CTAs' halves
-          tma_load_2d_2sm(st, first ? &maps.b1h : &maps.b2h, &fullb_bar[s], kc, first ? b_row1 : b_row2);
-          tma_load_2d_2sm(st + kBBytes, first ? &maps.b1l : &maps.b2l, &fullb_bar[s], kc, first ? b_row1 : b_row2);
         }
       }
     }
@@ -399,14 +349,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           mbar_wait(&full_bar[s], (it / kStages) & 1);
           if (tl && tc == 1 && kb < 16) tl[20 + kb] = clock64();
           tc_fence_after();
-          const int sB = it % kBStages;
-          if (kSplit) {
-            mbar_wait(&fullb_bar[sB], (it / kBStages) & 1);
-            tc_fence_after();
-          }
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
-          const uint32_t sa_l = sa_h + kABytes;
-          const uint32_t sb_h = kSplit ? smem_u32(smem + kBRingOff + sB * kBStageBytes) : sa_h + kBOff, sb_l = sb_h + kBBytes;
+          const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + kBOff, sb_l = sb_h + kBBytes;
           const bool skip_lo = p.b2_lo_zero && kb >= nkb1;          // B_lo == 0: the A_hi.B_lo pass adds exact zeros
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -418,7 +362,6 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             if (!HI) tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
           }
           tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);              // frees the stage in both CTAs
-          if (kSplit) tc_commit_2sm(&emptyb_bar[sB], (uint16_t)0x3);
         }
         tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);          // accumulator halves complete in both CTAs
       }
