@@ -206,8 +206,6 @@ struct TcParams {
   float* statpart;       // EPI_F32_STATS
   // A-operand converters (ACV)
   const float* mu;       // ACV_NORM_RELU: [S][512]
-  const float* a_raw;    // ACV: fp32 source of the converted A operand [rows, a_raw_ld]
-  int a_raw_ld;
   const float* rstd;
   // EPI_SCORE_*
   float inv_scale;
@@ -324,7 +322,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           const CUtensorMap* mbl = first ? &maps.b1l : &maps.b2l;
           const int brow = first ? b_row1 : b_row2;
           if (conv) {
-            // the converter warps fetch the raw fp32 tile themselves, straight into registers (no shared-memory round trip)
+            // raw fp32 [128 x 64] = two 32-column boxes, landing where the hi / lo planes will be written
+            mbar_expect_tx(&raw_bar[s], 2 * kABytes);
+            tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
+            tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
           } else {
             tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
             if (!HI) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
@@ -366,17 +367,14 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       }
     }
   } else if (ACV != ACV_NONE && warp >= 8) {
-    // ===================== A-operand converters (warps 8-15): raw fp32 rows -> (hi, lo) planes of the stage =====================
-    // The kernel is bound by the shared-memory port (per k-block and SM: 144 KB of UMMA operand reads + TMA fills + whatever
-    // the conversion moves), so the raw tile never touches shared memory: every converter lane loads its 8 fp32 values per row
-    // straight from global memory into registers (8 lanes = one 256-byte row segment, 4 rows per warp instruction), one
-    // k-block AHEAD of the one being converted, and writes only the two planes (64 KB less port traffic per k-block than
-    // landing the raw tile by TMA and rewriting it in place).
-    // Warp cw owns rows [16 cw, 16 cw + 16) of the tile; lane = (row 4i + lane/8, 8-column group c = lane%8); the plane stores
-    // touch each bank group exactly once per wavefront under the 128-byte swizzle.
+    // ===================== A-operand converters (warps 8-15): raw fp32 tile -> (hi, lo) planes, in place =====================
+    // Warp cw owns rows [16 cw, 16 cw + 16) of the tile: it reads exactly the smem bytes it later overwrites (row r of the raw
+    // boxes and row r of the planes are the same two 128-byte slots), so a __syncwarp between the read and the write phase is
+    // the only ordering needed.  Lane = (row 4i + lane/8, 8-column group c = lane%8): reads raw chunks 2c', 2c'+1 of box c/4,
+    // writes chunk c of both planes -- every shared-memory instruction touches each bank group exactly once per wavefront.
     reg_dec<kConvRegs>();
     constexpr int kLPR = BK / 8;                     // lanes per row = 8-column groups per k-block
-    constexpr int kRPI = 32 / kLPR;                  // rows per warp instruction
+    constexpr int kRPI = 32 / kLPR;                  // rows per shared-memory instruction
     constexpr int kRowIters = BM / kConvWarps / kRPI;
     const int cw = warp - 8;
     const int c = lane % kLPR, rsub = lane / kLPR;
@@ -386,24 +384,13 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       if (crank != 0) mbar_arrive_remote(bar, 0);
       else mbar_arrive(bar);
     };
-    auto unit_row0 = [&](int u_) {
-      const int z_ = u_ / units_per_batch, rem_ = u_ - z_ * units_per_batch;
-      return (int)(z_ * p.a_batch_rows) + ((rem_ / p.n_tiles) * 2 + crank) * BM;
-    };
-    float4 na[kRowIters], nb[kRowIters];             // raw values of the NEXT converted k-block, in flight
-    auto load_raw = [&](int u_, int kb_) {
-      const float* base = p.a_raw + (long long)(unit_row0(u_) + cw * (BM / kConvWarps) + rsub) * p.a_raw_ld + kb_ * BK + 8 * c;
-#pragma unroll
-      for (int i = 0; i < kRowIters; ++i) {
-        const float4* src = reinterpret_cast<const float4*>(base + (long long)(kRPI * i) * p.a_raw_ld);
-        na[i] = __ldg(src);
-        nb[i] = __ldg(src + 1);
-      }
-    };
-    if (unit0 < total_units && nkb1 > 0) load_raw(unit0, 0);
-    uint32_t it = 0, tidx = 0;
+    uint32_t it = 0, raw_phase = 0, tidx = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++tidx) {
-      const int seg = p.L.seg_of_row(unit_row0(u));
+      const int z = u / units_per_batch, rem = u - z * units_per_batch;
+      const int m_tile = (rem / p.n_tiles) * 2 + crank;
+      const int row0 = m_tile * BM;
+      const int seg = p.L.seg_of_row(row0);
+      (void)z;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % kStages;
         const bool conv = kb < nkb1;
@@ -415,15 +402,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           if (lane == 0) conv_arrive(&full_bar[s]);
           continue;
         }
-        float4 ra[kRowIters], rb[kRowIters];
-#pragma unroll
-        for (int i = 0; i < kRowIters; ++i) { ra[i] = na[i]; rb[i] = nb[i]; }
-        {                                            // issue the loads of the following converted k-block (this tile or the next)
-          int un = u, kn = kb + 1;
-          if (kn >= nkb1) { un = u + unit_step; kn = 0; }
-          if (un < total_units) load_raw(un, kn);
-        }
         const uint32_t st = smem_u32(smem) + s * kStageBytes;
+        const uint32_t rawbox = st + ((2 * c) >> 3) * (BM * 128);
         const int kcol = kb * BK + 8 * c;            // first of this lane's 8 source columns
         float pa[8], pb[8];                          // per-column parameters: (-64 mu rstd, 64 rstd)
         {
@@ -437,8 +417,17 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 8; ++j) { pb[j] *= kPre; pa[j] = -pa[j] * pb[j]; }
         }
-        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);      // the stage's previous use has been consumed by the tensor core
+        mbar_wait(&raw_bar[s], (raw_phase >> s) & 1);
+        raw_phase ^= 1u << s;
         if (tl && cw == 0 && lane == 0 && tidx == 1 && kb < 8) tl[3 + 2 * kb] = clock64();
+        float4 ra[kRowIters], rb[kRowIters];
+#pragma unroll
+        for (int i = 0; i < kRowIters; ++i) {
+          const int r = cw * (BM / kConvWarps) + kRPI * i + rsub;
+          ra[i] = lds128(rawbox + r * 128 + ((((2 * c) & 7) ^ (r & 7)) << 4));
+          rb[i] = lds128(rawbox + r * 128 + ((((2 * c + 1) & 7) ^ (r & 7)) << 4));
+        }
+        __syncwarp();                      // every lane holds its raw values before any lane overwrites them
 #pragma unroll
         for (int i = 0; i < kRowIters; ++i) {
           const int r = cw * (BM / kConvWarps) + kRPI * i + rsub;
@@ -1003,7 +992,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   tp.L = p.L; tp.bias = p.bias; tp.tl = timeline;
   tp.inv_scale = p.inv_scale; tp.rowsum_part = p.rowsum_part; tp.colsum_part = p.colsum_part; tp.inv_rowsum = p.inv_rowsum;
   tp.inv_colsum = p.inv_colsum; tp.conf = p.conf; tp.conf_tma = conf_tma; tp.rowbest = p.rowbest; tp.colbest = p.colbest;
-  tp.mu = p.mu; tp.rstd = p.rstd; tp.a_raw = p.a_raw; tp.a_raw_ld = p.a_raw_ld;
+  tp.mu = p.mu; tp.rstd = p.rstd;
   tp.kmean = p.kmean; tp.cross = p.cross; tp.statpart = p.statpart;
   if ((p.epi == EPI_QSCALE || p.b2_per_seg || p.epi == EPI_QKV || p.epi == EPI_F32_STATS || p.a_conv) && !tp.seg_rows) return -1;
   const int total_units = (tp.m_tiles / 2) * tp.n_tiles * tp.batch;
