@@ -149,6 +149,60 @@ int opb_ransac_pnp(const double* K, const double* pts2d, const double* pts3d, co
                    double reproj_error, uint64_t seed, double* workspace, double* pose_out, int32_t* inlier_mask, int32_t* n_inliers,
                    void* stream);
 
+/* ---- adjacent producer: SuperPoint key-point extractor ----
+ * Replaces SuperPoint.forward (reference src/models/extractors/SuperPoint/superpoint.py:140-197): shared VGG-style encoder
+ * (:142-152), score head + 65-way softmax + 8x8 pixel shuffle (:155-160), simple_nms (:47-61, :161), threshold / border /
+ * top-k key-point selection (:163-174), descriptor head (:180-181) and bilinear descriptor sampling (:79-92, :184-185).
+ * Its outputs are the `keypoints2d` / `descriptors2d_query` tensors inference.py:80-94 packs for the matcher; with a fixed
+ * capacity (max_keypoints >= 0) they stay on the device: descriptors [B, 256, cap] + counts [B] are exactly the
+ * `desc2d_query` / `n2d_lengths` arguments of opb_forward. */
+typedef struct opb_superpoint opb_superpoint; /* opaque */
+
+/* = the `config` mapping of SuperPoint.__init__ merged over its default_config (superpoint.py:97-103).  Note that the released
+ * inference configuration (src/sfm/extract_features.py:19-24) spells the threshold key 'keypoints_threshold', so the default
+ * 0.005 is what the reference runs with; nms_radius 3, max_keypoints 4096. */
+typedef struct opb_sp_config {
+  int32_t descriptor_dim;     /* 256 (only value supported)                                                    */
+  int32_t nms_radius;         /* 0..6                                                                          */
+  float keypoint_threshold;   /* superpoint.py:164                                                             */
+  int32_t max_keypoints;      /* > 0, or -1 = keep all (superpoint.py:133-135 raises for 0 and < -1)            */
+  int32_t remove_borders;     /* superpoint.py:64-69                                                           */
+  int32_t align_corners;      /* grid_sample flag: 1 under the reference's pinned torch 1.8 (superpoint.py:86)  */
+  int32_t device;
+} opb_sp_config;
+
+int opb_sp_create(const opb_sp_config* cfg, opb_superpoint** out);
+void opb_sp_destroy(opb_superpoint* h);
+const char* opb_sp_last_error(const opb_superpoint* h); /* h may be NULL: last create error */
+/* Reference state-dict keys ("conv1a.weight", "conv1a.bias", ... "convDb.bias"; superpoint.py:111-126), HOST fp32 arrays in
+ * the reference's own [C_out, C_in, kh, kw] layout.  opb_sp_finalize_weights packs them (tap-major reduction index, the two
+ * heads' 3x3 layers side by side, fp16 hi/lo split) and uploads. */
+int opb_sp_load_weight(opb_superpoint* h, const char* name, const float* data, size_t n_elems);
+int opb_sp_finalize_weights(opb_superpoint* h);
+/* First half of forward(): image device fp32 [B, 1, H, W] (H, W multiples of 8) -> internal candidate lists.
+ * counts (device int32 [B], may be NULL) receives the number of key points opb_sp_describe will emit for each image
+ * (= min(#candidates, max_keypoints)); a caller that needs exactly-sized outputs reads it (the reference synchronises at the
+ * same point: torch.nonzero, superpoint.py:163-165) and passes cap = max(counts). */
+int opb_sp_detect(opb_superpoint* h, const float* image, int32_t B, int32_t H, int32_t W, int32_t* counts, void* stream);
+/* Second half: key points (x, y) fp32 [B, cap, 2], scores fp32 [B, cap], descriptors fp32 [B, 256, cap] (channel-first like the
+ * reference's [256, n]; may be NULL), counts int32 [B]; entries >= counts[b] are not written.  Order: row-major (torch.nonzero)
+ * or, when an image has more than max_keypoints candidates, descending score (torch.topk). */
+int opb_sp_describe(opb_superpoint* h, float* keypoints, float* scores, float* descriptors, int32_t* counts, int32_t cap, void* stream);
+/* Both halves with a caller-chosen capacity, no host synchronisation (cap >= max_keypoints makes it exact). */
+int opb_sp_forward(opb_superpoint* h, const float* image, int32_t B, int32_t H, int32_t W, float* keypoints, float* scores,
+                   float* descriptors, int32_t* counts, int32_t cap, void* stream);
+int opb_sp_last_launch_count(const opb_superpoint* h);
+/* bench.py hooks: with profiling on, an event follows every launch of opb_sp_detect / opb_sp_describe; entry i = launch i
+ * (name, milliseconds, algorithmic FLOPs of a convolution: 2 * interior pixels * C_out * 9 * C_in). */
+int opb_sp_set_profiling(opb_superpoint* h, int32_t enable);
+int opb_sp_get_profile(opb_superpoint* h, int32_t index, char* name, size_t name_cap, double* ms, double* flops);
+/* test hooks: stop the encoder after step i (0 conv1a, 1 conv1b, 2 pool, 3 conv2a, 4 conv2b, 5 pool, 6 conv3a, 7 conv3b, 8 pool,
+ * 9 conv4a, 10 conv4b, 11 [convPa|convDa]; -1 = run everything) and read internal tensors as fp32: which = 0 dense scores
+ * [B,H,W], 1 scores after NMS, 2 convPb output rows [B*P, 128], 3 convDb output rows [B*P, 256], 4 the activation of the last
+ * step run, rows of the zero-bordered pixel grid [B*P, C]. */
+int opb_sp_debug_set_stop(opb_superpoint* h, int32_t layer);
+int opb_sp_debug_read(opb_superpoint* h, int32_t which, float* out, size_t capacity_elems, int64_t* n_elems, void* stream);
+
 /* ---- test hooks (used by tests/ and tools/ only; stable but not part of the drop-in surface) ---- */
 /* Programmatic dependent launch on (default) / off for every launch of the library (A/B measurements). */
 int opb_debug_set_pdl(int32_t enable);

@@ -24,6 +24,13 @@ class OpbConfig(C.Structure):
     ]
 
 
+class OpbSpConfig(C.Structure):
+    _fields_ = [
+        ("descriptor_dim", C.c_int32), ("nms_radius", C.c_int32), ("keypoint_threshold", C.c_float), ("max_keypoints", C.c_int32),
+        ("remove_borders", C.c_int32), ("align_corners", C.c_int32), ("device", C.c_int32),
+    ]
+
+
 # every symbol include/onepose_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _I = C.c_int32
@@ -58,6 +65,20 @@ SYMBOLS = {
     "opb_debug_gemm_aconv": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "opb_debug_split": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "opb_debug_read": (C.c_int, [_P, _I, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
+    # SuperPoint extractor
+    "opb_sp_create": (C.c_int, [C.POINTER(OpbSpConfig), C.POINTER(_P)]),
+    "opb_sp_destroy": (None, [_P]),
+    "opb_sp_last_error": (C.c_char_p, [_P]),
+    "opb_sp_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
+    "opb_sp_finalize_weights": (C.c_int, [_P]),
+    "opb_sp_detect": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "opb_sp_describe": (C.c_int, [_P, _P, _P, _P, _P, _I, _P]),
+    "opb_sp_forward": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "opb_sp_last_launch_count": (C.c_int, [_P]),
+    "opb_sp_set_profiling": (C.c_int, [_P, _I]),
+    "opb_sp_get_profile": (C.c_int, [_P, _I, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "opb_sp_debug_set_stop": (C.c_int, [_P, _I]),
+    "opb_sp_debug_read": (C.c_int, [_P, _I, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
 }
 
 _lib = None
@@ -83,6 +104,14 @@ def load() -> C.CDLL:
 
 class OpbError(RuntimeError):
     pass
+
+
+def check_sp(rc: int, handle=None, lib=None):
+    """Status check for the opb_sp_* (extractor) entry points."""
+    if rc == OPB_OK:
+        return
+    msg = (lib or load()).opb_sp_last_error(handle)
+    raise OpbError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
 
 
 def check(rc: int, handle=None):

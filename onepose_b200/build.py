@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libonepose_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "kv_state_tc.cu", "pnp_ransac.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "kv_state_tc.cu", "pnp_ransac.cu", "superpoint.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "gemm_tc.cuh"
+#include "host_util.cuh"
 #include "kernels_aux.cuh"
 #include "kv_state_tc.cuh"
 
@@ -25,54 +26,9 @@ constexpr int kQPassFrames = 16;    // granularity of the query-side layer-1 pas
 static thread_local std::string g_create_error;
 static bool g_pdl = true;
 static int g_ws_fill = -1;     // >= 0: byte value written into every fresh allocation that the algorithm does not require to be zero
+int ws_fill_byte() { return g_ws_fill; }
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  bool grew = false;      // set by ensure() when it (re)allocated: the caller orders the fill against its stream
-  cudaError_t ensure(size_t need, bool zero = false) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need);
-    if (e != cudaSuccess) return e;
-    bytes = need;
-    grew = true;
-    if (zero) e = cudaMemset(p, 0, need);                       // buffers whose untouched parts are read as zero (bd, flags)
-    else if (g_ws_fill >= 0) e = cudaMemset(p, g_ws_fill, need);   // test hook: poison everything else (opb_debug_set_ws_fill)
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-// A window of rows of a [rows, 256] plane pair (the residual stream of a chunk, the query-only buffer, ...).
-struct XView {
-  __half* hi;
-  __half* lo;
-  CPlanes c(int ld) const { return CPlanes{hi, lo, ld}; }
-  Planes m(int ld) const { return Planes{hi, lo, ld}; }
-};
-
-struct PlaneBuf {
-  DevBuf hi, lo;
-  cudaError_t ensure(size_t elems, bool zero = false) {
-    cudaError_t e = hi.ensure(elems * sizeof(__half), zero);
-    if (e != cudaSuccess) return e;
-    return lo.ensure(elems * sizeof(__half), zero);
-  }
-  void release() { hi.release(); lo.release(); }
-  CPlanes c(int ld, size_t off_elems = 0) const { return CPlanes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
-  Planes m(int ld, size_t off_elems = 0) const { return Planes{hi.as<__half>() + off_elems, lo.as<__half>() + off_elems, ld}; }
-  XView view(size_t row_off = 0) const { return XView{hi.as<__half>() + row_off * kD, lo.as<__half>() + row_off * kD}; }
-};
 
 struct AttnLayerW {       // one AttentionPropagation (reference GATs_SuperGlue.py:104-113)
   PlaneBuf wqkv;          // [768,256]  rows: Q | K | V, head-contiguous output channels
@@ -157,12 +113,6 @@ int fail(opb_matcher* m, int code, const char* fmt, ...) {
     if (_e != cudaSuccess)                                                                            \
       return fail(m, OPB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
-
-static void split_host(const std::vector<double>& w, std::vector<__half>& hi, std::vector<__half>& lo) {
-  hi.resize(w.size());
-  lo.resize(w.size());
-  for (size_t i = 0; i < w.size(); ++i) split_f32((float)w[i], hi[i], lo[i]);
-}
 
 // weight uploads are synchronous copies on the legacy stream; opb_finalize_weights ends with a device synchronisation so that
 // they are ordered against whatever (non-blocking) stream the caller uses afterwards

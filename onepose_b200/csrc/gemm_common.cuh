@@ -29,6 +29,8 @@ enum GemmEpilogue {
                       // x_new = [hn | x] . [W1 | I]^T + b  (K2 = 256 identity block; x_hi*64 + x_lo*64 is exact in the fp32
                       // accumulator), so the epilogue has no global loads -- every chunk of an epilogue ends in a proxy fence that
                       // waits for the thread's outstanding loads, which made a load-x-in-the-epilogue form latency-bound
+  EPI_CONV = 11,      // 3x3 / 1x1 convolution over a zero-bordered pixel grid (superpoint.cu): out planes = [ReLU](acc + bias) on the
+                      // interior pixels, zero on the border / padding rows (so the output is again a valid zero-bordered grid)
 };
 
 struct GemmProblem {
@@ -39,7 +41,17 @@ struct GemmProblem {
   int a_hi_only;         // use only the hi plane of A (A_lo neither loaded nor multiplied): for a product whose OUTPUT is rounded to one
                          // fp16 plane anyway (k,v projection: the dropped term is below the output rounding, zero-mean per row, and the
                          // consumer averages over the segment's rows)
-  int rows, n_out;       // per batch; rows % 256 == 0 (a CTA pair works on two adjacent row tiles), n_out % 256 == 0
+  int rows, n_out;       // per batch; rows % 256 == 0 (a CTA pair works on two adjacent row tiles), n_out % bn == 0
+  int bn;                // column-tile width of the tcgen05 core: 0 / 256 (default), or 64 / 128 (EPI_CONV and EPI_F32 only)
+  // Implicit-GEMM convolution over a row-major pixel grid (A = activations [pixels, C_in], one row per pixel of a grid with a zero
+  // border): reduction block `tap` (= kb / kb_per_tap) reads the A rows shifted by tap_off[tap] pixels and the B columns
+  // [tap*C_in, (tap+1)*C_in) -- the 9 taps of a 3x3 kernel are 9 row-shifted TMA loads of the same matrix, never an im2col buffer.
+  int taps;              // 0: plain GEMM
+  int kb_per_tap;        // C_in / 64
+  int tap_off[9];
+  // EPI_CONV: pixel-grid geometry (row r is pixel q = r % cv_ppad of its image; y = q / cv_w2, x = q % cv_w2; interior:
+  // 1 <= y <= cv_h, 1 <= x <= cv_w) and the activation
+  int cv_w2, cv_h, cv_w, cv_ppad, relu;
   int batch;
   long long a_batch_rows, b_batch_rows, c_batch_elems;
   Layout L;

@@ -180,8 +180,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M = 256 across the CTA pair, N = BN
-constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+// kind::f16 instruction descriptor (built per column-tile width inside the kernel): D=f32, A=B=f16, both K-major, M = 256 across
+// the CTA pair, N = BN
 
 // byte offset of 16-byte chunk j of row r inside a 128-row x 128-B SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -217,6 +217,10 @@ struct TcParams {
   int conf_tma;          // 1: conf goes out through the 3-D tensor map (M % 4 == 0), 0: plain stores from the staged chunk
   unsigned long long* rowbest;
   unsigned long long* colbest;
+  // implicit-GEMM convolution (GemmProblem::taps) and the EPI_CONV geometry
+  int taps, kb_per_tap;
+  int tap_off[9];
+  int cv_w2, cv_h, cv_w, cv_ppad, relu;
 };
 
 struct Maps {
@@ -236,9 +240,16 @@ enum { ACV_NONE = 0, ACV_NORM_RELU = 1 };
 // HI: the A operand enters with its hi plane only (k,v projection, GemmProblem::a_hi_only): the stage shrinks to A_hi + B_hi + B_lo =
 // 48 KB and the ring deepens to FOUR stages in the same 192 KB -- with two passes a k-block is only ~1k cycles of MMA, and three
 // stages cannot cover the ~4k-cycle turn-around of a stage (load issue -> data landed) any more.
-template <int EPI, int ACV = ACV_NONE, bool HI = false>
+// BN_: column-tile width (256 for every matcher GEMM; 64 / 128 for the narrow convolution layers of the extractor: the B half-tile
+// shrinks to BN_/2 rows per CTA and the ring deepens to four stages).
+template <int EPI, int ACV = ACV_NONE, bool HI = false, int BN_ = 256>
 __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __grid_constant__ Maps maps, TcParams p) {
-  constexpr int kStages = HI ? 4 : kStagesFull;
+  constexpr int BN = BN_;
+  constexpr int kBBytes = (BN / 2) * BK * 2;
+  constexpr int kStageBytesFull = 2 * kABytes + 2 * kBBytes;
+  constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  static_assert(BN_ == 256 || (BN_ == 64 || BN_ == 128) && ACV == ACV_NONE && !HI && (EPI == EPI_CONV || EPI == EPI_F32), "narrow tiles: conv / fp32 epilogues only");
+  constexpr int kStages = (HI || BN_ != 256) ? 4 : kStagesFull;
   constexpr int kStageBytes = HI ? kABytes + 2 * kBBytes : kStageBytesFull;
   constexpr int kBOff = HI ? kABytes : 2 * kABytes;      // offset of the B planes inside a stage
   static_assert(!HI || ACV == ACV_NONE, "converters need the full stage");
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
     if (p.K2) { prefetch_tmap(&maps.a2h); prefetch_tmap(&maps.a2l); prefetch_tmap(&maps.b2h); prefetch_tmap(&maps.b2l); }
     if (ACV) prefetch_tmap(&maps.a_raw);
     if (EPI == EPI_F32 || EPI == EPI_F32_STATS || EPI == EPI_SCORE_CONF) prefetch_tmap(&maps.out_f32);
-    if (EPI == EPI_QKV || EPI == EPI_QSCALE || EPI == EPI_L2NORM || EPI == EPI_BIAS_PLANES) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
+    if (EPI == EPI_QKV || EPI == EPI_QSCALE || EPI == EPI_L2NORM || EPI == EPI_BIAS_PLANES || EPI == EPI_CONV) { prefetch_tmap(&maps.out_hi); prefetch_tmap(&maps.out_lo); }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
@@ -315,7 +326,14 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
           if (crank == 0)                                               // leader arms for both CTAs' loads
             mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);
-          const int kc = (first ? kb * BK : (kb - nkb1) * BK);
+          int kc = (first ? kb * BK : (kb - nkb1) * BK);
+          int arow = a_row, kcb = kc;                                   // A rows / B columns of this k-block
+          if (EPI == EPI_CONV && p.taps) {                              // implicit-GEMM convolution: tap t = row-shifted A, B columns follow kb
+            const int t = kb / p.kb_per_tap;
+            kcb = kb * BK;
+            kc = (kb - t * p.kb_per_tap) * BK;
+            arow = a_row + p.tap_off[t];                                // may leave [0, rows): the tensor map zero-fills
+          }
           const CUtensorMap* mah = first ? &maps.a1h : &maps.a2h;
           const CUtensorMap* mal = first ? &maps.a1l : &maps.a2l;
           const CUtensorMap* mbh = first ? &maps.b1h : &maps.b2h;
@@ -327,11 +345,11 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             tma_load_2d(st, &maps.a_raw, &raw_bar[s], kc, a_row);
             tma_load_2d(st + kABytes, &maps.a_raw, &raw_bar[s], kc + 32, a_row);
           } else {
-            tma_load_2d_2sm(st, mah, &full_bar[s], kc, a_row);
-            if (!HI) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, a_row);
+            tma_load_2d_2sm(st, mah, &full_bar[s], kc, arow);
+            if (!HI) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, arow);
           }
-          tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kc, brow);
-          tma_load_2d_2sm(st + kBOff + kBBytes, mbl, &full_bar[s], kc, brow);
+          tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kcb, brow);
+          tma_load_2d_2sm(st + kBOff + kBBytes, mbl, &full_bar[s], kcb, brow);
         }
       }
     }
@@ -689,6 +707,51 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         if (rbest_c >= 0)
           atomicMax(p.rowbest + (long long)z * p.L.N + row,
                     ((unsigned long long)__float_as_uint(rbest_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)rbest_c));
+      } else if (EPI == EPI_CONV) {
+        // ---- convolution layer out: planes = [ReLU](acc + bias) on interior pixels, zero on the grid's border and padding rows
+        // (the output is the next layer's zero-bordered input), 32 columns per chunk
+        const long long grow = (long long)out_row0 + r_in_tile;
+        const int qpix = (int)(grow % p.cv_ppad);
+        const int yy = qpix / p.cv_w2, xx = qpix - yy * p.cv_w2;
+        const bool row_ok = yy >= 1 && yy <= p.cv_h && xx >= 1 && xx <= p.cv_w;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c0, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * BN + c0;
+          uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
+          uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;
+          stage_wait();
+          epi_bar();
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j8 * 8 + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 oh, ol;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {    // same rounding as split_f32, two elements per conversion instruction
+              float2 sc = make_float2(fmaf(__uint_as_float(v[j8 * 8 + 2 * e]), kPreInv, bb[2 * e] * kPre),
+                                      fmaf(__uint_as_float(v[j8 * 8 + 2 * e + 1]), kPreInv, bb[2 * e + 1] * kPre));
+              if (p.relu) sc = make_float2(fmaxf(sc.x, 0.f), fmaxf(sc.y, 0.f));
+              if (!row_ok) sc = make_float2(0.f, 0.f);
+              const __half2 h2 = __float22half2_rn(sc);
+              const float2 back = __half22float2(h2);
+              reinterpret_cast<__half2*>(&oh)[e] = h2;
+              reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
+            }
+            *reinterpret_cast<uint4*>(sh + stg64_off(r_in_tile, j8)) = oh;
+            *reinterpret_cast<uint4*>(sl + stg64_off(r_in_tile, j8)) = ol;
+          }
+          fence_async_smem();
+          epi_bar();
+          if (leader) {
+            tma_store_2d(&maps.out_hi, sh, col0, out_row0);
+            tma_store_2d(&maps.out_lo, sl, col0, out_row0);
+            tma_store_commit();
+          }
+        }
       } else if (EPI == EPI_BIAS_PLANES) {
         // ---- out planes = acc + bias, 32 columns per chunk (a residual, if any, already sits in the accumulator: identity
         // K-block); rows past the segment's valid count are written as zero so that padding never accumulates state
@@ -923,10 +986,10 @@ int num_sms() {
   return n;
 }
 
-template <int EPI, int ACV = ACV_NONE, bool HI = false>
+template <int EPI, int ACV = ACV_NONE, bool HI = false, int BN_ = 256>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const Maps& mp, const TcParams& tp) {
   static bool attr_done = false;
-  auto* kern = gemm_tc_kernel<EPI, ACV, HI>;
+  auto* kern = gemm_tc_kernel<EPI, ACV, HI, BN_>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -942,8 +1005,12 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
 }
 
 int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timeline) {
-  if (p.rows % (2 * BM) || p.n_out % BN || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.batch <= 0) return -1;
+  const int bn = p.bn ? p.bn : BN;                 // column-tile width
+  if (bn != BN && !((bn == 64 || bn == 128) && (p.epi == EPI_CONV || p.epi == EPI_F32) && !p.K2 && !p.a_conv && !p.a_hi_only)) return -1;
+  if (p.rows % (2 * BM) || p.n_out % bn || p.K1 % BK || p.K2 % BK || p.K1 <= 0 || p.batch <= 0) return -1;
   if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM || p.epi == EPI_BIAS_PLANES) && p.n_out != BN) return -1;
+  if (p.taps && (p.epi != EPI_CONV || p.taps > 9 || p.kb_per_tap <= 0 || p.taps * p.kb_per_tap * BK != p.K1 || p.K2 || p.batch != 1)) return -1;
+  if (p.epi == EPI_CONV && (!p.bias || !p.out.hi || !p.out.lo || p.cv_ppad <= 0 || p.cv_w2 <= 0 || p.batch != 1)) return -1;
   if (p.a_hi_only && (p.a_conv || p.K2 || p.epi != EPI_QKV)) return -1;
   if (p.a_conv && (p.a_conv != ACV_NORM_RELU || p.batch != 1 || !p.a_raw || p.epi != EPI_BIAS_PLANES || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
@@ -956,9 +1023,12 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   const long long b1_rows = (long long)(p.batch - 1) * p.b_batch_rows + p.n_out;
   const long long b2_rows = p.b2_per_seg ? (long long)p.L.segs() * p.n_out : p.n_out;
   Maps mp;
-  bool ok = make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, BN / 2, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, BN / 2, false);
+  bool ok = make_map(&mp.b1h, p.b1.hi, b1_rows, p.K1, p.b1.ld, BK, bn / 2, false) && make_map(&mp.b1l, p.b1.lo, b1_rows, p.K1, p.b1.ld, BK, bn / 2, false);
   if (p.a_conv) { mp.a1h = mp.b1h; mp.a1l = mp.b1l; }     // every A1 tile comes in raw: the plane maps are never used
-  else ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, p.K1, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, p.K1, p.a1.ld, BK, BM, false);
+  else {
+    const long long a_cols = p.taps ? (long long)p.kb_per_tap * BK : p.K1;      // convolution: A has C_in columns, the taps shift its rows
+    ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false);
+  }
   if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.K1, p.a_raw_ld, 32, BM, true);
   else mp.a_raw = mp.b1h;
   if (ok && p.K2) {
@@ -986,7 +1056,10 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (!ok) return -2;
   TcParams tp{};
   tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.n_out = p.n_out;
-  tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / BN; tp.batch = p.batch;
+  tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / bn; tp.batch = p.batch;
+  tp.taps = p.taps; tp.kb_per_tap = p.kb_per_tap;
+  for (int t = 0; t < 9; ++t) tp.tap_off[t] = p.tap_off[t];
+  tp.cv_w2 = p.cv_w2; tp.cv_h = p.cv_h; tp.cv_w = p.cv_w; tp.cv_ppad = p.cv_ppad; tp.relu = p.relu;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;
   tp.L = p.L; tp.bias = p.bias; tp.tl = timeline;
@@ -1013,7 +1086,14 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
     le = launch_variant<EPI_BIAS_PLANES, ACV_NORM_RELU>(cfg, mp, tp);
   } else {
     switch (p.epi) {
-      case EPI_F32: le = launch_variant<EPI_F32>(cfg, mp, tp); break;
+      case EPI_F32:
+        le = bn == 64 ? launch_variant<EPI_F32, ACV_NONE, false, 64>(cfg, mp, tp)
+                      : bn == 128 ? launch_variant<EPI_F32, ACV_NONE, false, 128>(cfg, mp, tp) : launch_variant<EPI_F32>(cfg, mp, tp);
+        break;
+      case EPI_CONV:
+        le = bn == 64 ? launch_variant<EPI_CONV, ACV_NONE, false, 64>(cfg, mp, tp)
+                      : bn == 128 ? launch_variant<EPI_CONV, ACV_NONE, false, 128>(cfg, mp, tp) : launch_variant<EPI_CONV>(cfg, mp, tp);
+        break;
       case EPI_F32_STATS: le = launch_variant<EPI_F32_STATS>(cfg, mp, tp); break;
       case EPI_QSCALE: le = launch_variant<EPI_QSCALE>(cfg, mp, tp); break;
       case EPI_L2NORM: le = launch_variant<EPI_L2NORM>(cfg, mp, tp); break;

@@ -191,3 +191,52 @@ def make_pnp_scene(seed: int, n: int, outlier_frac: float = 0.4, noise_px: float
     out = rs.rand(n) < outlier_frac
     uv[out] = rs.rand(int(out.sum()), 2) * size
     return K, uv, P, np.concatenate([R, t[:, None]], 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# SuperPoint extractor: reference-shaped state dict and seeded grey images
+# ---------------------------------------------------------------------------------------------
+SUPERPOINT_LAYERS = [
+    # name, C_out, C_in, kernel  (reference src/models/extractors/SuperPoint/superpoint.py:111-126)
+    ("conv1a", 64, 1, 3), ("conv1b", 64, 64, 3), ("conv2a", 64, 64, 3), ("conv2b", 64, 64, 3),
+    ("conv3a", 128, 64, 3), ("conv3b", 128, 128, 3), ("conv4a", 128, 128, 3), ("conv4b", 128, 128, 3),
+    ("convPa", 256, 128, 3), ("convPb", 65, 256, 1), ("convDa", 256, 128, 3), ("convDb", 256, 256, 1),
+]
+
+# the extractor configuration inference.py runs with (src/sfm/extract_features.py:19-24).  NB the key 'keypoints_threshold'
+# is NOT the key SuperPoint reads ('keypoint_threshold', superpoint.py:99,164): the default 0.005 stays in force.
+SUPERPOINT_CONF = {"descriptor_dim": 256, "nms_radius": 3, "max_keypoints": 4096, "keypoints_threshold": 0.6}
+
+
+def make_superpoint_state_dict(seed: int = 0, score_gain: float = 6.0):
+    """He-initialised conv stack (activations stay O(1) through the ReLUs); the score head's last layer is scaled by
+    ``score_gain`` so that the 65-way softmax is peaked and the 0.005 threshold actually separates pixels."""
+    rs = np.random.RandomState(7000 + seed)
+    sd = {}
+    for name, cout, cin, k in SUPERPOINT_LAYERS:
+        fan_in = cin * k * k
+        w = (rs.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        b = rs.uniform(-0.05, 0.05, size=(cout,)).astype(np.float32)
+        if name == "convPb":
+            w *= np.float32(score_gain)
+        sd[name + ".weight"] = w
+        sd[name + ".bias"] = b
+    return sd
+
+
+def make_image(seed: int, H: int, W: int):
+    """Grey image in [0, 1], fp32 [1, H, W]: a few smooth blobs and edges plus fine texture (corners for the detector)."""
+    rs = np.random.RandomState(9000 + seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    img = np.zeros((H, W))
+    for _ in range(12):
+        cy, cx = rs.uniform(0, H), rs.uniform(0, W)
+        sy, sx = rs.uniform(H / 20, H / 4), rs.uniform(W / 20, W / 4)
+        img += rs.uniform(-1, 1) * np.exp(-(((yy - cy) / sy) ** 2 + ((xx - cx) / sx) ** 2))
+    for _ in range(6):   # rectangles: sharp corners
+        y0, x0 = int(rs.uniform(0, H * 0.8)), int(rs.uniform(0, W * 0.8))
+        y1, x1 = y0 + int(rs.uniform(8, H * 0.3)), x0 + int(rs.uniform(8, W * 0.3))
+        img[y0:y1, x0:x1] += rs.uniform(-0.6, 0.6)
+    img += 0.15 * rs.standard_normal((H, W))
+    img = (img - img.min()) / (img.max() - img.min())
+    return img.astype(np.float32)[None]

@@ -15,7 +15,13 @@ Also stores the adjacent producers: ``mean_descriptors`` / ``mean_scores``
 (reference ``src/sfm/postprocess/feature_process.py:297-317``; the module needs h5py at import
 time, so the two functions are exec'd from its SOURCE TEXT, unmodified) and
 ``pad_features3d_random`` / ``build_features3d_leaves`` (``src/utils/data_utils.py:143-205``,
-imported) under a fixed ``np.random.seed``.
+imported) under a fixed ``np.random.seed``; ``cv2.solvePnPRansac`` poses through ``ransac_PnP``
+(``src/utils/eval_utils.py:18-42``); and the SuperPoint extractor (``src/models/extractors/SuperPoint/superpoint.py``,
+imported) on seeded weights / images -- once as this image's torch runs it (grid_sample align_corners=False) and once with
+``torch.__version__`` reading "1.8.0", the reference's pinned version, so that the module itself takes its align_corners=True
+branch (superpoint.py:86).
+
+    python tests/golden/make_golden.py [superpoint|matcher|producers|pnp ...]     (default: everything)
 """
 import os
 import sys
@@ -207,12 +213,66 @@ def state_dict_spec():
     print("state_dict_spec:", len(spec), "keys")
 
 
+SUPERPOINT_CASES = [
+    # name, weight seed, score gain, image seeds, H, W, config, descriptor columns stored (every n-th key point)
+    dict(name="superpoint_b2_128x160", wseed=0, gain=4.0, images=[1, 2], H=128, W=160, conf=dict(synthetic.SUPERPOINT_CONF), every=1),
+    dict(name="superpoint_topk_96x128", wseed=1, gain=4.0, images=[3], H=96, W=128,
+         conf={"nms_radius": 4, "max_keypoints": 150, "keypoint_threshold": 0.005, "remove_borders": 4}, every=1),
+    dict(name="superpoint_all_64x64", wseed=2, gain=1.0, images=[4], H=64, W=64, conf={"max_keypoints": -1, "remove_borders": 2}, every=1),
+    dict(name="superpoint_512x512", wseed=0, gain=4.0, images=[5], H=512, W=512, conf=dict(synthetic.SUPERPOINT_CONF), every=16),
+]
+
+
+def superpoint_cases():
+    """SuperPoint.forward of the imported, unmodified reference module on seeded weights and images."""
+    import json
+    import warnings
+    from src.models.extractors.SuperPoint.superpoint import SuperPoint
+    with open(os.path.join(HERE, "superpoint_state_dict_spec.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in SuperPoint({}).state_dict().items()}, f, indent=0)
+    for c in SUPERPOINT_CASES:
+        sd = synthetic.make_superpoint_state_dict(c["wseed"], c["gain"])
+        model = SuperPoint(c["conf"]).eval()
+        model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+        img = torch.from_numpy(np.stack([synthetic.make_image(i, c["H"], c["W"]) for i in c["images"]], 0))
+        out = {"meta_wseed": c["wseed"], "meta_gain": c["gain"], "meta_images": np.array(c["images"]), "meta_H": c["H"], "meta_W": c["W"],
+               "meta_conf_keys": np.array(sorted(c["conf"].keys())), "meta_conf_vals": np.array([float(c["conf"][k]) for k in sorted(c["conf"].keys())]),
+               "meta_every": c["every"]}
+        real_version = torch.__version__
+        for tag, version in (("ac0", real_version), ("ac1", "1.8.0")):
+            torch.__version__ = version
+            try:
+                with torch.no_grad(), warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    pred = model(img)
+            finally:
+                torch.__version__ = real_version
+            for b in range(len(c["images"])):
+                if tag == "ac0":
+                    out[f"keypoints_{b}"] = pred["keypoints"][b].numpy()
+                    out[f"scores_{b}"] = pred["scores"][b].numpy()
+                else:
+                    assert np.array_equal(out[f"keypoints_{b}"], pred["keypoints"][b].numpy())
+                out[f"descriptors_{tag}_{b}"] = pred["descriptors"][b].numpy()[:, ::c["every"]]
+        n = [len(out[f"keypoints_{b}"]) for b in range(len(c["images"]))]
+        d = float(np.abs(out["descriptors_ac0_0"] - out["descriptors_ac1_0"]).max())
+        print(f"{c['name']}: key points {n}, score range [{out['scores_0'].min():.4f}, {out['scores_0'].max():.4f}], "
+              f"|desc(ac=False) - desc(ac=True)| max {d:.3f}")
+        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    state_dict_spec()
-    for c in CASES:
-        run_case(c)
-    empty_case()
-    mean_cases()
-    features3d_cases()
-    pnp_cases()
+    what = set(sys.argv[1:]) or {"matcher", "producers", "pnp", "superpoint"}
+    if "matcher" in what:
+        state_dict_spec()
+        for c in CASES:
+            run_case(c)
+        empty_case()
+    if "producers" in what:
+        mean_cases()
+        features3d_cases()
+    if "pnp" in what:
+        pnp_cases()
+    if "superpoint" in what:
+        superpoint_cases()

@@ -9,7 +9,7 @@ from onepose_b200 import synthetic
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FORWARD_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                       if not os.path.basename(p).startswith(("empty", "mean_", "features3d", "dustbin", "pnp_")))
+                       if not os.path.basename(p).startswith(("empty", "mean_", "features3d", "dustbin", "pnp_", "superpoint")))
 RELEASED_CASES = [c for c in FORWARD_CASES if not c.startswith(("noself", "lintrans", "additional"))]
 
 
@@ -41,3 +41,18 @@ def load_dustbin_case():
     data = {"keypoints2d": np.zeros((1, N, 2), np.float32), "keypoints3d": np.zeros((1, M, 3), np.float32),
             "descriptors2d_query": g["query"][None], "descriptors3d_db": g["desc3d"][None], "descriptors2d_db": g["desc2d"][None]}
     return g, hp, sd, data
+
+
+SUPERPOINT_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "superpoint_*.npz")))
+
+
+def load_superpoint_case(name):
+    """(fixture, state dict, config, images [B,1,H,W]) of a SuperPoint golden (inputs regenerated from the recorded seeds)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    sd = synthetic.make_superpoint_state_dict(int(g["meta_wseed"]), float(g["meta_gain"]))
+    conf = {}
+    for k, v in zip(g["meta_conf_keys"], g["meta_conf_vals"]):
+        k = str(k)
+        conf[k] = float(v) if "threshold" in k else int(v)
+    img = np.stack([synthetic.make_image(int(i), int(g["meta_H"]), int(g["meta_W"])) for i in g["meta_images"]], 0)
+    return g, sd, conf, img

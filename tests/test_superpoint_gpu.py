@@ -1,0 +1,163 @@
+"""SuperPoint extractor on the GPU (run with -m gpu on a B200): the CUDA path through the module / C ABI against the golden
+vectors of the reference module and against the CPU oracle, layer by layer and end to end.  Bars: key points (indices) bit-
+exact, scores within 2e-6, descriptors within 2e-5 (the network is fp32 in the reference; the device computes fp32 semantics
+with the 3-pass fp16-split tensor-core product)."""
+import numpy as np
+import pytest
+import torch
+
+from onepose_b200 import GATsSuperGlue, SuperPoint, synthetic
+from oracle import superpoint_oracle as O
+from tests import sp_emulation as E
+from tests.golden_util import SUPERPOINT_CASES, load_superpoint_case
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 2e-6
+DESC_TOL = 2e-5
+
+
+def _module(sd, conf, align_corners=True):
+    m = SuperPoint(conf, align_corners=align_corners).eval()
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    return m.cuda()
+
+
+def _compare_keypoints(out, ref_k, ref_s, tag, nms_ref=None):
+    """Key points bit-exact; if a candidate sits within fp32 noise of the threshold or of a neighbour in its NMS window the
+    reference's own decision is a coin flip -- report it precisely instead of hiding it."""
+    mine = out["keypoints"].cpu().numpy() if torch.is_tensor(out["keypoints"]) else out["keypoints"]
+    assert mine.shape == ref_k.shape, f"{tag}: {mine.shape[0]} key points, reference {ref_k.shape[0]}"
+    np.testing.assert_array_equal(mine, ref_k, err_msg=tag)
+    s = out["scores"].cpu().numpy() if torch.is_tensor(out["scores"]) else out["scores"]
+    assert np.abs(s - ref_s).max() <= SCORE_TOL, f"{tag}: score error {np.abs(s - ref_s).max():.2e}"
+
+
+# ----------------------------------------------------------------------------- encoder, layer by layer
+def test_encoder_layers_match_oracle():
+    sd = synthetic.make_superpoint_state_dict(0, 4.0)
+    H, W, B = 64, 80, 2
+    img = np.stack([synthetic.make_image(i, H, W) for i in (1, 2)], 0)
+    m = _module(sd, synthetic.SUPERPOINT_CONF)
+    p = O.params_from_numpy(sd)
+    x = torch.from_numpy(img)
+    m.forward_padded(x.cuda())                      # creates the handle
+    chans = [64, 64, 64, 64, 64, 64, 128, 128, 128, 128, 128]
+    stages = [0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3]
+    errs = []
+    for i in range(11):
+        m.debug_stop_after(i)
+        m.forward_padded(x.cuda())
+        s = stages[i]
+        h, w, P = E.stage(H, W, s)
+        rows = m.debug_read(4, B * P * chans[i]).cpu().numpy().reshape(B * P, chans[i])
+        ref = E.to_grid(O.encoder(p, x, upto=i).numpy())
+        err = float(np.abs(rows - ref).max())
+        errs.append(err)
+        assert err < 2e-5 * max(1.0, float(np.abs(ref).max())), f"encoder step {i} ({O.ENCODER[i]}): max error {err:.3e}, ref max {np.abs(ref).max():.3f}"
+        q = np.arange(B * P) % P
+        yy, xx = q // (w + 2), q % (w + 2)
+        border = (yy < 1) | (yy > h) | (xx < 1) | (xx > w)
+        assert not rows[border].any(), f"encoder step {i}: border / padding rows must be zero"
+    m.debug_stop_after(-1)
+    print("encoder max errors per step:", " ".join(f"{e:.1e}" for e in errs))
+
+
+def test_heads_scores_and_nms_match_oracle():
+    sd = synthetic.make_superpoint_state_dict(0, 4.0)
+    H, W, B = 64, 80, 2
+    img = np.stack([synthetic.make_image(i, H, W) for i in (1, 2)], 0)
+    m = _module(sd, synthetic.SUPERPOINT_CONF)
+    p = O.params_from_numpy(sd)
+    x = torch.from_numpy(img)
+    m.forward_padded(x.cuda())
+    feat = O.encoder(p, x)
+    h3, w3, P3 = E.stage(H, W, 3)
+    logits = m.debug_read(2, B * P3 * 128).cpu().numpy().reshape(B * P3, 128)[:, :65]
+    ref = O._conv(p, "convPb", O._conv(p, "convPa", feat), relu=False).numpy()
+    assert np.abs(E.from_grid(logits, B, 65, h3, w3) - ref).max() < 1e-4
+    dd = m.debug_read(3, B * P3 * 256).cpu().numpy().reshape(B * P3, 256)
+    refd = O._conv(p, "convDb", O._conv(p, "convDa", feat), relu=False).numpy()
+    assert np.abs(E.from_grid(dd, B, 256, h3, w3) - refd).max() < 1e-4
+    sc_ref = O.dense_scores(p, feat)
+    sc = m.debug_read(0, B * H * W).cpu().reshape(B, H, W)
+    assert float((sc - sc_ref).abs().max()) < SCORE_TOL
+    # NMS is exact integer-style logic on the scores it is given: feed the oracle's NMS the DEVICE scores
+    nms = m.debug_read(1, B * H * W).cpu().reshape(B, H, W)
+    assert torch.equal(nms, O.simple_nms(sc, 3))
+
+
+# ----------------------------------------------------------------------------- golden vectors of the reference module
+@pytest.mark.parametrize("name", SUPERPOINT_CASES)
+def test_golden_reference_outputs(name):
+    g, sd, conf, img = load_superpoint_case(name)
+    every = int(g["meta_every"])
+    x = torch.from_numpy(img).cuda()
+    for ac, tag in ((True, "ac1"), (False, "ac0")):
+        m = _module(sd, conf, align_corners=ac)
+        out = m(x)
+        for b in range(img.shape[0]):
+            one = {"keypoints": out["keypoints"][b], "scores": out["scores"][b]}
+            _compare_keypoints(one, g[f"keypoints_{b}"], g[f"scores_{b}"], f"{name}[{b}]")
+            d = out["descriptors"][b].cpu().numpy()
+            assert d.shape[0] == 256 and d.flags["C_CONTIGUOUS"]
+            err = np.abs(d[:, ::every] - g[f"descriptors_{tag}_{b}"]).max()
+            assert err <= DESC_TOL, f"{name}[{b}] {tag}: descriptor error {err:.2e}"
+        assert out["keypoints"][0].dtype == torch.float32 and out["scores"][0].dtype == torch.float32
+
+
+def test_batch_equals_single_images_and_is_deterministic():
+    sd = synthetic.make_superpoint_state_dict(3, 4.0)
+    H, W = 120, 104                                   # not multiples of the 32-pixel NMS tile
+    img = torch.from_numpy(np.stack([synthetic.make_image(i, H, W) for i in (7, 8, 9)], 0)).cuda()
+    m = _module(sd, {"nms_radius": 4, "max_keypoints": 300})
+    both = m(img)
+    again = m(img)
+    for b in range(3):
+        solo = m(img[b:b + 1])
+        for k in ("keypoints", "scores", "descriptors"):
+            assert torch.equal(both[k][b], solo[k][0]), (k, b)
+            assert torch.equal(both[k][b], again[k][b]), (k, b)
+    ref = O.forward(O.params_from_numpy(sd), img.cpu().numpy(), {"nms_radius": 4, "max_keypoints": 300})
+    for b in range(3):
+        _compare_keypoints({"keypoints": both["keypoints"][b], "scores": both["scores"][b]}, ref["keypoints"][b].numpy(),
+                           ref["scores"][b].numpy(), f"batch[{b}]")
+        assert float((both["descriptors"][b].cpu() - ref["descriptors"][b]).abs().max()) <= DESC_TOL
+
+
+def test_rejects_bad_shapes():
+    m = _module(synthetic.make_superpoint_state_dict(0), {})
+    with pytest.raises(Exception, match="multiples of 8"):
+        m(torch.zeros(1, 1, 60, 64, device="cuda"))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda"))
+    with pytest.raises(ValueError, match="capacity"):
+        m.forward_padded(torch.zeros(1, 1, 64, 64, device="cuda"))      # max_keypoints = -1 needs an explicit capacity
+
+
+# ----------------------------------------------------------------------------- device-resident hand-off to the matcher (N1)
+def test_extractor_feeds_matcher_without_host_round_trip():
+    """SuperPoint -> GATsSPG on the device: padded descriptors + counts go straight into match_frames(lengths=counts); the result
+    equals the reference's route (per-frame tensors sliced to their own length, inference.py:140-146)."""
+    sp = _module(synthetic.make_superpoint_state_dict(0, 4.0), {"nms_radius": 3, "max_keypoints": 256})
+    hp = dict(synthetic.DEFAULT_HPARAMS)
+    mm = GATsSuperGlue(hp).eval()
+    mm.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in synthetic.make_state_dict(0).items()})
+    mm = mm.cuda()
+    db, leaves = synthetic.make_object(3, 500, 8)
+    mm.set_object(torch.from_numpy(db).cuda(), torch.from_numpy(leaves).cuda())
+    img = torch.from_numpy(np.stack([synthetic.make_image(i, 96, 128) for i in (11, 12, 13)], 0)).cuda()
+    det = sp.forward_padded(img)
+    counts = det["counts"].cpu().tolist()
+    assert len(set(counts)) > 1 or counts[0] < 256, counts               # a ragged batch
+    # entries beyond a frame's count are unspecified: give them a defined value for the comparison below
+    desc = det["descriptors"].clone()
+    for b, n in enumerate(counts):
+        desc[b, :, n:] = 0
+    out = mm.match_frames(desc, lengths=det["counts"])
+    for b, n in enumerate(counts):
+        solo = mm.match_frames(desc[b:b + 1, :, :n].contiguous())
+        assert torch.equal(out["matches0"][b, :n], solo["matches0"][0])
+        assert torch.equal(out["matches1"][b], solo["matches1"][0])
+        assert float((out["conf_matrix"][b, :n] - solo["conf_matrix"][0]).abs().max()) < 1e-6
+        assert bool((out["matches0"][b, n:] == -1).all())
