@@ -18,6 +18,9 @@ Printed JSON line (rank 0): see the contract in the task description; extra obje
   value_no_conf the same step without materialising the confidence matrix (inference.py:146 discards it)
   latency_b1    the reference's own calling convention: B=1 per frame through forward(data) (inference.py:80-94,146)
   config4       BASELINE configs[3]: B=16, N2D=2000, N3D=15000 (full step and tail only)
+  superpoint    the producer of the query descriptors: SuperPoint at 512 x 512, images/s device / e2e / B=1, per-launch
+                profile with the convolution rooflines, the CPU port beside it, parity check of one image
+  pipeline      image -> pose on the device: SuperPoint -> matcher (ragged lengths) -> RANSAC-PnP, no host round trip between stages
   config5       BASELINE configs[4] substitute: 80 heterogeneous synthetic objects, LPT-sharded over the ranks, set_object and
                 workspace growth inside the timed region, STRONG scaling (fixed total work) -- whole-job frames/s
 """
@@ -56,7 +59,8 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region: NVML polled every ~5 ms from a thread (the timed region of the default
+    run is < 100 ms: nvidia-smi's 100 ms loop would see one sample); falls back to `nvidia-smi -lms` if pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -64,21 +68,58 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []          # (sm MHz, reasons bitmask, power W)
+        self.stop_flag = False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, reasons, n.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            sm = [x[0] for x in self.samples]
+            seen = sorted({name for _, r, _ in self.samples for name, b in bits.items() if r & b})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": seen, "samples": len(sm), "power_w_max": max((x[2] for x in self.samples), default=None), "source": "nvml, 4 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +132,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def cpu_threads():
@@ -352,6 +393,146 @@ def leg_pnp(dev, synthetic, frames=32, n=512):
     return out
 
 
+def leg_superpoint(dev, synthetic, rank, B=8, H=512, W=512, steps=5):
+    """The producer of the query descriptors: SuperPoint at the reference's 512 x 512 input
+    (src/sfm/extract_features.py:14-17), released configuration (nms_radius 3, max_keypoints 4096).  device: B images resident,
+    CUDA events; e2e: pinned host images -> device -> key points + counts back on the host; b1: the reference's own calling
+    convention, one image per forward(inp) (inference.py:137-138); per-launch profile with the convolution rooflines; the oracle
+    port of the reference CPU forward beside it."""
+    from onepose_b200 import SuperPoint
+    sd = synthetic.make_superpoint_state_dict(0, 4.0)
+    sp = SuperPoint(synthetic.SUPERPOINT_CONF).eval()
+    sp.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()})
+    sp = sp.to(dev)
+    host = torch.from_numpy(np.stack([synthetic.make_image(100 + i, H, W) for i in range(B)], 0)).pin_memory()
+    img = host.to(dev)
+    for _ in range(3):
+        out = sp.forward_padded(img)
+    launches = sp.launch_count()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        ev[s][0].record()
+        out = sp.forward_padded(img)
+        ev[s][1].record()
+    torch.cuda.synchronize(dev)
+    ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        o = sp.forward_padded(host.to(dev, non_blocking=True))
+        o["counts"].cpu(); o["keypoints"].cpu(); o["scores"].cpu()
+    e2e = (time.perf_counter() - t0) / steps
+    one = img[:1]
+    for _ in range(2):
+        sp(one)
+    eb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in eb:
+        a.record()
+        sp(one)
+        b.record()
+    torch.cuda.synchronize(dev)
+    b1_ms = statistics.median(a.elapsed_time(b) for a, b in eb)
+    sp.set_profiling(True)
+    sp.forward_padded(img)
+    prof = sp.get_profile()
+    sp.set_profiling(False)
+    pk = peaks()
+    layers = []
+    for name, t, fl in prof:
+        e = {"launch": name, "ms": round(t, 4)}
+        if fl > 0 and t > 0:
+            e["algorithmic_tflops"] = fl / (t * 1e-3) / 1e12
+            e["frac_of_bf16_peak"] = e["algorithmic_tflops"] / pk["tflops"]
+        layers.append(e)
+    conv_flops = sum(fl for _, _, fl in prof)
+    res = {"workload": f"B={B} grey images {H}x{W}, nms_radius 3, max_keypoints 4096 (extract_features.py:19-24)",
+           "ms_per_batch": ms, "images_per_s": B / (ms * 1e-3), "e2e_images_per_s": B / e2e, "h2d_bytes_per_batch": B * H * W * 4,
+           "b1_forward_ms": b1_ms, "launches_per_batch": launches, "keypoints_per_image": [int(v) for v in out["counts"].cpu()],
+           "algorithmic_gflop_per_image": conv_flops / B / 1e9, "whole_batch_tflops": conv_flops / (ms * 1e-3) / 1e12,
+           "whole_batch_frac_of_bf16_peak": conv_flops / (ms * 1e-3) / 1e12 / pk["tflops"], "launch_profile": layers,
+           "note": "fp32 semantics: every convolution is a 3-pass fp16-split tcgen05 implicit GEMM (frac <= 1/3 by construction)"}
+    if rank == 0:
+        try:
+            from oracle import superpoint_oracle as O
+            torch.set_num_threads(cpu_threads())
+            p = O.params_from_numpy(sd)
+            x = host[:1].numpy()
+            O.forward(p, x, synthetic.SUPERPOINT_CONF)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ref = O.forward(p, x, synthetic.SUPERPOINT_CONF)
+            res["cpu_port_ms_per_image"] = 1e3 * (time.perf_counter() - t0) / 3
+            mine = sp(one)
+            try:
+                d = O.compare_keypoints(mine["keypoints"][0].cpu().numpy(), mine["scores"][0].cpu().numpy(), ref["keypoints"][0].numpy(),
+                                        ref["scores"][0].numpy(), 3e-4, synthetic.SUPERPOINT_CONF["max_keypoints"])
+                same = (mine["keypoints"][0].cpu() == ref["keypoints"][0]).all(1)
+                d["max_abs_ddesc_same_position"] = float((mine["descriptors"][0].cpu() - ref["descriptors"][0])[:, same].abs().max())
+                d["ok"] = True
+            except AssertionError as e:
+                d = {"ok": False, "why": str(e)}
+            d["rule"] = "oracle.compare_keypoints: key points identical, or under top-k identical up to the order / cut membership of scores closer than 3e-4"
+            res["parity_check"] = d
+        except Exception as e:        # noqa: BLE001
+            res["cpu_port_ms_per_image"] = None
+            res["cpu_note"] = f"{type(e).__name__}: {e}"
+    return res
+
+
+def leg_pipeline(dev, synthetic, B=8, H=512, W=512, M=N3D, steps=5):
+    """Image -> pose without leaving the device: SuperPoint -> GATsSPG (padded descriptors + per-frame counts as
+    `lengths`) -> RANSAC-PnP over the matched pairs.  The reference's loop goes through numpy between every pair of stages
+    (inference.py:140-154).  Synthetic images and a random object: the matcher's matches are whatever random weights give
+    (data-independent cost except the PnP inlier counting), so this is a throughput figure, not an accuracy one."""
+    from onepose_b200 import GATsSuperGlue, SuperPoint, pnp
+    N = N2D
+    sp = SuperPoint({"nms_radius": 3, "max_keypoints": N}).eval()
+    sp.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in synthetic.make_superpoint_state_dict(0, 4.0).items()})
+    sp = sp.to(dev)
+    mm = GATsSuperGlue(dict(synthetic.DEFAULT_HPARAMS)).eval()
+    mm.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in synthetic.make_state_dict(0).items()})
+    mm = mm.to(dev)
+    db, leaves = synthetic.make_object(2, M, NLEAF)
+    mm.set_object(torch.from_numpy(db).to(dev), torch.from_numpy(leaves).to(dev), reserve=(B, N))
+    kp3d = torch.randn(M, 3, device=dev, dtype=torch.float64) * 0.1
+    K = torch.tensor([[600.0, 0, W / 2], [0, 600.0, H / 2], [0, 0, 1]], dtype=torch.float64, device=dev).expand(B, 3, 3).contiguous()
+    host = torch.from_numpy(np.stack([synthetic.make_image(200 + i, H, W) for i in range(B)], 0)).pin_memory()
+    frame_id = torch.arange(B, device=dev)[:, None].expand(B, N)
+
+    def step(img):
+        det = sp.forward_padded(img)                                          # [B, 256, N] descriptors + counts, device
+        out = mm.match_frames(det["descriptors"], return_conf=False, lengths=det["counts"])
+        m0 = out["matches0"]
+        valid = m0 > -1
+        order = torch.argsort((~valid).long().flatten() * B + frame_id.flatten(), stable=True)   # valid pairs first, grouped by frame
+        p2 = det["keypoints"].reshape(B * N, 2)[order]
+        p3 = kp3d[m0.clamp(min=0).flatten()[order]]
+        off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), valid.sum(1).cumsum(0)]).to(torch.int32)
+        pose, _, n_in = pnp.ransac_pnp_batch(K, p2, p3, off)
+        return pose, n_in, valid.sum()
+
+    img = host.to(dev)
+    for _ in range(2):
+        step(img)
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for s in range(steps):
+        pose, n_in, nv = step(img)
+        ev[s + 1].record()
+    torch.cuda.synchronize(dev)
+    ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    t0 = time.perf_counter()
+    for s in range(steps):
+        pose, n_in, nv = step(host.to(dev, non_blocking=True))
+        pose.cpu()
+    e2e = (time.perf_counter() - t0) / steps
+    return {"workload": f"B={B} images {H}x{W} -> <= {N} key points -> object with {M} 3D points (L={NLEAF}) -> pose",
+            "ms_per_batch": ms, "frames_per_s": B / (ms * 1e-3), "e2e_frames_per_s": B / e2e, "matched_pairs_per_batch": int(nv),
+            "note": "SuperPoint + matcher (no conf matrix, ragged lengths) + batched RANSAC-PnP, device-resident hand-offs; e2e = pinned "
+                    "host images in, poses out"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -526,6 +707,8 @@ def main():
         for name, fn in (("latency_b1", lambda: leg_latency_b1(model, dev, db, leaves, q_host)),
                          ("config4", lambda: leg_config4(model, dev, synthetic)),
                          ("pnp", lambda: leg_pnp(dev, synthetic) if rank == 0 else None),
+                         ("superpoint", lambda: leg_superpoint(dev, synthetic, rank) if rank == 0 else None),
+                         ("pipeline", lambda: leg_pipeline(dev, synthetic) if rank == 0 else None),
                          ("config5", lambda: leg_config5(model, dev, rank, world, dist))):
             try:
                 extra[name] = fn()

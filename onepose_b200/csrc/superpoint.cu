@@ -36,48 +36,52 @@ constexpr int kSelChunk = 2048;          // pixels per block of the key-point co
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, int H, int W, int ppad, long long rows, const float* __restrict__ w,
                                                  const float* __restrict__ bias, __half* __restrict__ ohi, __half* __restrict__ olo) {
-  __shared__ float sw[64 * 9], sb[64];
   griddep_sync();
-  for (int i = threadIdx.x; i < 64 * 9; i += 256) sw[i] = w[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long row = t >> 3;
-  const int g = (int)(t & 7);
-  if (row >= rows) return;
-  const int b = (int)(row / ppad), q = (int)(row - (long long)b * ppad);
-  const int y = q / (W + 2) - 1, x = q % (W + 2) - 1;          // image coordinates
-  uint4 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
-  if (y >= 0 && y < H && x >= 0 && x < W) {
-    const float* im = img + (long long)b * H * W;
-    float in[9];
+  // thread = (row, channel group g): g is fixed per thread (256 % 8 == 0), so its 8 x 9 weights and 8 biases live in registers
+  // and every thread walks a grid-stride sequence of rows
+  const int g = threadIdx.x & 7;
+  float wr[8][9], br[8];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+  for (int e = 0; e < 8; ++e) {
+    br[e] = __ldg(bias + g * 8 + e);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xx = x + kx - 1;
-        in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (long long)yy * W + xx) : 0.f;
-      }
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = g * 8 + e;
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc = fmaf(sw[c * 9 + k], in[k], acc);
-      v[e] = fmaxf(acc + sb[c], 0.f) * kPre;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 sc = make_float2(v[2 * e], v[2 * e + 1]);
-      const __half2 h2 = __float22half2_rn(sc);
-      const float2 back = __half22float2(h2);
-      reinterpret_cast<__half2*>(&oh)[e] = h2;
-      reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
-    }
+    for (int k = 0; k < 9; ++k) wr[e][k] = __ldg(w + (g * 8 + e) * 9 + k);
   }
-  reinterpret_cast<uint4*>(ohi)[row * 8 + g] = oh;
-  reinterpret_cast<uint4*>(olo)[row * 8 + g] = ol;
+  const long long row_step = (long long)gridDim.x * 32;
+  for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += row_step) {
+    const int b = (int)(row / ppad), q = (int)(row - (long long)b * ppad);
+    const int y = q / (W + 2) - 1, x = q % (W + 2) - 1;          // image coordinates
+    uint4 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const float* im = img + (long long)b * H * W;
+      float in[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xx = x + kx - 1;
+          in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (long long)yy * W + xx) : 0.f;
+        }
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc = fmaf(wr[e][k], in[k], acc);
+        v[e] = fmaxf(acc + br[e], 0.f) * kPre;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 sc = make_float2(v[2 * e], v[2 * e + 1]);
+        const __half2 h2 = __float22half2_rn(sc);
+        const float2 back = __half22float2(h2);
+        reinterpret_cast<__half2*>(&oh)[e] = h2;
+        reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
+      }
+    }
+    reinterpret_cast<uint4*>(ohi)[row * 8 + g] = oh;
+    reinterpret_cast<uint4*>(olo)[row * 8 + g] = ol;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -312,8 +316,9 @@ __global__ void __launch_bounds__(256) sp_compact(const float* __restrict__ nms,
 // #{j : key_j > key_i}; O(n^2) comparisons on at most a few 10^4 candidates.  Key points are (x, y) floats (superpoint.py:177).
 __global__ void __launch_bounds__(256) sp_emit(const int* __restrict__ cand_idx, const float* __restrict__ cand_score, const int* __restrict__ totals, int HW,
                                                int W, int k, int cap, float* __restrict__ kpts, float* __restrict__ kscores, int* __restrict__ counts) {
-  __shared__ float ts[256];
-  __shared__ int ti[256];
+  // key = (score bits, ~pixel index): scores are positive floats (> threshold >= 0 is not required: the sign bit is flipped
+  // into an order-preserving unsigned), so one 64-bit compare orders by (score descending, index ascending)
+  __shared__ unsigned long long tk[1024];
   griddep_sync();
   const int b = blockIdx.y;
   const int total = totals[b];
@@ -326,17 +331,31 @@ __global__ void __launch_bounds__(256) sp_emit(const int* __restrict__ cand_idx,
   const bool live = i < total;
   const float si = live ? cand_score[(long long)b * HW + i] : 0.f;
   const int pi = live ? cand_idx[(long long)b * HW + i] : 0;
+  auto make_key = [](float s, int p) {
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);               // monotone float -> unsigned
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
+  };
   int pos = i;
   if (k >= 0 && total > k) {
+    const unsigned long long ki = make_key(si, pi);
     int rank = 0;
-    for (int j0 = 0; j0 < total; j0 += 256) {
-      const int j = j0 + threadIdx.x;
+    for (int j0 = 0; j0 < total; j0 += 1024) {
       __syncthreads();
-      ts[threadIdx.x] = j < total ? cand_score[(long long)b * HW + j] : -INFINITY;
-      ti[threadIdx.x] = j < total ? cand_idx[(long long)b * HW + j] : 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * 256 + threadIdx.x;
+        tk[u * 256 + threadIdx.x] = j < total ? make_key(cand_score[(long long)b * HW + j], cand_idx[(long long)b * HW + j]) : 0ull;
+      }
       __syncthreads();
-      const int lim = min(256, total - j0);
-      for (int t = 0; t < lim; ++t) rank += (ts[t] > si || (ts[t] == si && ti[t] < pi)) ? 1 : 0;
+      const int lim = min(1024, total - j0);
+      int t = 0;
+      for (; t + 4 <= lim; t += 4) {                               // broadcast reads: two keys per 16-byte load
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&tk[t]);
+        const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(&tk[t + 2]);
+        rank += (a.x > ki) + (a.y > ki) + (c.x > ki) + (c.y > ki);
+      }
+      for (; t < lim; ++t) rank += tk[t] > ki;
     }
     pos = rank;
   }
@@ -686,7 +705,7 @@ int opb_sp_detect(opb_superpoint* h, const float* image, int32_t B, int32_t H, i
     return h->stop_after == idx;
   };
   // ---- shared encoder (superpoint.py:142-152)
-  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, blocks(s0.rows(B) * 8), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, s0.rows(B), (const float*)h->w1a.as<float>(),
+  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, dim3(148 * 16), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, s0.rows(B), (const float*)h->w1a.as<float>(),
           (const float*)h->b1a.as<float>(), A.hi.as<__half>(), A.lo.as<__half>());
   if (stopped(0, 0, 64, s0)) return OPB_OK;
   if (int rc = sp_run_conv(h, h->c1b, A, 64, 0, &Bf, nullptr, 64, s0, B, 1, st, "conv1b")) return rc;
