@@ -78,6 +78,7 @@ SYMBOLS = {
     "opb_sp_set_profiling": (C.c_int, [_P, _I]),
     "opb_sp_get_profile": (C.c_int, [_P, _I, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "opb_sp_debug_set_stop": (C.c_int, [_P, _I]),
+    "opb_debug_set_conv_halo": (C.c_int, [_I]),
     "opb_sp_debug_read": (C.c_int, [_P, _I, _P, C.c_size_t, C.POINTER(C.c_int64), _P]),
 }
 

@@ -180,6 +180,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
+// Same for an operand whose first row is row `r0` (0..7) of a 1024-byte swizzle atom: the start address moves by r0 * 128 bytes
+// and the descriptor's "matrix base offset" field (bits 49-51) carries r0, so that the hardware applies the XOR pattern of the
+// rows' true positions inside the atom.  Used by the halo convolution: one 130-row box serves the three horizontal taps.
+__device__ __forceinline__ uint64_t make_desc_rowoff(uint32_t smem_addr, uint32_t r0, uint32_t base_offset_mode) {
+  uint64_t d = make_desc(smem_addr + r0 * 128u);
+  if (base_offset_mode) d |= (uint64_t)(r0 & 7u) << 49;
+  return d;
+}
 // kind::f16 instruction descriptor (built per column-tile width inside the kernel): D=f32, A=B=f16, both K-major, M = 256 across
 // the CTA pair, N = BN
 
@@ -221,6 +229,7 @@ struct TcParams {
   int taps, kb_per_tap;
   int tap_off[9];
   int cv_w2, cv_h, cv_w, cv_ppad, relu;
+  int halo;              // 3x3 convolution with one (BM + 2)-row A box per (kernel row, 64-channel block): 1 / 2 = base-offset mode
 };
 
 struct Maps {
@@ -228,6 +237,7 @@ struct Maps {
   CUtensorMap out_f32;                                    // store: fp32 [rows, ldc], box 32 x 128 (SWIZZLE_128B)
   CUtensorMap out_hi, out_lo;                             // store: fp16-split planes, box 32 x 128 (SWIZZLE_64B)
   CUtensorMap a_raw;                                      // load: fp32 source of a converted A operand, box 32 x 128 (SWIZZLE_128B)
+                                                          // (halo convolution: a1h / a1l have boxes of BM + 2 rows)
 };
 
 // A-operand conversion: instead of fp16-split planes prepared by a separate kernel, the TMA producer lands the RAW fp32
@@ -255,7 +265,16 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
   static_assert(!HI || ACV == ACV_NONE, "converters need the full stage");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + kStages * kStageBytes;
+  // halo convolution (EPI_CONV, TcParams::halo): a stage = one (kernel row, 64-channel block) group = A_hi / A_lo boxes of BM + 2
+  // rows (the three horizontal taps read it at row offsets 0 / 1 / 2) + the B half-tiles of the three taps
+  constexpr int kHaloRows = BM + 2;
+  constexpr int kHaloABytes = (kHaloRows * 128 + 1023) / 1024 * 1024;         // 17408
+  constexpr int kHaloStageBytes = 2 * kHaloABytes + 6 * kBBytes;
+  constexpr int kHaloStages = (EPI == EPI_CONV && BN_ != 256) ? (BN_ == 64 ? 3 : 2) : 0;
+  constexpr int kRingBytes = kStages * kStageBytes > kHaloStages * kHaloStageBytes ? kStages * kStageBytes : kHaloStages * kHaloStageBytes;
+  static_assert(kRingBytes <= kStagesFull * (2 * kABytes + 2 * (256 / 2) * BK * 2), "ring exceeds the shared-memory budget");
+  const bool halo = EPI == EPI_CONV && kHaloStages > 0 && p.halo != 0;
+  uint8_t* staging = smem + kRingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumStaging * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
@@ -318,6 +337,26 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const int b_row1 = (int)(z * p.b_batch_rows) + n_tile * BN + crank * kBRowsLoad;
         const int seg = p.b2_per_seg ? p.L.seg_of_row(row0) : 0;     // the pair's row tiles share a segment (segments are 256-row aligned)
         const int b_row2 = (p.b2_per_seg ? seg * p.n_out : 0) + n_tile * BN + crank * kBRowsLoad;
+        if (halo) {
+          const int ngroups = 3 * p.kb_per_tap;
+          for (int g = 0; g < ngroups; ++g, ++it) {
+            const int s = it % kHaloStages;
+            mbar_wait(&empty_bar[s], ((it / kHaloStages) & 1) ^ 1);
+            uint8_t* st = smem + s * kHaloStageBytes;
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * (2 * kHaloRows * 128 + 6 * kBBytes));
+            const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
+            const int arow = a_row + (dy - 1) * p.cv_w2 - 1;          // first row of the box: tap (dy, dx = 0); may be < 0 (zero fill)
+            tma_load_2d_2sm(st, &maps.a1h, &full_bar[s], cb * BK, arow);
+            tma_load_2d_2sm(st + kHaloABytes, &maps.a1l, &full_bar[s], cb * BK, arow);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int kcb = ((dy * 3 + dx) * p.kb_per_tap + cb) * BK;
+              tma_load_2d_2sm(st + 2 * kHaloABytes + dx * 2 * kBBytes, &maps.b1h, &full_bar[s], kcb, b_row1);
+              tma_load_2d_2sm(st + 2 * kHaloABytes + dx * 2 * kBBytes + kBBytes, &maps.b1l, &full_bar[s], kcb, b_row1);
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
@@ -362,6 +401,31 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         mbar_wait(&tmem_empty_bar[buf], ((tc >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + buf * BN;
+        if (halo) {
+          const int ngroups = 3 * p.kb_per_tap;
+          for (int g = 0; g < ngroups; ++g, ++it) {
+            const int s = it % kHaloStages;
+            mbar_wait(&full_bar[s], (it / kHaloStages) & 1);
+            tc_fence_after();
+            const uint32_t sa_h = smem_u32(smem + s * kHaloStageBytes), sa_l = sa_h + kHaloABytes;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint32_t sb_h = sa_h + 2 * kHaloABytes + dx * 2 * kBBytes, sb_l = sb_h + kBBytes;
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint32_t koff = k * UMMA_K * 2;
+                const uint64_t ah = make_desc_rowoff(sa_h + koff, dx, p.halo == 1), al = make_desc_rowoff(sa_l + koff, dx, p.halo == 1);
+                const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
+                tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((g | dx | k) != 0));
+                tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
+                tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
+              }
+            }
+            tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);
+          }
+          tc_commit_2sm(&tmem_full_bar[buf], (uint16_t)0x3);
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&full_bar[s], (it / kStages) & 1);
@@ -976,6 +1040,9 @@ bool make_map3(CUtensorMap* out, const float* ptr, int M, int N, int B) {
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_conv_halo = 1;      // 0: nine row-shifted boxes per tile; 1: halo boxes, descriptor base offset = row offset; 2: halo boxes, base offset 0
+int conv_halo_mode() { return g_conv_halo; }
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -1000,6 +1067,8 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const Maps& mp, const 
 
 }  // namespace
 
+void set_conv_halo_mode(int mode) { g_conv_halo = mode; }
+
 bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32) {
   return make_map(out, ptr, rows, cols, ld, box_cols, box_rows, f32);
 }
@@ -1014,6 +1083,11 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.a_hi_only && (p.a_conv || p.K2 || p.epi != EPI_QKV)) return -1;
   if (p.a_conv && (p.a_conv != ACV_NORM_RELU || p.batch != 1 || !p.a_raw || p.epi != EPI_BIAS_PLANES || p.b2_per_seg || !p.mu || !p.rstd)) return -1;
   const bool f32_out = p.epi == EPI_F32 || p.epi == EPI_F32_STATS;
+  // halo convolution: 3x3 taps in row-major order with unit horizontal steps, narrow column tiles (the 256-wide tile has no room
+  // for two halo stages and is not L2-bound)
+  int halo = (p.epi == EPI_CONV && p.taps == 9 && bn != BN) ? conv_halo_mode() : 0;
+  for (int t = 0; t < 9 && halo; ++t)
+    if (p.tap_off[t] != (t / 3 - 1) * p.cv_w2 + (t % 3 - 1)) halo = 0;
   if (p.epi == EPI_QKV && (p.n_out != 2 * BN || p.batch != 1 || !p.out.hi || !p.bias)) return -1;
   if ((p.epi == EPI_QSCALE || p.epi == EPI_L2NORM) && !p.bias) return -1;
   const bool score = p.epi == EPI_SCORE_SUMS || p.epi == EPI_SCORE_CONF;
@@ -1027,7 +1101,8 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (p.a_conv) { mp.a1h = mp.b1h; mp.a1l = mp.b1l; }     // every A1 tile comes in raw: the plane maps are never used
   else {
     const long long a_cols = p.taps ? (long long)p.kb_per_tap * BK : p.K1;      // convolution: A has C_in columns, the taps shift its rows
-    ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, BM, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, BM, false);
+    const int a_box_rows = halo ? BM + 2 : BM;                                   // halo convolution: one box serves the three horizontal taps
+    ok = ok && make_map(&mp.a1h, p.a1.hi, a_rows, a_cols, p.a1.ld, BK, a_box_rows, false) && make_map(&mp.a1l, p.a1.lo, a_rows, a_cols, p.a1.ld, BK, a_box_rows, false);
   }
   if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.K1, p.a_raw_ld, 32, BM, true);
   else mp.a_raw = mp.b1h;
@@ -1059,7 +1134,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / bn; tp.batch = p.batch;
   tp.taps = p.taps; tp.kb_per_tap = p.kb_per_tap;
   for (int t = 0; t < 9; ++t) tp.tap_off[t] = p.tap_off[t];
-  tp.cv_w2 = p.cv_w2; tp.cv_h = p.cv_h; tp.cv_w = p.cv_w; tp.cv_ppad = p.cv_ppad; tp.relu = p.relu;
+  tp.cv_w2 = p.cv_w2; tp.cv_h = p.cv_h; tp.cv_w = p.cv_w; tp.cv_ppad = p.cv_ppad; tp.relu = p.relu; tp.halo = halo;
   tp.a_batch_rows = p.a_batch_rows; tp.b_batch_rows = p.b_batch_rows; tp.c_batch_rows = p.rows;
   tp.seg_rows = (p.batch == 1 && p.L.R > 0 && p.L.rows() == p.rows) ? 1 : 0;
   tp.L = p.L; tp.bias = p.bias; tp.tl = timeline;

@@ -15,4 +15,7 @@ bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long 
 // Programmatic dependent launch switch shared by every launch site (default on; opb_debug_set_pdl).
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
+// 3x3 convolutions on narrow column tiles (EPI_CONV): 1 (default) = halo boxes -- one (BM + 2)-row A box per kernel row serves the three
+// horizontal taps through row-offset UMMA descriptors; 0 = nine row-shifted boxes per tile (A/B switch: opb_debug_set_conv_halo).
+void set_conv_halo_mode(int mode);
 }  // namespace opb

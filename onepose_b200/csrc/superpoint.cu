@@ -801,6 +801,12 @@ int opb_sp_get_profile(opb_superpoint* h, int32_t index, char* name, size_t name
   return OPB_OK;
 }
 
+int opb_debug_set_conv_halo(int32_t mode) {
+  if (mode < 0 || mode > 2) return OPB_E_INVALID;
+  set_conv_halo_mode(mode);
+  return OPB_OK;
+}
+
 int opb_sp_debug_set_stop(opb_superpoint* h, int32_t layer) {
   if (!h) return OPB_E_INVALID;
   h->stop_after = layer;
