@@ -180,14 +180,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// Same for an operand whose first row is row `r0` (0..7) of a 1024-byte swizzle atom: the start address moves by r0 * 128 bytes
-// and the descriptor's "matrix base offset" field (bits 49-51) carries r0, so that the hardware applies the XOR pattern of the
-// rows' true positions inside the atom.  Used by the halo convolution: one 130-row box serves the three horizontal taps.
-__device__ __forceinline__ uint64_t make_desc_rowoff(uint32_t smem_addr, uint32_t r0, uint32_t base_offset_mode) {
-  uint64_t d = make_desc(smem_addr + r0 * 128u);
-  if (base_offset_mode) d |= (uint64_t)(r0 & 7u) << 49;
-  return d;
-}
+// Same for an operand whose first row is row `r0` of the box that was landed at `smem_addr` (1024-byte aligned): the start
+// address simply moves by r0 * 128 bytes.  The swizzle XOR is a function of the ABSOLUTE shared-memory address bits (the
+// hardware un-swizzles exactly what TMA wrote), so a row-offset start needs nothing else -- measured on B200: with the
+// descriptor's "matrix base offset" field (bits 49-51) left at 0 the results are bit-identical to separately loaded boxes,
+// with base offset = r0 they are garbage.  Used by the halo convolution: one 130-row box serves the three horizontal taps.
+__device__ __forceinline__ uint64_t make_desc_rowoff(uint32_t smem_addr, uint32_t r0) { return make_desc(smem_addr + r0 * 128u); }
 // kind::f16 instruction descriptor (built per column-tile width inside the kernel): D=f32, A=B=f16, both K-major, M = 256 across
 // the CTA pair, N = BN
 
@@ -229,7 +227,7 @@ struct TcParams {
   int taps, kb_per_tap;
   int tap_off[9];
   int cv_w2, cv_h, cv_w, cv_ppad, relu;
-  int halo;              // 3x3 convolution with one (BM + 2)-row A box per (kernel row, 64-channel block): 1 / 2 = base-offset mode
+  int halo;              // 3x3 convolution with one (BM + 2)-row A box per (kernel row, 64-channel block)
 };
 
 struct Maps {
@@ -414,7 +412,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint32_t koff = k * UMMA_K * 2;
-                const uint64_t ah = make_desc_rowoff(sa_h + koff, dx, p.halo == 1), al = make_desc_rowoff(sa_l + koff, dx, p.halo == 1);
+                const uint64_t ah = make_desc_rowoff(sa_h + koff, dx), al = make_desc_rowoff(sa_l + koff, dx);
                 const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
                 tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((g | dx | k) != 0));
                 tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
@@ -1040,7 +1038,7 @@ bool make_map3(CUtensorMap* out, const float* ptr, int M, int N, int B) {
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int g_conv_halo = 1;      // 0: nine row-shifted boxes per tile; 1: halo boxes, descriptor base offset = row offset; 2: halo boxes, base offset 0
+int g_conv_halo = 1;      // 0: nine row-shifted boxes per tile; 1: halo boxes (default)
 int conv_halo_mode() { return g_conv_halo; }
 
 int num_sms() {
@@ -1067,7 +1065,7 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const Maps& mp, const 
 
 }  // namespace
 
-void set_conv_halo_mode(int mode) { g_conv_halo = mode; }
+void set_conv_halo_mode(int mode) { g_conv_halo = mode ? 1 : 0; }
 
 bool make_tensor_map_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool f32) {
   return make_map(out, ptr, rows, cols, ld, box_cols, box_rows, f32);

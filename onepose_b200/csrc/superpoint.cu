@@ -37,21 +37,22 @@ constexpr int kSelChunk = 2048;          // pixels per block of the key-point co
 __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, int H, int W, int ppad, long long rows, const float* __restrict__ w,
                                                  const float* __restrict__ bias, __half* __restrict__ ohi, __half* __restrict__ olo) {
   griddep_sync();
-  // thread = (row, channel group g): g is fixed per thread (256 % 8 == 0), so its 8 x 9 weights and 8 biases live in registers
-  // and every thread walks a grid-stride sequence of rows
-  const int g = threadIdx.x & 7;
-  float wr[8][9], br[8];
+  // thread = (row, 4-channel group g): g is fixed per thread (256 % 16 == 0), so its 4 x 9 weights and 4 biases live in registers
+  // and every thread walks a grid-stride sequence of rows (16 lanes = one 128-byte plane row per store instruction)
+  const int g = threadIdx.x & 15;
+  float wr[4][9], br[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    br[e] = __ldg(bias + g * 8 + e);
+  for (int e = 0; e < 4; ++e) {
+    br[e] = __ldg(bias + g * 4 + e);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[e][k] = __ldg(w + (g * 8 + e) * 9 + k);
+    for (int k = 0; k < 9; ++k) wr[e][k] = __ldg(w + (g * 4 + e) * 9 + k);
   }
-  const long long row_step = (long long)gridDim.x * 32;
-  for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += row_step) {
+  const long long row_step = (long long)gridDim.x * 16;
+#pragma unroll 2
+  for (long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); row < rows; row += row_step) {
     const int b = (int)(row / ppad), q = (int)(row - (long long)b * ppad);
     const int y = q / (W + 2) - 1, x = q % (W + 2) - 1;          // image coordinates
-    uint4 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
+    uint2 oh = make_uint2(0, 0), ol = make_uint2(0, 0);
     if (y >= 0 && y < H && x >= 0 && x < W) {
       const float* im = img + (long long)b * H * W;
       float in[9];
@@ -62,16 +63,16 @@ __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, 
           const int yy = y + ky - 1, xx = x + kx - 1;
           in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (long long)yy * W + xx) : 0.f;
         }
-      float v[8];
+      float v[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < 4; ++e) {
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc = fmaf(wr[e][k], in[k], acc);
         v[e] = fmaxf(acc + br[e], 0.f) * kPre;
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 2; ++e) {
         const float2 sc = make_float2(v[2 * e], v[2 * e + 1]);
         const __half2 h2 = __float22half2_rn(sc);
         const float2 back = __half22float2(h2);
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, 
         reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
       }
     }
-    reinterpret_cast<uint4*>(ohi)[row * 8 + g] = oh;
-    reinterpret_cast<uint4*>(olo)[row * 8 + g] = ol;
+    reinterpret_cast<uint2*>(ohi)[row * 16 + g] = oh;
+    reinterpret_cast<uint2*>(olo)[row * 16 + g] = ol;
   }
 }
 
@@ -705,7 +706,7 @@ int opb_sp_detect(opb_superpoint* h, const float* image, int32_t B, int32_t H, i
     return h->stop_after == idx;
   };
   // ---- shared encoder (superpoint.py:142-152)
-  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, dim3(148 * 16), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, s0.rows(B), (const float*)h->w1a.as<float>(),
+  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, dim3(148 * 32), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, s0.rows(B), (const float*)h->w1a.as<float>(),
           (const float*)h->b1a.as<float>(), A.hi.as<__half>(), A.lo.as<__half>());
   if (stopped(0, 0, 64, s0)) return OPB_OK;
   if (int rc = sp_run_conv(h, h->c1b, A, 64, 0, &Bf, nullptr, 64, s0, B, 1, st, "conv1b")) return rc;
@@ -802,7 +803,7 @@ int opb_sp_get_profile(opb_superpoint* h, int32_t index, char* name, size_t name
 }
 
 int opb_debug_set_conv_halo(int32_t mode) {
-  if (mode < 0 || mode > 2) return OPB_E_INVALID;
+  if (mode < 0 || mode > 1) return OPB_E_INVALID;
   set_conv_halo_mode(mode);
   return OPB_OK;
 }

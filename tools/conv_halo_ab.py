@@ -1,6 +1,6 @@
 """A/B of the convolution operand staging (opb_debug_set_conv_halo): correctness of the encoder layers against the oracle and
 time of one SuperPoint batch, one process per mode (a wrong descriptor mode must not take the others down).
-    python tools/conv_halo_ab.py            # runs modes 0, 1, 2 in subprocesses
+    python tools/conv_halo_ab.py            # runs modes 0 (nine boxes) and 1 (halo boxes) in subprocesses
     python tools/conv_halo_ab.py MODE       # one mode"""
 import os
 import subprocess
@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 if len(sys.argv) == 1:
-    for mode in (0, 1, 2):
+    for mode in (0, 1):
         r = subprocess.run([sys.executable, __file__, str(mode)], capture_output=True, text=True, timeout=300)
         print(f"== mode {mode} (rc {r.returncode})\n{r.stdout[-1500:]}{r.stderr[-600:] if r.returncode else ''}", flush=True)
     sys.exit(0)
