@@ -203,7 +203,8 @@ int opb_sp_get_profile(opb_superpoint* h, int32_t index, char* name, size_t name
 int opb_sp_debug_set_stop(opb_superpoint* h, int32_t layer);
 /* 3x3 convolutions on the 64- / 128-wide column tiles: 1 (default) = halo boxes (one (128 + 2)-row A box per kernel row and
  * 64-channel block serves the three horizontal taps through row-offset UMMA descriptors: a third of the L2 -> shared-memory
- * traffic), 0 = nine row-shifted boxes per tile.  Same results bit for bit; A/B switch for tests/ and tools/. */
+ * traffic), 0 = nine row-shifted boxes per tile.  Same operand bytes (bit-identical results with 64 input channels; a different
+ * accumulation order of the same products with 128); A/B switch for tests/ and tools/. */
 int opb_debug_set_conv_halo(int32_t mode);
 int opb_sp_debug_read(opb_superpoint* h, int32_t which, float* out, size_t capacity_elems, int64_t* n_elems, void* stream);
 

@@ -59,7 +59,7 @@ def test_encoder_layers_match_oracle():
         ref = E.to_grid(O.encoder(p, x, upto=i).numpy())
         err = float(np.abs(rows - ref).max())
         errs.append(err)
-        assert err < 2e-5 * max(1.0, float(np.abs(ref).max())), f"encoder step {i} ({O.ENCODER[i]}): max error {err:.3e}, ref max {np.abs(ref).max():.3f}"
+        assert err < 3e-5 * max(1.0, float(np.abs(ref).max())), f"encoder step {i} ({O.ENCODER[i]}): max error {err:.3e}, ref max {np.abs(ref).max():.3f}"
         q = np.arange(B * P) % P
         yy, xx = q // (w + 2), q % (w + 2)
         border = (yy < 1) | (yy > h) | (xx < 1) | (xx > w)
@@ -137,28 +137,38 @@ def test_batch_equals_single_images_and_is_deterministic():
         assert float((both["descriptors"][b].cpu() - ref["descriptors"][b])[:, same].abs().max()) <= DESC_TOL
 
 
-def test_halo_and_nine_box_staging_agree_bitwise():
+def test_halo_and_nine_box_staging_agree():
     """The two ways of staging the A operand of a 3x3 convolution (one 130-row halo box per kernel row vs nine row-shifted boxes)
-    feed the tensor core the same bytes: identical results, bit for bit."""
+    feed the tensor core the same bytes.  With 64 input channels the MMA order is the same too: bit-identical activations; with
+    128 input channels the halo form visits (kernel row, channel block, dx) instead of (tap, channel block), a different
+    accumulation order of the same products: equal to fp32 rounding."""
     from onepose_b200 import _lib
     lib = _lib.load()
     sd = synthetic.make_superpoint_state_dict(1, 4.0)
-    img = torch.from_numpy(np.stack([synthetic.make_image(i, 72, 88) for i in (21, 22)], 0)).cuda()
+    H, W = 72, 88
+    img = torch.from_numpy(np.stack([synthetic.make_image(i, H, W) for i in (21, 22)], 0)).cuda()
     m = _module(sd, {"nms_radius": 3, "max_keypoints": 200})
-    outs = []
+    m.forward_padded(img)
+    acts, outs = [], []
     try:
         for mode in (0, 1):
             assert lib.opb_debug_set_conv_halo(mode) == 0
+            m.debug_stop_after(4)                                  # conv2b: every layer so far has 64 input channels
+            m.forward_padded(img)
+            h, w, P = E.stage(H, W, 1)
+            acts.append(m.debug_read(4, 2 * P * 64).clone())
+            m.debug_stop_after(-1)
             o = m.forward_padded(img)
-            outs.append((o["keypoints"].clone(), o["scores"].clone(), o["descriptors"].clone(), o["counts"].clone()))
+            outs.append({k: v.clone() for k, v in o.items()})
     finally:
         lib.opb_debug_set_conv_halo(1)
-    n = outs[0][3].tolist()
-    assert torch.equal(outs[0][3], outs[1][3])
-    for b in range(2):
-        assert torch.equal(outs[0][0][b, :n[b]], outs[1][0][b, :n[b]])            # key points [B, cap, 2]
-        assert torch.equal(outs[0][1][b, :n[b]], outs[1][1][b, :n[b]])            # scores [B, cap]
-        assert torch.equal(outs[0][2][b, :, :n[b]], outs[1][2][b, :, :n[b]])      # descriptors [B, 256, cap]
+        m.debug_stop_after(-1)
+    assert torch.equal(acts[0], acts[1])
+    assert torch.equal(outs[0]["counts"], outs[1]["counts"])
+    for b, n in enumerate(outs[0]["counts"].tolist()):
+        assert torch.equal(outs[0]["keypoints"][b, :n], outs[1]["keypoints"][b, :n])
+        assert float((outs[0]["scores"][b, :n] - outs[1]["scores"][b, :n]).abs().max()) < 2e-6
+        assert float((outs[0]["descriptors"][b, :, :n] - outs[1]["descriptors"][b, :, :n]).abs().max()) < 2e-6
 
 
 def test_rejects_bad_shapes():

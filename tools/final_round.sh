@@ -15,4 +15,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 85 -c 1
 # matching kernels per step: 69 (79 in the first); take the last ~27 of the third step (and the first of the next): GATs layer 9, self layer 10, cross layer 11, tail
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel|kv_state_h|gats_aggregate|kv_state_reduce|in_stats_final" -s 190 -c 30 -o gpurun_out/${tag}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_ncu_full.log 2>&1; tail -2 gpurun_out/${tag}_ncu_full.log
 timeout 900 python tools/damping_sweep.py --out gpurun_out/${tag}_damping_sweep.json > gpurun_out/${tag}_damping_sweep.log 2>&1; tail -12 gpurun_out/${tag}_damping_sweep.log
+# SuperPoint: launch list of one batch and ncu --set full of its 20 launches (second batch of sp_bench.py --once)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_superpoint_launches_ncu.csv python tools/sp_bench.py --once > gpurun_out/${tag}_sp_ncu_list.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -s 20 -c 20 -o gpurun_out/${tag}_superpoint_full python tools/sp_bench.py --once > gpurun_out/${tag}_sp_ncu_full.log 2>&1; tail -2 gpurun_out/${tag}_sp_ncu_full.log
 ls -la gpurun_out | tail -12
