@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
   constexpr int kRingBytes = kStages * kStageBytes > kHaloStages * kHaloStageBytes ? kStages * kStageBytes : kHaloStages * kHaloStageBytes;
   static_assert(kRingBytes <= kStagesFull * (2 * kABytes + 2 * (256 / 2) * BK * 2), "ring exceeds the shared-memory budget");
   const bool halo = EPI == EPI_CONV && kHaloStages > 0 && p.halo != 0;
+  // Split accumulators (narrow tiles only: a 256-column buffer holds 256 / BN accumulators).  The fp32 TMEM accumulator is
+  // TRUNCATED on every MMA, a bias toward zero that grows with the number of accumulate steps at full magnitude.  The two
+  // correction passes (A_hi.B_lo, A_lo.B_hi: 2^-11 of the main term) get an accumulator of their own, and with 64-wide tiles the
+  // main term is further split by kernel row; the epilogue adds the partial sums in registers with round-to-nearest.
+  constexpr bool kSplitAcc = BN_ != 256;
+  constexpr int kBufCols = kSplitAcc ? 256 : BN;                 // TMEM columns per accumulator buffer
+  constexpr int kMainAcc = BN_ == 64 ? 3 : 1;                    // accumulators of the A_hi.B_hi term (3: one per kernel row of a 3x3 convolution)
+  // accumulator slots of a buffer: 0 = main[0], 1 = corrections, 2.. = main[1..] (written by 3x3 convolutions only)
+  const int n_main = (kMainAcc > 1 && EPI == EPI_CONV && p.taps == 9) ? kMainAcc : 1;
+  constexpr int kHaloStagesDiv = kHaloStages ? kHaloStages : 1;  // (modulus of the halo ring; never used when there is none)
   uint8_t* staging = smem + kRingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kNumStaging * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
@@ -338,8 +348,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         if (halo) {
           const int ngroups = 3 * p.kb_per_tap;
           for (int g = 0; g < ngroups; ++g, ++it) {
-            const int s = it % kHaloStages;
-            mbar_wait(&empty_bar[s], ((it / kHaloStages) & 1) ^ 1);
+            const int s = it % kHaloStagesDiv;
+            mbar_wait(&empty_bar[s], ((it / kHaloStagesDiv) & 1) ^ 1);
             uint8_t* st = smem + s * kHaloStageBytes;
             if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * (2 * kHaloRows * 128 + 6 * kBBytes));
             const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
@@ -398,14 +408,25 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
         const uint32_t buf = tc & 1;
         mbar_wait(&tmem_empty_bar[buf], ((tc >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d = tmem_base + buf * BN;
+        const uint32_t d = tmem_base + buf * kBufCols;
+        uint32_t started = 0;                                       // split accumulators already written in this tile
+        auto acc_of = [&](int a, uint32_t& flag) {                   // TMEM address of split accumulator a; flag = accumulate?
+          flag = (started >> a) & 1u;
+          started |= 1u << a;
+          return d + (uint32_t)(a * BN);
+        };
         if (halo) {
           const int ngroups = 3 * p.kb_per_tap;
           for (int g = 0; g < ngroups; ++g, ++it) {
-            const int s = it % kHaloStages;
-            mbar_wait(&full_bar[s], (it / kHaloStages) & 1);
+            const int s = it % kHaloStagesDiv;
+            mbar_wait(&full_bar[s], (it / kHaloStagesDiv) & 1);
             tc_fence_after();
             const uint32_t sa_h = smem_u32(smem + s * kHaloStageBytes), sa_l = sa_h + kHaloABytes;
+            const int am = (g / p.kb_per_tap) % n_main;             // kernel row -> main accumulator
+            uint32_t fm, fc;
+            const uint32_t dm = acc_of(am ? am + 1 : 0, fm), dc = acc_of(1, fc);
+            // (issuing the group's main term first and the corrections afterwards, or keeping a single main accumulator, measured
+            // the same time: tools/conv_halo_ab.py)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
               const uint32_t sb_h = sa_h + 2 * kHaloABytes + dx * 2 * kBBytes, sb_l = sb_h + kBBytes;
@@ -414,9 +435,9 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
                 const uint32_t koff = k * UMMA_K * 2;
                 const uint64_t ah = make_desc_rowoff(sa_h + koff, dx), al = make_desc_rowoff(sa_l + koff, dx);
                 const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
-                tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((g | dx | k) != 0));
-                tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
-                tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
+                tc_mma_f16_2sm(dm, ah, bh, kIdesc2, (dx | k) ? 1u : fm);
+                tc_mma_f16_2sm(dc, ah, bl, kIdesc2, (dx | k) ? 1u : fc);
+                tc_mma_f16_2sm(dc, al, bh, kIdesc2, 1u);
               }
             }
             tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);
@@ -437,6 +458,16 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
             const uint64_t ah = make_desc(sa_h + koff), al = make_desc(sa_l + koff);
             const uint64_t bh = make_desc(sb_h + koff), bl = make_desc(sb_l + koff);
+            if (kSplitAcc) {                                        // narrow tiles: never HI / skip_lo (launch_gemm_tc)
+              uint32_t fm, fc;
+              const int dy = (EPI == EPI_CONV && p.taps == 9) ? kb / (3 * p.kb_per_tap) : 0;
+              const int am = dy % n_main;
+              const uint32_t dm = acc_of(am ? am + 1 : 0, fm), dc = acc_of(1, fc);
+              tc_mma_f16_2sm(dm, ah, bh, kIdesc2, fm);
+              tc_mma_f16_2sm(dc, ah, bl, kIdesc2, fc);
+              tc_mma_f16_2sm(dc, al, bh, kIdesc2, 1u);
+              continue;
+            }
             tc_mma_f16_2sm(d, ah, bh, kIdesc2, (uint32_t)((kb | k) != 0));
             if (!skip_lo) tc_mma_f16_2sm(d, ah, bl, kIdesc2, 1u);
             if (!HI) tc_mma_f16_2sm(d, al, bh, kIdesc2, 1u);
@@ -559,7 +590,23 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
       mbar_wait(&tmem_full_bar[buf], (tc >> 1) & 1);
       if (tl && threadIdx.x == 128 && tc < 8) tl[40 + 2 * tc] = clock64();
       tc_fence_after();
-      const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t lane_base = tmem_base + buf * kBufCols + ((uint32_t)(q * 32) << 16);
+      // 32 accumulator columns starting at c: one tcgen05.ld, or (split accumulators) the round-to-nearest sum of the partials
+      auto load_acc = [&](int c, uint32_t (&v)[32]) {
+        tmem_ld32(lane_base + c, v);
+        tmem_ld_wait();
+        if (kSplitAcc) {
+#pragma unroll
+          for (int a = 1; a <= kMainAcc; ++a) {
+            if (a > n_main) break;
+            uint32_t t[32];
+            tmem_ld32(lane_base + a * BN + c, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
+          }
+        }
+      };
       const int out_row0 = z * p.c_batch_rows + m_tile * BM;
       const int row0 = m_tile * BM;                               // within the batch
       int n_valid = BM;                                           // valid rows of this tile (segment-aware launches)
@@ -573,8 +620,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
-          tmem_ld32(lane_base + c0, v);
-          tmem_ld_wait();
+          load_acc(c0, v);
           const int col0 = n_tile * BN + c0;
           uint8_t* sb = staging + stage_sel(chunk_ctr) * kStagingBytes;
           stage_wait();                             // the store that last read this buffer is done with it
@@ -779,8 +825,7 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk_ctr) {
           uint32_t v[32];
-          tmem_ld32(lane_base + c0, v);
-          tmem_ld_wait();
+          load_acc(c0, v);
           const int col0 = n_tile * BN + c0;
           uint8_t* sh = staging + stage_sel(chunk_ctr) * 8192;
           uint8_t* sl = staging + kStagingBytes + stage_sel(chunk_ctr) * 8192;

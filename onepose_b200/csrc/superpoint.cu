@@ -677,9 +677,10 @@ int opb_sp_finalize_weights(opb_superpoint* h) {
   if (int rc = sp_pack(h, h->c4a, {"conv4a"}, 128, {128}, 3, 128, 128)) return rc;
   if (int rc = sp_pack(h, h->c4b, {"conv4b"}, 128, {128}, 3, 128, 128)) return rc;
   // the two heads' 3x3 layers read the same tensor: ONE GEMM with 512 output channels [convPa | convDa]
-  if (int rc = sp_pack(h, h->cPD, {"convPa", "convDa"}, 128, {256, 256}, 3, 512, 256)) return rc;
+  // (128-wide column tiles although C_out = 512 / 256: the narrow tiles keep the correction passes in their own accumulator)
+  if (int rc = sp_pack(h, h->cPD, {"convPa", "convDa"}, 128, {256, 256}, 3, 512, 128)) return rc;
   if (int rc = sp_pack(h, h->cPb, {"convPb"}, 256, {65}, 1, 128, 128)) return rc;
-  if (int rc = sp_pack(h, h->cDb, {"convDb"}, 256, {256}, 1, 256, 256)) return rc;
+  if (int rc = sp_pack(h, h->cDb, {"convDb"}, 256, {256}, 1, 256, 128)) return rc;
   SCK(h, cudaDeviceSynchronize());
   h->ready = true;
   return OPB_OK;

@@ -1,10 +1,12 @@
 """SuperPoint extractor on the GPU (run with -m gpu on a B200): the CUDA path through the module / C ABI against the golden
 vectors of the reference module and against the CPU oracle, layer by layer and end to end.  Bars: key points (indices) bit-
-exact, scores within 5e-5 abs, descriptors within 1e-5 abs.  The network is fp32 in the reference; the device computes fp32
-semantics with the 3-pass fp16-split tensor-core product, whose fp32 accumulator TRUNCATES (toward zero): about -2e-6 relative
-per layer, with the same sign in every layer, so through the 12 layers it adds up to ~1e-4 relative on the logits (the
-reference's own fp32 forward sits 1e-6 from an fp64 run).  The shrink is nearly uniform and softmax / L2 normalisation cancel a
-uniform part: scores end up within 2e-5, descriptors within 2e-6, and key points stay bit-identical -- except that under top-k
+exact, scores within 2e-5 abs, descriptors within 1e-5 abs.  The network is fp32 in the reference; the device computes fp32
+semantics with the 3-pass fp16-split tensor-core product, whose fp32 accumulator TRUNCATES (toward zero) on every MMA: a bias
+with the same sign in every layer.  With one accumulator per tile it added up to 7e-5 on O(3) activations after eleven layers;
+the narrow convolution tiles now keep the correction passes (and, at 64 channels, each kernel row) in accumulators of their
+own and add the partial sums in registers: 2e-5 after eleven layers (the first GEMM layer sits at 1.7e-6, the distance of the
+reference's own fp32 forward from an fp64 run), logits within 1e-4 of values up to 15.  Softmax / L2 normalisation cancel the
+uniform part of the shrink: scores within 6e-6, descriptors within 2e-6, key points bit-identical -- except that under top-k
 the ORDER of candidates whose scores differ by less than that noise may swap (oracle.compare_keypoints states the rule)."""
 import numpy as np
 import pytest
@@ -17,7 +19,7 @@ from tests.golden_util import SUPERPOINT_CASES, load_superpoint_case
 
 pytestmark = pytest.mark.gpu
 
-SCORE_TOL = 5e-5         # measured: <= 2e-5 on every fixture
+SCORE_TOL = 2e-5         # measured: <= 6.3e-6 on every fixture
 DESC_TOL = 1e-5          # measured: ~2e-6
 
 
@@ -59,7 +61,7 @@ def test_encoder_layers_match_oracle():
         ref = E.to_grid(O.encoder(p, x, upto=i).numpy())
         err = float(np.abs(rows - ref).max())
         errs.append(err)
-        assert err < 3e-5 * max(1.0, float(np.abs(ref).max())), f"encoder step {i} ({O.ENCODER[i]}): max error {err:.3e}, ref max {np.abs(ref).max():.3f}"
+        assert err < 1e-5 * max(1.0, float(np.abs(ref).max())), f"encoder step {i} ({O.ENCODER[i]}): max error {err:.3e}, ref max {np.abs(ref).max():.3f}"
         q = np.arange(B * P) % P
         yy, xx = q // (w + 2), q % (w + 2)
         border = (yy < 1) | (yy > h) | (xx < 1) | (xx > w)
@@ -80,10 +82,10 @@ def test_heads_scores_and_nms_match_oracle():
     h3, w3, P3 = E.stage(H, W, 3)
     logits = m.debug_read(2, B * P3 * 128).cpu().numpy().reshape(B * P3, 128)[:, :65]
     ref = O._conv(p, "convPb", O._conv(p, "convPa", feat), relu=False).numpy()
-    assert np.abs(E.from_grid(logits, B, 65, h3, w3) - ref).max() < 1e-4 * np.abs(ref).max()
+    assert np.abs(E.from_grid(logits, B, 65, h3, w3) - ref).max() < 2e-5 * np.abs(ref).max()
     dd = m.debug_read(3, B * P3 * 256).cpu().numpy().reshape(B * P3, 256)
     refd = O._conv(p, "convDb", O._conv(p, "convDa", feat), relu=False).numpy()
-    assert np.abs(E.from_grid(dd, B, 256, h3, w3) - refd).max() < 1e-4 * np.abs(refd).max()
+    assert np.abs(E.from_grid(dd, B, 256, h3, w3) - refd).max() < 2e-5 * np.abs(refd).max()
     sc_ref = O.dense_scores(p, feat)
     sc = m.debug_read(0, B * H * W).cpu().reshape(B, H, W)
     assert float((sc - sc_ref).abs().max()) < SCORE_TOL

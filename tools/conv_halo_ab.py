@@ -44,6 +44,16 @@ for i in (1, 3, 4, 6, 7, 9, 10):
     errs.append(float(np.abs(rows - E.to_grid(O.encoder(p, x, upto=i).numpy())).max()))
 sp.debug_stop_after(-1)
 print("encoder errors (conv1b 2a 2b 3a 3b 4a 4b):", " ".join(f"{e:.1e}" for e in errs))
+sp.forward_padded(x.cuda())
+feat = O.encoder(p, x)
+h3, w3, P3 = E.stage(H, W, 3)
+lg = sp.debug_read(2, B * P3 * 128).cpu().numpy().reshape(B * P3, 128)[:, :65]
+dd = sp.debug_read(3, B * P3 * 256).cpu().numpy().reshape(B * P3, 256)
+sc = sp.debug_read(0, B * H * W).cpu().reshape(B, H, W)
+print("logits err %.2e  dense-descriptor err %.2e  dense-score err %.2e" % (
+    np.abs(E.from_grid(lg, B, 65, h3, w3) - O._conv(p, "convPb", O._conv(p, "convPa", feat), relu=False).numpy()).max(),
+    np.abs(E.from_grid(dd, B, 256, h3, w3) - O._conv(p, "convDb", O._conv(p, "convDa", feat), relu=False).numpy()).max(),
+    float((sc - O.dense_scores(p, feat)).abs().max())))
 img = torch.from_numpy(np.stack([synthetic.make_image(100 + i, 512, 512) for i in range(8)], 0)).cuda()
 for _ in range(3):
     sp.forward_padded(img)
