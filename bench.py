@@ -527,8 +527,36 @@ def leg_pipeline(dev, synthetic, B=8, H=512, W=512, M=N3D, steps=5):
         pose, n_in, nv = step(host.to(dev, non_blocking=True))
         pose.cpu()
     e2e = (time.perf_counter() - t0) / steps
+    # the reference's own loop, statement by statement, with the three drop-ins (inference.py:132-154): one image per iteration,
+    # detections through numpy, pack_data re-uploading the per-object tensors, matches back to numpy, PnP on numpy arrays
+    d3h, d2h = torch.from_numpy(db), torch.from_numpy(leaves)
+    kp3h = kp3d.float().cpu()
+    Kh = K[0].cpu().numpy()
+
+    def reference_loop(n):
+        for f in range(n):
+            inp = host[f % B][None].to(dev)
+            pred_detection = {k: v[0].cpu().numpy() for k, v in sp(inp).items()}                       # :137-138
+            data = {"keypoints2d": torch.Tensor(pred_detection["keypoints"])[None].to(dev), "keypoints3d": kp3h[None].to(dev),
+                    "descriptors2d_query": torch.Tensor(pred_detection["descriptors"])[None].to(dev),
+                    "descriptors3d_db": d3h[None].to(dev), "descriptors2d_db": d2h[None].to(dev)}             # pack_data :80-94
+            pred, _ = mm(data)                                                                                # :146
+            matches = pred["matches0"].detach().cpu().numpy()
+            valid = matches > -1
+            mk2, mk3 = pred_detection["keypoints"][valid], kp3h.numpy()[matches[valid]]
+            pnp.ransac_PnP(Kh, mk2, mk3, scale=1000)                                                          # :154
+
+    reference_loop(3)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    reference_loop(16)
+    torch.cuda.synchronize(dev)
+    loop_ms = 1e3 * (time.perf_counter() - t0) / 16
     return {"workload": f"B={B} images {H}x{W} -> <= {N} key points -> object with {M} 3D points (L={NLEAF}) -> pose",
             "ms_per_batch": ms, "frames_per_s": B / (ms * 1e-3), "e2e_frames_per_s": B / e2e, "matched_pairs_per_batch": int(nv),
+            "inference_py_loop_ms_per_frame": loop_ms,
+            "inference_py_loop_note": "inference.py:132-154 as written (B=1, detections and matches through numpy, the 57 MB of per-object "
+                                      "tensors re-uploaded by pack_data every frame) with the three drop-in modules; wall clock",
             "note": "SuperPoint + matcher (no conf matrix, ragged lengths) + batched RANSAC-PnP, device-resident hand-offs; e2e = pinned "
                     "host images in, poses out"}
 
