@@ -108,7 +108,7 @@ def test_dustbin_object_exact_ties():
 
 # ----------------------------------------------------------------------------- oracle on seeded inputs
 @pytest.mark.parametrize("B,N,M,L,damped", [(3, 300, 700, 8, True), (1, 129, 257, 5, True), (2, 17, 40, 8, False),
-                                            (5, 256, 384, 8, True), (2, 203, 333, 8, True)])
+                                            (5, 256, 384, 8, True), (2, 203, 333, 8, True), (1, 64, 100, 1, True), (2, 90, 150, 12, True)])
 def test_oracle_parity_batched(B, N, M, L, damped):
     hp = dict(synthetic.DEFAULT_HPARAMS)
     sd = synthetic.make_state_dict(4, damped=damped)
