@@ -34,11 +34,12 @@ constexpr int kSelChunk = 2048;          // pixels per block of the key-point co
 // conv1a: 1 -> 64 channels, 3x3, ReLU (superpoint.py:111,142).  K = 9 is no tensor-core shape: thread = (pixel row, 8 output
 // channels); writes the zero-bordered planes of the first GEMM layer.  img fp32 [B, H, W].
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, int H, int W, int ppad, long long rows, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, int H, int W, int ppad, const float* __restrict__ w,
                                                  const float* __restrict__ bias, __half* __restrict__ ohi, __half* __restrict__ olo) {
   griddep_sync();
-  // thread = (row, 4-channel group g): g is fixed per thread (256 % 16 == 0), so its 4 x 9 weights and 4 biases live in registers
-  // and every thread walks a grid-stride sequence of rows (16 lanes = one 128-byte plane row per store instruction)
+  // grid (chunks of 256 grid pixels, image); thread = (pixel, 4-channel group g): g is fixed per thread (256 % 16 == 0), so its
+  // 4 x 9 weights and 4 biases live in registers; 16 lanes = one 128-byte plane row per store instruction.  All index math is
+  // 32-bit (a 64-bit division per pixel made the first version of this kernel instruction-bound).
   const int g = threadIdx.x & 15;
   float wr[4][9], br[4];
 #pragma unroll
@@ -47,21 +48,25 @@ __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, 
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[e][k] = __ldg(w + (g * 4 + e) * 9 + k);
   }
-  const long long row_step = (long long)gridDim.x * 16;
-#pragma unroll 2
-  for (long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); row < rows; row += row_step) {
-    const int b = (int)(row / ppad), q = (int)(row - (long long)b * ppad);
-    const int y = q / (W + 2) - 1, x = q % (W + 2) - 1;          // image coordinates
+  const int b = blockIdx.y;
+  const float* im = img + (size_t)b * H * W;
+  const unsigned w2 = (unsigned)(W + 2);
+  const size_t row_base = (size_t)b * ppad;
+#pragma unroll 4
+  for (int it = 0; it < 16; ++it) {
+    const unsigned q = blockIdx.x * 256u + it * 16u + (threadIdx.x >> 4);
+    if (q >= (unsigned)ppad) break;
+    const unsigned yq = q / w2;
+    const int y = (int)yq - 1, x = (int)(q - yq * w2) - 1;       // image coordinates
     uint2 oh = make_uint2(0, 0), ol = make_uint2(0, 0);
     if (y >= 0 && y < H && x >= 0 && x < W) {
-      const float* im = img + (long long)b * H * W;
       float in[9];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int yy = y + ky - 1, xx = x + kx - 1;
-          in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (long long)yy * W + xx) : 0.f;
+          in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + yy * W + xx) : 0.f;
         }
       float v[4];
 #pragma unroll
@@ -80,8 +85,8 @@ __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, 
         reinterpret_cast<__half2*>(&ol)[e] = __float22half2_rn(make_float2(sc.x - back.x, sc.y - back.y));
       }
     }
-    reinterpret_cast<uint2*>(ohi)[row * 16 + g] = oh;
-    reinterpret_cast<uint2*>(olo)[row * 16 + g] = ol;
+    reinterpret_cast<uint2*>(ohi)[(row_base + q) * 16 + g] = oh;
+    reinterpret_cast<uint2*>(olo)[(row_base + q) * 16 + g] = ol;
   }
 }
 
@@ -155,23 +160,29 @@ __global__ void __launch_bounds__(256) sp_scores(const float* __restrict__ logit
 // Positions outside the image do not exist for torch's max_pool2d (implicit -inf padding): -inf scores / zero mask here.
 // Separable running maximum over shrinking valid regions; shared memory: 6 float planes of (32 + 10 r)^2.
 // ------------------------------------------------------------------------------------------------------------------
+// Work distribution inside the tile: one warp per row of the region, lanes over columns -- no integer divisions (the first
+// version indexed a flattened range with / and % per element and was instruction-bound).
+#define SP_FOR_REGION(lo_, hi_, ...)                                                           \
+  for (int y = (lo_) + (int)(threadIdx.x >> 5); y < (hi_); y += (int)(blockDim.x >> 5))          \
+    for (int x = (lo_) + (int)(threadIdx.x & 31); x < (hi_); x += 32) { __VA_ARGS__ }
+
 __device__ __forceinline__ void pool_sep(const float* in, float* tmp, float* out, int D, int margin, int r) {
   // out = max over the (2r+1)^2 window of `in`, valid on [margin + r, D - margin - r)^2 given `in` valid on [margin, D - margin)^2
   const int lo = margin, hi = D - margin;
-  const int nx = hi - lo - 2 * r, ny = hi - lo;
-  for (int i = threadIdx.x; i < nx * ny; i += blockDim.x) {
-    const int y = lo + i / nx, x = lo + r + i % nx;
-    float m = in[y * D + x - r];
-    for (int d = -r + 1; d <= r; ++d) m = fmaxf(m, in[y * D + x + d]);
-    tmp[y * D + x] = m;
-  }
+  for (int y = lo + (int)(threadIdx.x >> 5); y < hi; y += (int)(blockDim.x >> 5))
+    for (int x = lo + r + (int)(threadIdx.x & 31); x < hi - r; x += 32) {
+      const float* p = in + y * D + x;
+      float m = p[-r];
+      for (int d = -r + 1; d <= r; ++d) m = fmaxf(m, p[d]);
+      tmp[y * D + x] = m;
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
-    const int y = lo + r + i / nx, x = lo + r + i % nx;
-    float m = tmp[(y - r) * D + x];
-    for (int d = -r + 1; d <= r; ++d) m = fmaxf(m, tmp[(y + d) * D + x]);
+  SP_FOR_REGION(lo + r, hi - r, {
+    const float* p = tmp + y * D + x;
+    float m = p[-r * D];
+    for (int d = -r + 1; d <= r; ++d) m = fmaxf(m, p[d * D]);
     out[y * D + x] = m;
-  }
+  })
   __syncthreads();
 }
 
@@ -187,55 +198,46 @@ __global__ void __launch_bounds__(512) sp_nms(const float* __restrict__ scores, 
   griddep_sync();
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kNmsTile - halo, x0 = blockIdx.x * kNmsTile - halo;
-  const float* src = scores + (long long)b * H * W;
-  for (int i = threadIdx.x; i < DD; i += blockDim.x) {
-    const int y = y0 + i / D, x = x0 + i % D;
-    S[i] = (y >= 0 && y < H && x >= 0 && x < W) ? src[(long long)y * W + x] : -INFINITY;
-    Mk[i] = 0.f;
-  }
+  const float* src = scores + (size_t)b * H * W;
+  SP_FOR_REGION(0, D, {
+    const int gy = y0 + y, gx = x0 + x;
+    S[y * D + x] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? src[gy * W + gx] : -INFINITY;
+    Mk[y * D + x] = 0.f;
+  })
   __syncthreads();
   pool_sep(S, T, P, D, 0, r);                                   // valid on margin r
   int margin = r;
-  {
-    const int n = D - 2 * margin;
-    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-      const int k = (margin + i / n) * D + margin + i % n;
-      Mk[k] = (S[k] == P[k] && S[k] != -INFINITY) ? 1.f : 0.f;  // max_mask = scores == max_pool(scores)
-    }
-  }
+  SP_FOR_REGION(margin, D - margin, {
+    const int k = y * D + x;
+    Mk[k] = (S[k] == P[k] && S[k] != -INFINITY) ? 1.f : 0.f;    // max_mask = scores == max_pool(scores)
+  })
   __syncthreads();
   for (int it = 0; it < 2; ++it) {
     pool_sep(Mk, T, Sup, D, margin, r);                         // supp_mask = max_pool(max_mask.float()) > 0
     margin += r;
-    {
-      const int n = D - 2 * margin;
-      for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-        const int k = (margin + i / n) * D + margin + i % n;
-        SS[k] = S[k] == -INFINITY ? -INFINITY : (Sup[k] > 0.f ? 0.f : S[k]);   // supp_scores = where(supp_mask, 0, scores)
-      }
-    }
+    SP_FOR_REGION(margin, D - margin, {
+      const int k = y * D + x;
+      SS[k] = S[k] == -INFINITY ? -INFINITY : (Sup[k] > 0.f ? 0.f : S[k]);     // supp_scores = where(supp_mask, 0, scores)
+    })
     __syncthreads();
     pool_sep(SS, T, P, D, margin, r);
     margin += r;
-    {
-      const int n = D - 2 * margin;
-      for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-        const int k = (margin + i / n) * D + margin + i % n;
-        if (!(Sup[k] > 0.f) && SS[k] == P[k] && S[k] != -INFINITY) Mk[k] = 1.f;   // max_mask |= new_max_mask & ~supp_mask
-      }
-    }
+    SP_FOR_REGION(margin, D - margin, {
+      const int k = y * D + x;
+      if (!(Sup[k] > 0.f) && SS[k] == P[k] && S[k] != -INFINITY) Mk[k] = 1.f;   // max_mask |= new_max_mask & ~supp_mask
+    })
     __syncthreads();
   }
-  float* dst = out + (long long)b * H * W;
-  for (int i = threadIdx.x; i < kNmsTile * kNmsTile; i += blockDim.x) {
-    const int ty = i / kNmsTile, tx = i % kNmsTile;
-    const int y = blockIdx.y * kNmsTile + ty, x = blockIdx.x * kNmsTile + tx;
-    if (y < H && x < W) {
-      const int k = (halo + ty) * D + halo + tx;
-      dst[(long long)y * W + x] = Mk[k] == 1.f ? S[k] : 0.f;    // torch.where(max_mask, scores, zeros)
+  float* dst = out + (size_t)b * H * W;
+  SP_FOR_REGION(halo, halo + kNmsTile, {
+    const int gy = y0 + y, gx = x0 + x;
+    if (gy < H && gx < W) {
+      const int k = y * D + x;
+      dst[gy * W + gx] = Mk[k] == 1.f ? S[k] : 0.f;             // torch.where(max_mask, scores, zeros)
     }
-  }
+  })
 }
+#undef SP_FOR_REGION
 
 // ------------------------------------------------------------------------------------------------------------------
 // Key-point selection (superpoint.py:163-174): pixels with nms score > threshold, inside the border margin, in row-major
@@ -707,7 +709,7 @@ int opb_sp_detect(opb_superpoint* h, const float* image, int32_t B, int32_t H, i
     return h->stop_after == idx;
   };
   // ---- shared encoder (superpoint.py:142-152)
-  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, dim3(148 * 32), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, s0.rows(B), (const float*)h->w1a.as<float>(),
+  SLAUNCH(h, st, "sp_conv1a", sp_conv1a, dim3((s0.ppad + 255) / 256, B), dim3(256), 0, st, image, (int)H, (int)W, s0.ppad, (const float*)h->w1a.as<float>(),
           (const float*)h->b1a.as<float>(), A.hi.as<__half>(), A.lo.as<__half>());
   if (stopped(0, 0, 64, s0)) return OPB_OK;
   if (int rc = sp_run_conv(h, h->c1b, A, 64, 0, &Bf, nullptr, 64, s0, B, 1, st, "conv1b")) return rc;

@@ -35,6 +35,7 @@ for r in data:
         "dram_pct": get(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "sm_pct": get(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
         "regs": get(r, "launch__registers_per_thread"),
+        "l2_to_sm_read_MB": (get(r, "l1tex__m_xbar2l1tex_read_bytes.sum", "MB")),
     })
 json.dump({"capture": desc, "launches": launches}, open(out, "w"), indent=1)
 print(f"{len(launches)} launches -> {out}")
