@@ -61,13 +61,21 @@ __global__ void __launch_bounds__(256) sp_conv1a(const float* __restrict__ img, 
     uint2 oh = make_uint2(0, 0), ol = make_uint2(0, 0);
     if (y >= 0 && y < H && x >= 0 && x < W) {
       float in[9];
+      if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) {           // interior (99 % of the pixels): nine unconditional loads
+        const float* c = im + (y - 1) * W + (x - 1);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int yy = y + ky - 1, xx = x + kx - 1;
-          in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + yy * W + xx) : 0.f;
-        }
+          for (int kx = 0; kx < 3; ++kx) in[ky * 3 + kx] = __ldg(c + ky * W + kx);
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = y + ky - 1, xx = x + kx - 1;
+            in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + yy * W + xx) : 0.f;
+          }
+      }
       float v[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
