@@ -726,7 +726,7 @@ def main():
     traffic = None
     if os.path.exists(ncu_path):                     # DRAM bytes of one full-chunk launch of that variant from the committed ncu --set full capture
         for k in json.load(open(ncu_path)).get("launches", []):
-            if "gemm_tc_kernel<1, 0>" in k["kernel"] and k.get("dram_read_MB") is not None:
+            if "gemm_tc_kernel<1, 0" in k["kernel"] and k.get("dram_read_MB") is not None:
                 traffic = (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
 
     # ---------------- extra legs (bounded; a failure is reported, not fatal) ----------------
