@@ -173,6 +173,26 @@ def test_halo_and_nine_box_staging_agree():
         assert float((outs[0]["descriptors"][b, :, :n] - outs[1]["descriptors"][b, :, :n]).abs().max()) < 2e-6
 
 
+def test_no_keypoints_and_constant_image():
+    """Edge cases of the selection: nothing above the threshold -> empty tensors of the reference's shapes; a constant image ->
+    the interior cells produce exactly tied scores (a plateau per channel position), which the reference's NMS keeps."""
+    sd = synthetic.make_superpoint_state_dict(0, 4.0)
+    p = O.params_from_numpy(sd)
+    img = synthetic.make_image(1, 64, 64)[None]
+    m = _module(sd, {"keypoint_threshold": 2.0})
+    out = m(torch.from_numpy(img).cuda())
+    assert tuple(out["keypoints"][0].shape) == (0, 2) and tuple(out["scores"][0].shape) == (0,) and tuple(out["descriptors"][0].shape) == (256, 0)
+    conf = {"nms_radius": 3, "max_keypoints": -1, "remove_borders": 4}
+    flat = np.full((2, 1, 64, 80), 0.5, np.float32)
+    flat[1] = 0.25
+    ref = O.forward(p, flat, conf)
+    out = _module(sd, conf)(torch.from_numpy(flat).cuda())
+    for b in range(2):
+        _compare_keypoints({"keypoints": out["keypoints"][b], "scores": out["scores"][b]}, ref["keypoints"][b].numpy(), ref["scores"][b].numpy(),
+                           f"constant[{b}]")
+        assert float((out["descriptors"][b].cpu() - ref["descriptors"][b]).abs().max()) <= DESC_TOL
+
+
 def test_rejects_bad_shapes():
     m = _module(synthetic.make_superpoint_state_dict(0), {})
     with pytest.raises(Exception, match="multiples of 8"):
