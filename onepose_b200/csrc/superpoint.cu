@@ -461,7 +461,8 @@ struct opb_superpoint {
   // workspace
   int ws_B = 0, ws_H = 0, ws_W = 0;
   PlaneBuf arena[2];               // ping-pong activations
-  DevBuf logits, ddesc, scores, nms, cand_idx, cand_score, blk_counts, totals, counts_int;
+  DevBuf logits, ddesc, scores, nms, cand_idx, cand_score, blk_counts, totals;
+  int find_code = 0;               // status of the last failed weight look-up (missing: OPB_E_STATE, wrong size: OPB_E_INVALID)
   int last_B = 0, last_H = 0, last_W = 0;
   int launches = 0;
   int stop_after = -1;             // test hook: leave the encoder after layer i (opb_sp_debug_set_stop)
@@ -518,9 +519,9 @@ void sp_mark(opb_superpoint* h, cudaStream_t st, const char* name, double flops)
 
 const std::vector<float>* sp_find(opb_superpoint* h, const std::string& key, size_t n) {
   auto it = h->host_w.find(key);
-  if (it == h->host_w.end()) { sfail(h, OPB_E_STATE, "missing weight '%s'", key.c_str()); return nullptr; }
+  if (it == h->host_w.end()) { h->find_code = sfail(h, OPB_E_STATE, "missing weight '%s'", key.c_str()); return nullptr; }
   if (it->second.size() != n) {
-    sfail(h, OPB_E_INVALID, "weight '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), n);
+    h->find_code = sfail(h, OPB_E_INVALID, "weight '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), n);
     return nullptr;
   }
   return &it->second;
@@ -552,7 +553,7 @@ int sp_pack(opb_superpoint* h, SpConv& L, const std::vector<std::string>& names,
     const int cout = couts[li];
     const auto* ww = sp_find(h, names[li] + ".weight", (size_t)cout * cin * taps);
     const auto* bb = sp_find(h, names[li] + ".bias", (size_t)cout);
-    if (!ww || !bb) return OPB_E_STATE;
+    if (!ww || !bb) return h->find_code;
     for (int n = 0; n < cout; ++n) {
       for (int c = 0; c < cin; ++c)
         for (int t = 0; t < taps; ++t) w[(size_t)(row0 + n) * K + (size_t)t * cin + c] = (*ww)[((size_t)n * cin + c) * taps + t];
@@ -592,7 +593,6 @@ int sp_ensure_workspace(opb_superpoint* h, int B, int H, int W) {
   SCK(h, h->cand_score.ensure(Bc * HW * sizeof(float)));
   SCK(h, h->blk_counts.ensure((size_t)Bc * ((HW + kSelChunk - 1) / kSelChunk) * sizeof(int)));
   SCK(h, h->totals.ensure((size_t)Bc * sizeof(int)));
-  SCK(h, h->counts_int.ensure((size_t)Bc * sizeof(int)));
   SCK(h, cudaDeviceSynchronize());
   h->ws_B = Bc; h->ws_H = H; h->ws_W = W;
   return 0;
@@ -658,7 +658,7 @@ void opb_sp_destroy(opb_superpoint* h) {
   for (SpConv* L : {&h->c1b, &h->c2a, &h->c2b, &h->c3a, &h->c3b, &h->c4a, &h->c4b, &h->cPD, &h->cPb, &h->cDb}) { L->w.release(); L->b.release(); }
   h->w1a.release(); h->b1a.release();
   h->arena[0].release(); h->arena[1].release();
-  for (DevBuf* d : {&h->logits, &h->ddesc, &h->scores, &h->nms, &h->cand_idx, &h->cand_score, &h->blk_counts, &h->totals, &h->counts_int}) d->release();
+  for (DevBuf* d : {&h->logits, &h->ddesc, &h->scores, &h->nms, &h->cand_idx, &h->cand_score, &h->blk_counts, &h->totals}) d->release();
   for (auto e : h->ev) cudaEventDestroy(e);
   delete h;
 }
@@ -676,7 +676,7 @@ int opb_sp_finalize_weights(opb_superpoint* h) {
   if (!h) return OPB_E_INVALID;
   const auto* w1 = sp_find(h, "conv1a.weight", 64 * 9);
   const auto* b1 = sp_find(h, "conv1a.bias", 64);
-  if (!w1 || !b1) return OPB_E_STATE;
+  if (!w1 || !b1) return h->find_code;
   if (int rc = sp_upload_f32(h, h->w1a, *w1)) return rc;
   if (int rc = sp_upload_f32(h, h->b1a, *b1)) return rc;
   if (int rc = sp_pack(h, h->c1b, {"conv1b"}, 64, {64}, 3, 64, 64)) return rc;
