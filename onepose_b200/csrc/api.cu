@@ -69,6 +69,7 @@ struct opb_matcher {
   int chunk_frames = 0;   // user override
   int ws_frames = 0, ws_N = 0;
   bool hoist = true;      // evaluate the frame-invariant layers once per object (object_prologue)
+  int identity_diag = 1;  // residual identity K-block as N = 64 MMAs on the diagonal blocks (opb_debug_set_identity_diag)
   int kv_two_pass = 1;    // k,v projection as A_hi.(B_hi + B_lo): its output is one fp16 plane, the A_lo term is below that rounding
   PlaneBuf x, qp, pn, g, xq, bd, lin_a, lin_b;
   DevBuf kvt;             // fp16 [rows, 512]
@@ -306,7 +307,7 @@ static int run_attn_layer(opb_matcher* m, const Layout& L, XView x, AttnLayerW& 
   p3.L = L; p3.batch = 1; p3.rows = rows;
   p3.K1 = 512; p3.b1 = W.w1.c(512); p3.n_out = 256; p3.bias = W.b1.as<float>();
   p3.epi = EPI_BIAS_PLANES; p3.out = x.m(kD);
-  p3.a2 = x.c(kD); p3.K2 = kD; p3.b2 = m->eye.c(kD); p3.b2_lo_zero = 1;
+  p3.a2 = x.c(kD); p3.K2 = kD; p3.b2 = m->eye.c(kD); p3.b2_lo_zero = 1; p3.b2_identity = m->identity_diag;
   p3.a_conv = 1; p3.a_raw = m->hid.as<float>(); p3.a_raw_ld = 512; p3.mu = m->mu.as<float>(); p3.rstd = m->rstd.as<float>();
   return run_gemm(m, p3, st, 2.0 * valid_rows * 256 * 512, "mlp3");
 }
@@ -842,6 +843,13 @@ int opb_debug_set_kv_passes(opb_matcher* m, int32_t passes) {
   return OPB_OK;
 }
 
+int opb_debug_set_identity_diag(opb_matcher* m, int32_t enable) {
+  if (!m) return OPB_E_INVALID;
+  m->identity_diag = enable ? 1 : 0;
+  m->prologue_ready = false;
+  return OPB_OK;
+}
+
 int opb_debug_set_ws_fill(int32_t byte) {
   g_ws_fill = byte < 0 ? -1 : (byte & 0xFF);
   return OPB_OK;
@@ -884,7 +892,7 @@ int opb_debug_gemm_aconv(const float* a_raw, const void* b_hi, const void* b_lo,
   p.L.B = 1; p.L.N = rows; p.L.M = 0; p.L.n_pad = rows; p.L.m_pad = 0; p.L.R = rows;
   p.epi = EPI_BIAS_PLANES; p.out = Planes{(__half*)x_hi, (__half*)x_lo, kD};
   p.a2 = CPlanes{(const __half*)x_hi, (const __half*)x_lo, kD}; p.K2 = kD; p.b2 = CPlanes{(const __half*)eye_hi, (const __half*)eye_lo, kD};
-  p.b2_lo_zero = 1;
+  p.b2_lo_zero = 1; p.b2_identity = 1;
   p.a_conv = 1; p.a_raw = a_raw; p.a_raw_ld = 512; p.mu = mu; p.rstd = rstd;
   int rc = launch_gemm_tc(p, (cudaStream_t)stream, timeline);
   return rc == 0 ? OPB_OK : (rc == -1 ? OPB_E_INVALID : OPB_E_CUDA);

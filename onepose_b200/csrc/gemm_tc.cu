@@ -198,6 +198,7 @@ struct TcParams {
   int K1, K2;            // reduction split (multiples of BK)
   int b2_per_seg;
   int b2_lo_zero;        // skip the A_hi . B_lo pass of the K2 block (identity K-block: B_lo == 0)
+  int b2_identity;       // K2 block = identity: diagonal 64 x 64 blocks as N = 64 MMAs (GemmProblem::b2_identity)
   int n_out;
   int m_tiles, n_tiles, batch;
   long long a_batch_rows, b_batch_rows;
@@ -256,6 +257,8 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
   constexpr int kBBytes = (BN / 2) * BK * 2;
   constexpr int kStageBytesFull = 2 * kABytes + 2 * kBBytes;
   constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+  constexpr uint32_t kIdesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // N = 64 (identity K-block)
+  constexpr int kDiagBBytes = 32 * BK * 2;         // this CTA's half (32 rows) of a 64 x 64 diagonal block of the identity
   static_assert(BN_ == 256 || (BN_ == 64 || BN_ == 128) && ACV == ACV_NONE && !HI && (EPI == EPI_CONV || EPI == EPI_F32), "narrow tiles: conv / fp32 epilogues only");
   constexpr int kStages = (HI || BN_ != 256) ? 4 : kStagesFull;
   constexpr int kStageBytes = HI ? kABytes + 2 * kBBytes : kStageBytesFull;
@@ -371,8 +374,9 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           uint8_t* st = smem + s * kStageBytes;
           const bool first = kb < nkb1;
           const bool conv = ACV == ACV_NORM_RELU && first;           // this k-block's A tile comes in raw
+          const bool diag = BN_ == 256 && !first && p.b2_identity;     // identity K-block: B = one 64 x 64 diagonal block, hi plane only
           if (crank == 0)                                               // leader arms for both CTAs' loads
-            mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : 2 * kStageBytes);
+            mbar_expect_tx(&full_bar[s], conv ? 4 * kBBytes : (diag ? 2 * (2 * kABytes + kDiagBBytes) : 2 * kStageBytes));
           int kc = (first ? kb * BK : (kb - nkb1) * BK);
           int arow = a_row, kcb = kc;                                   // A rows / B columns of this k-block
           if (EPI == EPI_CONV && p.taps) {                              // implicit-GEMM convolution: tap t = row-shifted A, B columns follow kb
@@ -394,6 +398,10 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           } else {
             tma_load_2d_2sm(st, mah, &full_bar[s], kc, arow);
             if (!HI) tma_load_2d_2sm(st + kABytes, mal, &full_bar[s], kc, arow);
+          }
+          if (diag) {                                                   // rows [kc + 32 crank, +32) x columns [kc, kc + 64) of I (box: 32 rows)
+            tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kc, kc + crank * 32);
+            continue;
           }
           tma_load_2d_2sm(st + kBOff, mbh, &full_bar[s], kcb, brow);
           tma_load_2d_2sm(st + kBOff + kBBytes, mbl, &full_bar[s], kcb, brow);
@@ -453,6 +461,20 @@ __global__ void __launch_bounds__(threads_of(ACV), 1) gemm_tc_kernel(const __gri
           const uint32_t sa_h = smem_u32(smem + s * kStageBytes);
           const uint32_t sa_l = sa_h + kABytes, sb_h = sa_h + kBOff, sb_l = sb_h + kBBytes;
           const bool skip_lo = p.b2_lo_zero && kb >= nkb1;          // B_lo == 0: the A_hi.B_lo pass adds exact zeros
+          if (BN_ == 256 && kb >= nkb1 && p.b2_identity) {
+            // identity K-block j: only output columns [64 j, 64 j + 64) receive anything -> N = 64 MMAs on that slice of the
+            // accumulator (the other 192 columns of a full-width MMA would add exact zeros)
+            const uint32_t dj = d + (uint32_t)(kb - nkb1) * 64u;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 2;
+              const uint64_t bh = make_desc(sb_h + koff);
+              tc_mma_f16_2sm(dj, make_desc(sa_h + koff), bh, kIdesc64, 1u);
+              tc_mma_f16_2sm(dj, make_desc(sa_l + koff), bh, kIdesc64, 1u);
+            }
+            tc_commit_2sm(&empty_bar[s], (uint16_t)0x3);
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the swizzle row
@@ -1150,7 +1172,7 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (ok && p.a_conv) ok = make_map(&mp.a_raw, p.a_raw, a_rows, p.K1, p.a_raw_ld, 32, BM, true);
   else mp.a_raw = mp.b1h;
   if (ok && p.K2) {
-    ok = make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, BN / 2, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / 2, false) &&
+    ok = make_map(&mp.b2h, p.b2.hi, b2_rows, p.K2, p.b2.ld, BK, p.b2_identity ? 32 : BN / 2, false) && make_map(&mp.b2l, p.b2.lo, b2_rows, p.K2, p.b2.ld, BK, BN / 2, false) &&
          make_map(&mp.a2h, p.a2.hi, a_rows, p.K2, p.a2.ld, BK, BM, false) && make_map(&mp.a2l, p.a2.lo, a_rows, p.K2, p.a2.ld, BK, BM, false);
   } else if (ok) {
     mp.a2h = mp.a1h; mp.a2l = mp.a1l; mp.b2h = mp.b1h; mp.b2l = mp.b1l;
@@ -1174,6 +1196,8 @@ int launch_gemm_tc(const GemmProblem& p, cudaStream_t stream, long long* timelin
   if (!ok) return -2;
   TcParams tp{};
   tp.K1 = p.K1; tp.K2 = p.K2; tp.b2_per_seg = p.b2_per_seg; tp.b2_lo_zero = p.b2_lo_zero; tp.n_out = p.n_out;
+  tp.b2_identity = p.b2_identity;
+  if (p.b2_identity && (!p.b2_lo_zero || p.b2_per_seg || p.K2 != p.n_out || p.n_out != BN || p.K1 <= 0 || bn != BN)) return -1;
   tp.m_tiles = p.rows / BM; tp.n_tiles = p.n_out / bn; tp.batch = p.batch;
   tp.taps = p.taps; tp.kb_per_tap = p.kb_per_tap;
   for (int t = 0; t < 9; ++t) tp.tap_off[t] = p.tap_off[t];
