@@ -77,6 +77,19 @@ class _GnnParams(nn.Module):
             [_GATsParams(dim) if i % 3 == 0 else _PropagationParams(dim) for i in range(len(GNN_LAYERS))])
 
 
+def _out_view(out, name, shape, dtype, dev):
+    """A result tensor of `shape`: a view of the caller's flat buffer out[name] if given, else a fresh allocation."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if out is not None and name in out:
+        t = out[name]
+        if t.dtype != dtype or t.device != dev or t.numel() < n or not t.is_contiguous():
+            raise ValueError(f"out['{name}'] must be a contiguous {dtype} buffer on {dev} with at least {n} elements")
+        return t.view(-1)[:n].view(shape)
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
 class GATsSuperGlue(nn.Module):
     def __init__(self, hparams):
         super().__init__()
@@ -176,21 +189,28 @@ class GATsSuperGlue(nn.Module):
         if self._handle is None or self._M is None:
             raise RuntimeError("no object set: call set_object(descriptors3d_db, descriptors2d_db) first (or use forward(data))")
 
-    def match_frames(self, descriptors2d_query: torch.Tensor, return_conf: bool = True, lengths: torch.Tensor | None = None):
+    def match_frames(self, descriptors2d_query: torch.Tensor, return_conf: bool = True, lengths: torch.Tensor | None = None,
+                     out: dict | None = None):
         """B frames of the current object.  descriptors2d_query [B, 256, N] CUDA fp32; lengths (optional) CUDA int32 [B] =
         valid query points per frame (ragged batch: SuperPoint yields a different count per frame).
         Returns dict of batched tensors (matches0 [B,N] int64, ..., conf_matrix [B,N,M] or None).  Asynchronous: no host
-        synchronisation; a range violation (see check_range) turns the call's matches into -1."""
+        synchronisation; a range violation (see check_range) turns the call's matches into -1.
+        out (optional): flat CUDA buffers {"matches0", "matches1": int64, "matching_scores0", "matching_scores1", "conf_matrix":
+        fp32} at least as large as the results; the returned tensors are views of them (a serving loop allocates once)."""
         self._require_object()
         q = descriptors2d_query.float().contiguous()
         B, _, N = q.shape
         M = self._M
         dev = q.device
-        m0 = torch.empty(B, N, dtype=torch.int64, device=dev)
-        m1 = torch.empty(B, M, dtype=torch.int64, device=dev)
-        s0 = torch.empty(B, N, dtype=torch.float32, device=dev)
-        s1 = torch.empty(B, M, dtype=torch.float32, device=dev)
-        conf = torch.empty(B, N, M, dtype=torch.float32, device=dev) if return_conf else None
+
+        def buf(name, shape, dtype):
+            return _out_view(out, name, shape, dtype, dev)
+
+        m0 = buf("matches0", (B, N), torch.int64)
+        m1 = buf("matches1", (B, M), torch.int64)
+        s0 = buf("matching_scores0", (B, N), torch.float32)
+        s1 = buf("matching_scores1", (B, M), torch.float32)
+        conf = buf("conf_matrix", (B, N, M), torch.float32) if return_conf else None
         if lengths is not None:
             lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
             if lengths.numel() != B:

@@ -124,3 +124,21 @@ def test_features3d_module_mirrors_reference_names():
     assert list(inspect.signature(features3d.mean_scores).parameters)[:2] == ["scores", "idxs"]
     with pytest.raises(RuntimeError, match="no CPU path"):
         features3d.pad_features3d_random(np.ones((4, 3), np.float32), np.ones((3, 1), np.float32), 5, device="cpu")
+
+
+def test_caller_supplied_result_buffers_are_viewed_not_copied():
+    """match_frames(out=...): results land in views of the caller's flat buffers (a serving loop allocates once)."""
+    from onepose_b200.matcher import _out_view
+    dev = torch.device("cpu")
+    pool = {"matches0": torch.zeros(100, dtype=torch.int64), "conf_matrix": torch.zeros(1000)}
+    v = _out_view(pool, "matches0", (3, 20), torch.int64, dev)
+    assert tuple(v.shape) == (3, 20) and v.data_ptr() == pool["matches0"].data_ptr() and v.is_contiguous()
+    c = _out_view(pool, "conf_matrix", (2, 10, 30), torch.float32, dev)
+    assert tuple(c.shape) == (2, 10, 30) and c.data_ptr() == pool["conf_matrix"].data_ptr()
+    fresh = _out_view(pool, "matches1", (2, 5), torch.int64, dev)             # not in the pool: allocated
+    assert tuple(fresh.shape) == (2, 5)
+    assert tuple(_out_view(None, "matches0", (4, 4), torch.int64, dev).shape) == (4, 4)
+    with pytest.raises(ValueError):
+        _out_view(pool, "conf_matrix", (2, 10, 60), torch.float32, dev)         # too small
+    with pytest.raises(ValueError):
+        _out_view(pool, "matches0", (3, 20), torch.float32, dev)                # wrong dtype
