@@ -109,7 +109,7 @@ def test_pixel_grid_convolution_is_nine_shifted_gemms(small):
     assert np.abs(E.from_grid(logits.astype(np.float32), B, 65, h3, w3) - ref).max() < 2e-4
 
 
-@pytest.mark.parametrize("r", [1, 3, 4])
+@pytest.mark.parametrize("r", [0, 1, 3, 4, 6])
 def test_tiled_nms_equals_simple_nms(small, r):
     sd, p, x, H, W = small
     sc = O.dense_scores(p, O.encoder(p, x))
