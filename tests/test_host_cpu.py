@@ -142,3 +142,21 @@ def test_caller_supplied_result_buffers_are_viewed_not_copied():
         _out_view(pool, "conf_matrix", (2, 10, 60), torch.float32, dev)         # too small
     with pytest.raises(ValueError):
         _out_view(pool, "matches0", (3, 20), torch.float32, dev)                # wrong dtype
+
+
+def test_plain_c_client_links_and_runs(tmp_path):
+    """The boundary is a C ABI: a C99 program (tests/c_abi/client.c) compiles against the header alone, links the in-tree library and
+    gets status codes + messages, no exceptions (here, without a GPU: OPB_E_CUDA from both constructors)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    libdir = os.path.join(ROOT, "onepose_b200")
+    exe = tmp_path / "client"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi", "client.c"),
+                        "-L", libdir, "-l:libonepose_b200.so", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "opb_create ->" in r.stdout and "opb_sp_create ->" in r.stdout
